@@ -1,0 +1,147 @@
+/*
+ * kdpc.h — C ABI of libkdpc.so, the B200 (sm_100a) point-cloud op library.
+ *
+ * This is the drop-in boundary for the hot path of yunminjin2/KD-PointCloud:
+ * every entry point replaces one native launcher of the reference's
+ * `pointnet2_cuda` extension (pointnet2/src/*_gpu.h, bound in
+ * pointnet2/src/pointnet2_api.cpp:10-24) or one torch op chain of
+ * pointconv_util.py that the reference runs as many small library kernels.
+ *
+ * Conventions (same as the reference's launchers, sampling_gpu.h:12-27):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer;
+ *   - the CALLER allocates every output and workspace (pointnet2_utils.py:25-26,
+ *     55,94-95,128,172); kernels never allocate;
+ *   - work is enqueued on `stream`; nothing synchronises;
+ *   - return value: 0 on success, a positive cudaError_t on a launch failure,
+ *     a negative KDPC_E* code for a rejected argument.  (The reference prints to
+ *     stderr and calls exit(-1), sampling_gpu.cu:248-252; we return instead.)
+ *   - "cm" tensors are channel-major  [B, C, N]  (the pointnet2 layout);
+ *     "pm" tensors are point-major    [B, N, C]  (what pointconv_util.py permutes to
+ *     before every op, e.g. pointconv_util.py:118,130).
+ */
+#ifndef KDPC_H_
+#define KDPC_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *kdpc_stream_t;
+
+#define KDPC_OK            0
+#define KDPC_EINVAL       -1   /* null pointer / non-positive size                    */
+#define KDPC_EUNSUPPORTED -2   /* size outside what the kernels are instantiated for  */
+
+#define KDPC_ABI_VERSION 1
+int kdpc_abi_version(void);
+const char *kdpc_error_string(int code);
+
+/* ---- pointnet2 ops (channel-major API of pointnet2/pointnet2_utils.py) ----------------- */
+
+/* furthest_point_sampling_kernel_launcher, sampling_gpu.h:26-27 / sampling_gpu.cu:93-253.
+ * xyz [B,N,3] -> idx int32 [B,M], idx[:,0] = 0.  temp [B,N] may be NULL; when given it
+ * receives the final min-distance field exactly as the reference leaves it. Bit-exact
+ * incl. the reference's block-size dependent tie rule. */
+int kdpc_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, kdpc_stream_t stream);
+
+/* gather_points_kernel_launcher_fast, sampling_gpu.h:12-13.  f [B,C,N], idx [B,M] -> out [B,C,M] */
+int kdpc_gather(int b, int c, int n, int m, const float *f, const int *idx, float *out, kdpc_stream_t stream);
+/* gather_points_grad_kernel_launcher_fast, sampling_gpu.h:19-20. grad_f [B,C,N] is OVERWRITTEN
+ * (no pre-zeroing needed) and the sum order is fixed (ascending j) => deterministic, unlike the
+ * reference's atomicAdd.  ws: B*(N+1+M)*4 bytes (inverse index, see kdpc_build_csr). */
+int kdpc_gather_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, void *ws,
+                     float *grad_f, kdpc_stream_t stream);
+
+/* group_points_kernel_launcher_fast, group_points_gpu.h.  f [B,C,N], idx [B,S,K] -> out [B,C,S,K] */
+int kdpc_group(int b, int c, int n, int s, int k, const float *f, const int *idx, float *out, kdpc_stream_t stream);
+/* group_points_grad_kernel_launcher_fast. grad_f [B,C,N] overwritten, deterministic.
+ * ws: B*(N+1+S*K)*4 bytes. */
+int kdpc_group_grad(int b, int c, int n, int s, int k, const float *grad_out, const int *idx, void *ws,
+                    float *grad_f, kdpc_stream_t stream);
+
+/* three_nn_kernel_launcher_fast, interpolate_gpu.h. unknown [B,N,3], known [B,M,3] ->
+ * dist2 [B,N,3] (SQUARED, ascending), idx int32 [B,N,3]; ties keep the lower index.
+ * ws: workspace of B*M*16 bytes. */
+int kdpc_three_nn(int b, int n, int m, const float *unknown, const float *known, void *ws,
+                  float *dist2, int *idx, kdpc_stream_t stream);
+/* three_interpolate_kernel_launcher_fast. f [B,C,M], idx/w [B,N,3] -> out [B,C,N] */
+int kdpc_three_interpolate(int b, int c, int m, int n, const float *f, const int *idx, const float *w,
+                           float *out, kdpc_stream_t stream);
+/* three_interpolate_grad_kernel_launcher_fast (n interpolated points, m source points, as in
+ * interpolate_gpu.h). grad_f [B,C,M] overwritten, deterministic.  ws: B*(M+1+3N)*4 bytes. */
+int kdpc_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                const float *w, void *ws, float *grad_f, kdpc_stream_t stream);
+/* ball_query_kernel_launcher_fast, ball_query_gpu.h. idx [B,M,nsample] fully written. */
+int kdpc_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                    const float *xyz, int *idx, kdpc_stream_t stream);
+
+/* ---- pointconv_util ops (point-major) ------------------------------------------------ */
+
+/* square_distance, pointconv_util.py:73-94: out[b,i,j] = rn(rn(-2*dot + |src_i|^2) + |dst_j|^2) */
+int kdpc_square_distance(int b, int s, int n, const float *src, const float *dst, float *out, kdpc_stream_t stream);
+
+/* knn_point, pointconv_util.py:96-107, without materialising the [B,S,N] matrix.
+ * query [B,S,3], cand [B,N,3] -> the k candidates with smallest square_distance, ordered
+ * ascending by (distance, index).  idx32 / idx64 / dist may each be NULL.  ws: B*N*16 bytes.
+ * k <= 32. */
+int kdpc_knn(int b, int s, int n, int k, const float *query, const float *cand, void *ws,
+             int *idx32, long long *idx64, float *dist, kdpc_stream_t stream);
+
+/* index_points_gather, pointconv_util.py:109-120 (pm): out[b,j,:] = f[b,idx[b,j],:]; f [B,N,C].
+ * With m = S*K this is also index_points_group (pointconv_util.py:122-133) producing
+ * [B,S,K,C] directly (the reference returns a permuted view of [B,C,S,K]). */
+int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const int *idx, float *out, kdpc_stream_t stream);
+
+/* group / group_query, pointconv_util.py:135-182, fused: out[b,s,k,:] =
+ * [cand_xyz[idx]-query_xyz[s] (3), feats[idx] (D)].  feats may be NULL (d = 0). */
+int kdpc_group_concat(int b, int n, int s, int k, int d, const float *cand_xyz, const float *query_xyz,
+                      const float *feats, const int *idx, float *out, kdpc_stream_t stream);
+
+/* WeightNet, pointconv_util.py:184-215 with hidden_unit=[h1,h2], bn=False: per row
+ * relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3).  x = in + row*in_stride (3 floats);
+ * out [rows, wout].  Weights are the nn.Conv2d 1x1 weights flattened row-major [out,in]. */
+int kdpc_weightnet(long long rows, const float *in, int in_stride, int h1, int h2, int wout,
+                   const float *w1, const float *b1, const float *w2, const float *b2,
+                   const float *w3, const float *b3, float *out, kdpc_stream_t stream);
+
+/* PointConv aggregation, pointconv_util.py:249 / :437: out[r, c*wout + w] =
+ * sum_k grouped[r,k,c] * wn[r,k,w].  grouped [R,K,C], wn [R,K,wout] -> out [R, C*wout]. */
+int kdpc_pointconv_agg(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
+                       float *out, kdpc_stream_t stream);
+
+/* CrossLayerLight.cross front half, pointconv_util.py:1836-1843:
+ * out[b,s,k,:] = act(p2[b,idx[b,s,k],:] + p1[b,s,:] + pos_w (xyz2[idx]-xyz1[s]) + pos_b),
+ * act = LeakyReLU(slope) (slope = 0 gives ReLU).  p1 [B,S,D], p2 [B,N,D], pos_w [D,3]. */
+int kdpc_costvol_pre(int b, int s, int n, int k, int d, const float *xyz1, const float *xyz2,
+                     const float *p1, const float *p2, const int *idx, const float *pos_w,
+                     const float *pos_b, float slope, float *out, kdpc_stream_t stream);
+
+/* max over the K axis: in [R,K,D] -> out [R,D], argmax int32 [R,D] (may be NULL). F.max_pool2d at
+ * pointconv_util.py:1848. */
+int kdpc_max_over_k(long long rows, int k, int d, const float *in, float *out, int *arg, kdpc_stream_t stream);
+
+/* UpsampleFlow / PointWarping inverse-distance interpolation, pointconv_util.py:2131-2139,
+ * 2164-2171: w_j = (1/max(|cand[idx_j]-q|,1e-10)) / sum_j(...);  out[b,i,:] = sum_j w_j feat[b,idx_j,:].
+ * q_xyz [B,N,3], c_xyz [B,S,3], idx [B,N,3], feat [B,S,C] -> out [B,N,C]; w_out [B,N,3] may be NULL. */
+int kdpc_interp3(int b, int n, int s, int c, const float *q_xyz, const float *c_xyz, const int *idx,
+                 const float *feat, float *out, float *w_out, kdpc_stream_t stream);
+
+/* ---- deterministic backward plumbing ------------------------------------------------- */
+
+/* Inverse of an index list: idx int32 [B,M] with values in [0,N)  ->  offsets int32 [B,N+1] and
+ * perm int32 [B,M] such that perm[b, offsets[b,i] .. offsets[b,i+1]) lists, ASCENDING, the j with
+ * idx[b,j] == i.  Replaces the float atomicAdd of sampling_gpu.cu:62, group_points_gpu.cu:24,
+ * interpolate_gpu.cu:139-141 by a fixed-order segmented reduction. */
+int kdpc_build_csr(int b, int n, int m, const int *idx, int *offsets, int *perm, kdpc_stream_t stream);
+
+/* grad_f[b,i,:] (=|+=) sum_{p in seg(i)} wgt[b,perm[p]] * g[b, perm[p]/gdiv, :]   (point-major,
+ * g [B, M/gdiv, C], wgt [B,M] or NULL).  gdiv = 1: backward of gather_rows / grouping;
+ * gdiv = 3 with wgt: backward of interp3 w.r.t. feat. */
+int kdpc_scatter_rows_csr(int b, int n, int m, int c, int gdiv, const float *g, const float *wgt,
+                          const int *offsets, const int *perm, float *grad_f, int accumulate,
+                          kdpc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDPC_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of libkdpc.so (the C ABI declared in include/kdpc.h) and its build recipe.
+
+The library is built IN-TREE next to this file (``build()``), so the ``.so`` travels with the
+repository snapshot.  There is no CPU implementation behind this module: if the library is
+missing, or a tensor is not on a CUDA device, the ops raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libkdpc.so")
+SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
+           "scatter.cu", "loss.cu", "pointconv_fused.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "kdpc.h")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every kernel for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: argtypes (restype is int unless noted)
+    "kdpc_fps": [c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_gather": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_gather_grad": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
+    "kdpc_group": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_group_grad": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
+    "kdpc_three_nn": [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
+    "kdpc_three_interpolate": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
+    "kdpc_three_interpolate_grad": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
+    "kdpc_ball_query": [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],
+    "kdpc_square_distance": [c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_knn": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_gather_rows": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_group_concat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
+    "kdpc_weightnet": [c_longlong, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_pointconv_agg": [c_longlong, c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_costvol_pre": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
+    "kdpc_max_over_k": [c_longlong, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_interp3": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
+}
+
+_lib = None
+
+
+class KdpcError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load libkdpc.so (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KdpcError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU or PyTorch fallback for the kdpc ops.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.kdpc_abi_version.restype = c_int
+        L.kdpc_error_string.restype = c_char_p
+        L.kdpc_error_string.argtypes = [c_int]
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return ["kdpc_abi_version", "kdpc_error_string"] + list(_SIGNATURES)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().kdpc_error_string(rc).decode()
+        raise KdpcError(f"{what} failed with status {rc}: {msg}")

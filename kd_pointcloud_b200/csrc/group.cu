@@ -1,0 +1,269 @@
+// Gather / grouping kernels for sm_100a.
+//
+// Channel-major (pointnet2 API) versions replace gather_points_kernel_fast
+// (reference pointnet2/src/sampling_gpu.cu:8-24) and group_points_kernel_fast
+// (group_points_gpu.cu:47-66); point-major versions replace the permute+contiguous+op+permute
+// adapters index_points_gather / index_points_group and the group / group_query op chains
+// (pointconv_util.py:109-182).  All of them are pure data movement => HBM-bound; the design
+// goal is one pass, 128-bit accesses, and indices read once.
+#include "common.cuh"
+
+namespace kdpc {
+
+// ------------------------------------------------------------------------------------------
+// channel-major gather: out[b,c,j] = f[b,c,idx[b,j]].  On the model path C = 3 (new_xyz, GT flow).
+__global__ void gather_cm_kernel(int c, int n, int m, const float *__restrict__ f, const int *__restrict__ idx,
+                                 float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int src = idx[(size_t)b * m + j];             // index read ONCE, reused for all channels
+    const float *fb = f + (size_t)b * c * n;
+    float *ob = out + (size_t)b * c * m;
+    for (int ci = 0; ci < c; ++ci) ob[(size_t)ci * m + j] = __ldg(fb + (size_t)ci * n + src);
+}
+
+// channel-major grouping: out[b,c,s,k] = f[b,c,idx[b,s,k]].
+// A CTA stages CPB whole channel rows (N floats each) in shared memory, then streams the
+// index list once for those channels: random reads hit shared memory instead of L2 sectors
+// (a 4-byte random global read moves a 32-byte sector), index traffic drops by CPB x, and the
+// output is written fully coalesced.
+template <int CPB>
+__global__ void __launch_bounds__(512)
+group_cm_smem_kernel(int c, int n, int sk, int chunk, const float *__restrict__ f, const int *__restrict__ idx,
+                     float *__restrict__ out) {
+    extern __shared__ float rows[];                      // [CPB][n]
+    const int b = blockIdx.z, c0 = blockIdx.y * CPB;
+    const float *fb = f + ((size_t)b * c + c0) * n;
+    const int nch = min(CPB, c - c0);
+    for (int i = threadIdx.x; i < nch * n; i += blockDim.x) rows[i] = fb[i];
+    __syncthreads();
+    const int *ib = idx + (size_t)b * sk;
+    float *ob = out + ((size_t)b * c + c0) * sk;
+    const int e0 = blockIdx.x * chunk, e1 = min(sk, e0 + chunk);
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int src = ib[e];
+#pragma unroll
+        for (int ci = 0; ci < CPB; ++ci)
+            if (ci < nch) ob[(size_t)ci * sk + e] = rows[ci * n + src];
+    }
+}
+
+__global__ void group_cm_direct_kernel(int c, int n, int sk, const float *__restrict__ f, const int *__restrict__ idx,
+                                       float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= sk) return;
+    const int src = idx[(size_t)b * sk + e];
+    const float *fb = f + (size_t)b * c * n;
+    float *ob = out + (size_t)b * c * sk;
+    for (int ci = 0; ci < c; ++ci) ob[(size_t)ci * sk + e] = __ldg(fb + (size_t)ci * n + src);
+}
+
+// ------------------------------------------------------------------------------------------
+// point-major row gather: out[r,:] = f[b(r), idx[r], :]   (rows r = b*m + j, C floats per row).
+// VEC = 4: C % 4 == 0 and both bases 16-byte aligned -> one float4 per thread, consecutive threads
+// cover consecutive 16-byte pieces of the same output row (fully coalesced stores, row-contiguous
+// 128-bit loads).
+template <int VEC>
+__global__ void gather_rows_kernel(long long total, int n, int m, int cvec, const float *__restrict__ f,
+                                   const int *__restrict__ idx, float *__restrict__ out) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long r = e / cvec;
+    const int cv = (int)(e - r * cvec);
+    const long long b = r / m;
+    const int src = __ldg(idx + r);
+    const size_t in_off = ((size_t)b * n + src) * (size_t)cvec + cv;
+    if (VEC == 4) {
+        reinterpret_cast<float4 *>(out)[e] = __ldg(reinterpret_cast<const float4 *>(f) + in_off);
+    } else {
+        out[e] = __ldg(f + in_off);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused group + relative xyz + concat (pointconv_util.py:135-182):
+//   out[r, 0:3]   = cand_xyz[b, idx[r]] - query_xyz[b, s(r)]
+//   out[r, 3:3+D] = feats[b, idx[r], :]
+// Row width W = 3 + D is odd-sized (67, 131, ...), so rows are assembled in shared memory and the
+// CTA's contiguous output span [r0*W, (r0+R)*W) is then written with aligned 128-bit stores.
+constexpr int GC_ROWS = 32;          // rows per CTA (multiple of 4 keeps the span 16-byte aligned)
+constexpr int GC_THREADS = 256;
+
+__global__ void __launch_bounds__(GC_THREADS)
+group_concat_kernel(long long rows, int n, int s, int k, int d, const float *__restrict__ cand_xyz,
+                    const float *__restrict__ query_xyz, const float *__restrict__ feats,
+                    const int *__restrict__ idx, float *__restrict__ out) {
+    extern __shared__ __align__(16) float stage[];       // [GC_ROWS][W]
+    __shared__ int src_s[GC_ROWS];
+    const int w = 3 + d;
+    const long long r0 = (long long)blockIdx.x * GC_ROWS;
+    const int nr = (int)min((long long)GC_ROWS, rows - r0);
+    const int tid = threadIdx.x;
+
+    if (tid < nr) {
+        const long long r = r0 + tid;
+        const long long bs_ = r / k;                      // b*s + s_idx
+        const long long b = bs_ / s;
+        const int src = idx[r];
+        src_s[tid] = src;
+        const float *cp = cand_xyz + ((size_t)b * n + src) * 3;
+        const float *qp = query_xyz + (size_t)bs_ * 3;
+        float *o = stage + tid * w;
+        o[0] = cp[0] - qp[0];
+        o[1] = cp[1] - qp[1];
+        o[2] = cp[2] - qp[2];
+    }
+    __syncthreads();
+    if (d > 0) {
+        const long long b = r0 / ((long long)s * k);      // rows of one CTA may straddle a batch edge
+        if ((d & 3) == 0) {
+            const int dv = d >> 2;
+            for (int e = tid; e < nr * dv; e += GC_THREADS) {
+                const int rl = e / dv, cv = e - rl * dv;
+                const long long bb = (r0 + rl) / ((long long)s * k);
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(feats + ((size_t)bb * n + src_s[rl]) * d) + cv);
+                float *o = stage + rl * w + 3 + cv * 4;
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            }
+        } else {
+            for (int e = tid; e < nr * d; e += GC_THREADS) {
+                const int rl = e / d, ci = e - rl * d;
+                const long long bb = (r0 + rl) / ((long long)s * k);
+                stage[rl * w + 3 + ci] = __ldg(feats + ((size_t)bb * n + src_s[rl]) * d + ci);
+            }
+        }
+        (void)b;
+    }
+    __syncthreads();
+    const long long o0 = r0 * w;                          // multiple of 4 floats (GC_ROWS % 4 == 0)
+    const int tot = nr * w;
+    const int tot4 = tot >> 2;
+    float4 *o4 = reinterpret_cast<float4 *>(out + o0);
+    const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+    for (int e = tid; e < tot4; e += GC_THREADS) st_stream_f4(o4 + e, s4[e]);
+    for (int e = (tot4 << 2) + tid; e < tot; e += GC_THREADS) out[o0 + e] = stage[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// ball query (ball_query_gpu.cu:9-45): first nsample candidates inside the radius, in index
+// order, padded with the first hit; rows with no hit are zero.  Candidates are staged in shared
+// memory tiles; a warp leaves the scan when all of its queries are full.
+constexpr int BQ_THREADS = 128;
+constexpr int BQ_TILE = 1024;
+
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz,
+                  const float *__restrict__ xyz, int *__restrict__ idx) {
+    __shared__ float tile[BQ_TILE * 3];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * BQ_THREADS + threadIdx.x;
+    const bool active = q < m;
+    const float r2 = __fmul_rn(radius, radius);
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int *o = nullptr;
+    if (active) {
+        const float *qp = new_xyz + ((size_t)b * m + q) * 3;
+        qx = qp[0]; qy = qp[1]; qz = qp[2];
+        o = idx + ((size_t)b * m + q) * nsample;
+    }
+    int cnt = active ? 0 : nsample;
+    const float *pb = xyz + (size_t)b * n * 3;
+    for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
+        const int tn = min(BQ_TILE, n - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * 3; i += BQ_THREADS) tile[i] = pb[(size_t)t0 * 3 + i];
+        __syncthreads();
+        if (__syncthreads_and(cnt >= nsample)) break;
+        for (int j = 0; j < tn && cnt < nsample; ++j) {
+            const float d2 = direct_dist(qx - tile[j * 3 + 0], qy - tile[j * 3 + 1], qz - tile[j * 3 + 2]);
+            if (d2 < r2) {
+                if (cnt == 0)
+                    for (int l = 0; l < nsample; ++l) o[l] = t0 + j;
+                o[cnt++] = t0 + j;
+            }
+        }
+    }
+    if (active && cnt == 0)
+        for (int l = 0; l < nsample; ++l) o[l] = 0;       // pointnet2_utils.py:224 pre-zeroes idx
+}
+
+}  // namespace kdpc
+
+using namespace kdpc;
+
+KDPC_API int kdpc_gather(int b, int c, int n, int m, const float *f, const int *idx, float *out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(f && idx && out && b > 0 && c > 0 && n > 0 && m > 0);
+    if (b > 65535) return KDPC_EUNSUPPORTED;
+    dim3 grid((m + 255) / 256, b);
+    gather_cm_kernel<<<grid, 256, 0, to_stream(stream)>>>(c, n, m, f, idx, out);
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_group(int b, int c, int n, int s, int k, const float *f, const int *idx, float *out,
+                        kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(f && idx && out && b > 0 && c > 0 && n > 0 && s > 0 && k > 0);
+    if (b > 65535) return KDPC_EUNSUPPORTED;
+    const long long skl = (long long)s * k;
+    if (skl > 0x7fffffffLL) return KDPC_EUNSUPPORTED;
+    const int sk = (int)skl;
+    cudaStream_t st = to_stream(stream);
+    constexpr int CPB = 4;
+    const size_t smem = (size_t)CPB * n * sizeof(float);
+    if (smem <= 200 * 1024 && c >= 2) {
+        cudaError_t e = cudaFuncSetAttribute(group_cm_smem_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const int cgroups = (c + CPB - 1) / CPB;
+        // enough CTAs to cover the 148 SMs, but each one must amortise staging its channel rows
+        int split = (2 * kNumSMs + cgroups * b - 1) / (cgroups * b);
+        split = max(1, min(split, (sk + 8191) / 8192));
+        const int chunk = (sk + split - 1) / split;
+        dim3 grid(split, cgroups, b);
+        group_cm_smem_kernel<CPB><<<grid, 512, smem, st>>>(c, n, sk, chunk, f, idx, out);
+    } else {
+        dim3 grid((sk + 255) / 256, b);
+        group_cm_direct_kernel<<<grid, 256, 0, st>>>(c, n, sk, f, idx, out);
+    }
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const int *idx, float *out,
+                              kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(f && idx && out && b > 0 && n > 0 && m > 0 && c > 0);
+    cudaStream_t st = to_stream(stream);
+    const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    if (vec) {
+        const long long total = (long long)b * m * (c / 4);
+        gather_rows_kernel<4><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, m, c / 4, f, idx, out);
+    } else {
+        const long long total = (long long)b * m * c;
+        gather_rows_kernel<1><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, m, c, f, idx, out);
+    }
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_group_concat(int b, int n, int s, int k, int d, const float *cand_xyz, const float *query_xyz,
+                               const float *feats, const int *idx, float *out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(cand_xyz && query_xyz && idx && out && b > 0 && n > 0 && s > 0 && k > 0 && d >= 0);
+    KDPC_CHECK_ARGS(d == 0 || feats != nullptr);
+    if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return KDPC_EINVAL;
+    if (d > 0 && (d % 4 == 0) && (reinterpret_cast<uintptr_t>(feats) % 16) != 0) return KDPC_EINVAL;
+    const long long rows = (long long)b * s * k;
+    const size_t smem = (size_t)GC_ROWS * (3 + d) * sizeof(float);
+    if (smem > 200 * 1024) return KDPC_EUNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(group_concat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    group_concat_kernel<<<(unsigned)div_up_ll(rows, GC_ROWS), GC_THREADS, smem, to_stream(stream)>>>(
+        rows, n, s, k, d, cand_xyz, query_xyz, feats, idx, out);
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                             const float *xyz, int *idx, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(new_xyz && xyz && idx && b > 0 && n > 0 && m > 0 && nsample > 0);
+    if (b > 65535) return KDPC_EUNSUPPORTED;
+    dim3 grid((m + BQ_THREADS - 1) / BQ_THREADS, b);
+    ball_query_kernel<<<grid, BQ_THREADS, 0, to_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    KDPC_RETURN_LAST();
+}

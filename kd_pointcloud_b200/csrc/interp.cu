@@ -1,0 +1,110 @@
+// Three-neighbour interpolation kernels for sm_100a.
+//
+//  * three_interpolate (channel-major pointnet2 API): replaces three_interpolate_kernel_fast
+//    (reference pointnet2/src/interpolate_gpu.cu:77-97); same fma order as the reference's SASS.
+//  * interp3 (point-major): the inverse-distance interpolation shared by UpsampleFlow and
+//    PointWarping (pointconv_util.py:2131-2139, 2164-2171) fused into one pass: weights from the
+//    coordinates + weighted sum of three feature rows, one 128-bit access per thread.
+#include "common.cuh"
+
+namespace kdpc {
+
+__global__ void three_interpolate_cm_kernel(int c, int m, int n, const float *__restrict__ f,
+                                            const int *__restrict__ idx, const float *__restrict__ w,
+                                            float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int *ip = idx + ((size_t)b * n + i) * 3;
+    const float *wp = w + ((size_t)b * n + i) * 3;
+    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];        // read once, reused for all channels
+    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const float *fb = f + (size_t)b * c * m;
+    float *ob = out + (size_t)b * c * n;
+    for (int ci = 0; ci < c; ++ci) {
+        const float *fr = fb + (size_t)ci * m;
+        // w0*p0 + w1*p1 + w2*p2 as nvcc contracts it in the reference: fma(w2,p2, fma(w0,p0, rn(w1*p1)))
+        float t = __fmul_rn(w1, __ldg(fr + i1));
+        t = __fmaf_rn(w0, __ldg(fr + i0), t);
+        ob[(size_t)ci * n + i] = __fmaf_rn(w2, __ldg(fr + i2), t);
+    }
+}
+
+__device__ __forceinline__ void interp3_weights(const float *__restrict__ q, const float *__restrict__ cb,
+                                                int i0, int i1, int i2, float &w0, float &w1, float &w2) {
+    const float qx = q[0], qy = q[1], qz = q[2];
+    float r[3];
+    const int ii[3] = {i0, i1, i2};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float *cp = cb + (size_t)ii[j] * 3;
+        const float dx = cp[0] - qx, dy = cp[1] - qy, dz = cp[2] - qz;
+        // torch.norm(dim=3).clamp(min=1e-10); 1.0 / dist          (pointconv_util.py:2133-2135)
+        const float dist = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-10f);
+        r[j] = 1.0f / dist;
+    }
+    const float norm = (r[0] + r[1]) + r[2];
+    w0 = r[0] / norm; w1 = r[1] / norm; w2 = r[2] / norm;
+}
+
+template <int VEC>
+__global__ void interp3_kernel(long long total, int n, int s, int cvec, const float *__restrict__ q_xyz,
+                               const float *__restrict__ c_xyz, const int *__restrict__ idx,
+                               const float *__restrict__ feat, float *__restrict__ out, float *__restrict__ w_out) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long r = e / cvec;                         // r = b*n + i
+    const int cv = (int)(e - r * cvec);
+    const long long b = r / n;
+    const int *ip = idx + r * 3;
+    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
+    float w0, w1, w2;
+    interp3_weights(q_xyz + r * 3, c_xyz + (size_t)b * s * 3, i0, i1, i2, w0, w1, w2);
+    if (w_out != nullptr && cv == 0) { w_out[r * 3 + 0] = w0; w_out[r * 3 + 1] = w1; w_out[r * 3 + 2] = w2; }
+    const size_t fb = (size_t)b * s * cvec;
+    if (VEC == 4) {
+        const float4 *f4 = reinterpret_cast<const float4 *>(feat);
+        const float4 a = __ldg(f4 + fb + (size_t)i0 * cvec + cv);
+        const float4 bq = __ldg(f4 + fb + (size_t)i1 * cvec + cv);
+        const float4 cq = __ldg(f4 + fb + (size_t)i2 * cvec + cv);
+        float4 o;
+        o.x = (w0 * a.x + w1 * bq.x) + w2 * cq.x;
+        o.y = (w0 * a.y + w1 * bq.y) + w2 * cq.y;
+        o.z = (w0 * a.z + w1 * bq.z) + w2 * cq.z;
+        o.w = (w0 * a.w + w1 * bq.w) + w2 * cq.w;
+        reinterpret_cast<float4 *>(out)[e] = o;
+    } else {
+        const float a = __ldg(feat + fb + (size_t)i0 * cvec + cv);
+        const float bq = __ldg(feat + fb + (size_t)i1 * cvec + cv);
+        const float cq = __ldg(feat + fb + (size_t)i2 * cvec + cv);
+        out[e] = (w0 * a + w1 * bq) + w2 * cq;
+    }
+}
+
+}  // namespace kdpc
+
+using namespace kdpc;
+
+KDPC_API int kdpc_three_interpolate(int b, int c, int m, int n, const float *f, const int *idx, const float *w,
+                                    float *out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(f && idx && w && out && b > 0 && c > 0 && m > 0 && n > 0);
+    if (b > 65535) return KDPC_EUNSUPPORTED;
+    dim3 grid((n + 255) / 256, b);
+    three_interpolate_cm_kernel<<<grid, 256, 0, to_stream(stream)>>>(c, m, n, f, idx, w, out);
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_interp3(int b, int n, int s, int c, const float *q_xyz, const float *c_xyz, const int *idx,
+                          const float *feat, float *out, float *w_out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(q_xyz && c_xyz && idx && feat && out && b > 0 && n > 0 && s > 0 && c > 0);
+    cudaStream_t st = to_stream(stream);
+    const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    if (vec) {
+        const long long total = (long long)b * n * (c / 4);
+        interp3_kernel<4><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, s, c / 4, q_xyz, c_xyz, idx, feat, out, w_out);
+    } else {
+        const long long total = (long long)b * n * c;
+        interp3_kernel<1><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, s, c, q_xyz, c_xyz, idx, feat, out, w_out);
+    }
+    KDPC_RETURN_LAST();
+}

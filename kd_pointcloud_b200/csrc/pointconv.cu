@@ -1,0 +1,130 @@
+// PointConv pieces for sm_100a (unfused building blocks).
+//
+//  * weightnet : the per-neighbour MLP 3 -> h1 -> h2 -> wout with ReLU after EVERY layer
+//                (reference WeightNet, pointconv_util.py:184-215, bn=False), which the reference
+//                runs as three cuDNN 1x1 convolutions on a strided [B,3,K,S] view.
+//  * pointconv_agg : out[r, c*wout + w] = sum_k grouped[r,k,c] * wn[r,k,w]
+//                (the torch.matmul at pointconv_util.py:249 / :437, B*S tiny matrices).
+// The fully fused PointConv (gather + weightnet + aggregation + Linear on tcgen05) lives in
+// pointconv_fused.cu; these kernels serve the stand-alone WeightNet / group API and the backward.
+#include "common.cuh"
+
+namespace kdpc {
+
+template <int H1, int H2, int WOUT>
+__global__ void __launch_bounds__(256)
+weightnet_kernel(long long rows, const float *__restrict__ in, int in_stride, const float *__restrict__ w1,
+                 const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
+                 const float *__restrict__ w3, const float *__restrict__ b3, float *__restrict__ out) {
+    __shared__ float sw1[H1 * 3], sb1[H1], sw2[H2 * H1], sb2[H2], sw3[WOUT * H2], sb3[WOUT];
+    for (int i = threadIdx.x; i < H1 * 3; i += blockDim.x) sw1[i] = w1[i];
+    for (int i = threadIdx.x; i < H1; i += blockDim.x) sb1[i] = b1[i];
+    for (int i = threadIdx.x; i < H2 * H1; i += blockDim.x) sw2[i] = w2[i];
+    for (int i = threadIdx.x; i < H2; i += blockDim.x) sb2[i] = b2[i];
+    for (int i = threadIdx.x; i < WOUT * H2; i += blockDim.x) sw3[i] = w3[i];
+    for (int i = threadIdx.x; i < WOUT; i += blockDim.x) sb3[i] = b3[i];
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *x = in + r * in_stride;
+    const float x0 = x[0], x1 = x[1], x2 = x[2];
+    float h1[H1], h2[H2];
+#pragma unroll
+    for (int o = 0; o < H1; ++o)
+        h1[o] = fmaxf(sb1[o] + sw1[o * 3 + 0] * x0 + sw1[o * 3 + 1] * x1 + sw1[o * 3 + 2] * x2, 0.f);
+#pragma unroll
+    for (int o = 0; o < H2; ++o) {
+        float a = sb2[o];
+#pragma unroll
+        for (int i = 0; i < H1; ++i) a += sw2[o * H1 + i] * h1[i];
+        h2[o] = fmaxf(a, 0.f);
+    }
+    float *op = out + r * WOUT;
+#pragma unroll
+    for (int o4 = 0; o4 < WOUT; o4 += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float a = sb3[o4 + u];
+#pragma unroll
+            for (int i = 0; i < H2; ++i) a += sw3[(o4 + u) * H2 + i] * h2[i];
+            v[u] = fmaxf(a, 0.f);
+        }
+        *reinterpret_cast<float4 *>(op + o4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// One CTA per AGG_ROWS points; thread = one channel c, WOUT accumulators.
+// grouped[r,k,c] is read coalesced across c; wn[r,k,:] comes from shared memory (broadcast).
+constexpr int AGG_THREADS = 128;
+
+template <int WOUT>
+__global__ void __launch_bounds__(AGG_THREADS)
+pointconv_agg_kernel(long long rows, int k, int c, const float *__restrict__ grouped, const float *__restrict__ wn,
+                     float *__restrict__ out) {
+    extern __shared__ float swn[];                        // [k][WOUT]
+    const long long r = blockIdx.x;
+    const float *wr = wn + r * (long long)k * WOUT;
+    for (int i = threadIdx.x; i < k * WOUT; i += AGG_THREADS) swn[i] = wr[i];
+    __syncthreads();
+    const float *gr = grouped + r * (long long)k * c;
+    float *orow = out + r * (long long)c * WOUT;
+    for (int ci = threadIdx.x; ci < c; ci += AGG_THREADS) {
+        float acc[WOUT];
+#pragma unroll
+        for (int w = 0; w < WOUT; ++w) acc[w] = 0.f;
+        for (int kk = 0; kk < k; ++kk) {
+            const float g = __ldg(gr + (size_t)kk * c + ci);
+            const float *wk = swn + kk * WOUT;
+#pragma unroll
+            for (int w = 0; w < WOUT; ++w) acc[w] = fmaf(g, wk[w], acc[w]);
+        }
+        float4 *o4 = reinterpret_cast<float4 *>(orow + (size_t)ci * WOUT);
+#pragma unroll
+        for (int w = 0; w < WOUT; w += 4) st_stream_f4(o4 + (w >> 2), make_float4(acc[w], acc[w + 1], acc[w + 2], acc[w + 3]));
+    }
+}
+
+}  // namespace kdpc
+
+using namespace kdpc;
+
+KDPC_API int kdpc_weightnet(long long rows, const float *in, int in_stride, int h1, int h2, int wout,
+                            const float *w1, const float *b1, const float *w2, const float *b2,
+                            const float *w3, const float *b3, float *out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(in && w1 && b1 && w2 && b2 && w3 && b3 && out && rows > 0 && in_stride >= 3);
+    if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return KDPC_EINVAL;
+    cudaStream_t st = to_stream(stream);
+    const unsigned grid = (unsigned)div_up_ll(rows, 256);
+#define KDPC_WN_CASE(A, B_, C) \
+    if (h1 == A && h2 == B_ && wout == C) { \
+        weightnet_kernel<A, B_, C><<<grid, 256, 0, st>>>(rows, in, in_stride, w1, b1, w2, b2, w3, b3, out); \
+        return (int)cudaGetLastError(); }
+    KDPC_WN_CASE(8, 8, 4)
+    KDPC_WN_CASE(8, 8, 8)
+    KDPC_WN_CASE(8, 8, 16)
+    KDPC_WN_CASE(8, 8, 32)
+    KDPC_WN_CASE(8, 8, 48)
+#undef KDPC_WN_CASE
+    return KDPC_EUNSUPPORTED;
+}
+
+KDPC_API int kdpc_pointconv_agg(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
+                                float *out, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(grouped && wn && out && rows > 0 && k > 0 && c > 0);
+    if ((reinterpret_cast<uintptr_t>(out) % 16) != 0 || rows > 0x7fffffffLL) return KDPC_EINVAL;
+    cudaStream_t st = to_stream(stream);
+    const size_t smem = (size_t)k * wout * sizeof(float);
+    if (smem > 48 * 1024) return KDPC_EUNSUPPORTED;
+#define KDPC_AGG_CASE(W) \
+    if (wout == W) { \
+        pointconv_agg_kernel<W><<<(unsigned)rows, AGG_THREADS, smem, st>>>(rows, k, c, grouped, wn, out); \
+        return (int)cudaGetLastError(); }
+    KDPC_AGG_CASE(4)
+    KDPC_AGG_CASE(8)
+    KDPC_AGG_CASE(16)
+    KDPC_AGG_CASE(32)
+    KDPC_AGG_CASE(48)
+#undef KDPC_AGG_CASE
+    return KDPC_EUNSUPPORTED;
+}

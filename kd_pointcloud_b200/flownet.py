@@ -1,0 +1,163 @@
+"""Bi-PointFlowNet (``PointConvBidirection``) on the kdpc layers.
+
+Mirror of the reference's teacher ``models_bid_pointconv.PointConvBidirection``
+(models_bid_pointconv.py:14-207) and student ``models_bid_lighttoken_res.PointConvBidirection``
+(models_bid_lighttoken_res.py:14-189) — the two are the same architecture with identical
+``state_dict`` keys; ``weightnet`` is the student's only knob.  Same attribute names, so
+reference checkpoints load; same ``forward(xyz1, xyz2, color1, color2)`` 8-tuple.
+
+What differs is the schedule, not the math:
+  * activations stay point-major end to end (the reference permutes/copies around every op);
+  * both clouds go through the weight-shared encoder as ONE batch of 2B clouds (one FPS launch
+    covers 2B CTAs, half the launches everywhere); the encoder has no BatchNorm, so this is
+    exactly equivalent;
+  * each 3-NN / kNN index set is computed once and shared by every consumer of the same
+    (query, candidate) pair.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import functional as KF
+from .functional import cm, knn_idx
+from .pointconv_util import (Conv1d, CrossLayerLight, PointConvD, PointWarping, SceneFlowEstimatorResidual,
+                             UpsampleFlow)
+
+scale = 1.0
+
+
+class PointConvBidirection(nn.Module):
+    def __init__(self, weightnet: int = 16):
+        super().__init__()
+        flow_nei, feat_nei = 32, 16
+        self.scale = scale
+        # l0: 8192
+        self.level0 = Conv1d(3, 32)
+        self.level0_1 = Conv1d(32, 32)
+        self.cross0 = CrossLayerLight(flow_nei, 32 + 32, [32, 32], [32, 32])
+        self.flow0 = SceneFlowEstimatorResidual(32 + 64, 32, weightnet=weightnet)
+        self.level0_2 = Conv1d(32, 64)
+        # l1: 2048
+        self.level1 = PointConvD(2048, feat_nei, 64 + 3, 64, weightnet=weightnet)
+        self.cross1 = CrossLayerLight(flow_nei, 64 + 32, [64, 64], [64, 64])
+        self.flow1 = SceneFlowEstimatorResidual(64 + 64, 64, weightnet=weightnet)
+        self.level1_0 = Conv1d(64, 64)
+        self.level1_1 = Conv1d(64, 128)
+        # l2: 512
+        self.level2 = PointConvD(512, feat_nei, 128 + 3, 128, weightnet=weightnet)
+        self.cross2 = CrossLayerLight(flow_nei, 128 + 64, [128, 128], [128, 128])
+        self.flow2 = SceneFlowEstimatorResidual(128 + 64, 128, weightnet=weightnet)
+        self.level2_0 = Conv1d(128, 128)
+        self.level2_1 = Conv1d(128, 256)
+        # l3: 256
+        self.level3 = PointConvD(256, feat_nei, 256 + 3, 256, weightnet=weightnet)
+        self.cross3 = CrossLayerLight(flow_nei, 256 + 64, [256, 256], [256, 256])
+        self.flow3 = SceneFlowEstimatorResidual(256, 256, weightnet=weightnet)
+        self.level3_0 = Conv1d(256, 256)
+        self.level3_1 = Conv1d(256, 512)
+        # l4: 64
+        self.level4 = PointConvD(64, feat_nei, 512 + 3, 256, weightnet=weightnet)
+        # deconv
+        self.deconv4_3 = Conv1d(256, 64)
+        self.deconv3_2 = Conv1d(256, 64)
+        self.deconv2_1 = Conv1d(128, 32)
+        self.deconv1_0 = Conv1d(64, 32)
+        self.warping = PointWarping()
+        self.upsample = UpsampleFlow()
+
+    def forward(self, xyz1, xyz2, color1, color2):
+        # xyz*, color*: [B,N,3]   (models_bid_pointconv.py:74-92)
+        B = xyz1.shape[0]
+        up = self.upsample.forward_pm
+        cat_c = lambda *ts: torch.cat(ts, dim=2)
+        both = lambda a, b: torch.cat([a, b], dim=0)
+
+        # ---- encoder: clouds 1 and 2 as one batch of 2B (weights are shared, no BN) --------------
+        pc_l0 = both(xyz1, xyz2).contiguous()
+        f_l0 = self.level0_1.forward_pm(self.level0.forward_pm(both(color1, color2)))
+        f_l0_1 = self.level0_2.forward_pm(f_l0)
+
+        pc_l1, f_l1, fps_l1 = self.level1.forward_pm(pc_l0, f_l0_1)
+        f_l1 = self.level1_0.forward_pm(f_l1)
+        f_l1_2 = self.level1_1.forward_pm(f_l1)
+
+        pc_l2, f_l2, fps_l2 = self.level2.forward_pm(pc_l1, f_l1_2)
+        f_l2 = self.level2_0.forward_pm(f_l2)
+        f_l2_3 = self.level2_1.forward_pm(f_l2)
+
+        pc_l3, f_l3, fps_l3 = self.level3.forward_pm(pc_l2, f_l2_3)
+        f_l3 = self.level3_0.forward_pm(f_l3)
+        f_l3_4 = self.level3_1.forward_pm(f_l3)
+
+        pc_l4, f_l4, _ = self.level4.forward_pm(pc_l3, f_l3_4)
+        f_l4_3 = self.deconv4_3.forward_pm(up(pc_l3, pc_l4, f_l4))
+
+        # 3-NN index sets dense<-sparse, computed once for both clouds and reused below
+        up32 = knn_idx(3, pc_l3, pc_l2)
+        up21 = knn_idx(3, pc_l2, pc_l1)
+        up10 = knn_idx(3, pc_l1, pc_l0)
+
+        h = lambda t: (t[:B], t[B:])
+        (pc1_l0, pc2_l0), (pc1_l1, pc2_l1), (pc1_l2, pc2_l2), (pc1_l3, pc2_l3) = h(pc_l0), h(pc_l1), h(pc_l2), h(pc_l3)
+        feat1_l0, feat2_l0 = h(f_l0)
+        feat1_l1, feat2_l1 = h(f_l1)
+        feat1_l2, feat2_l2 = h(f_l2)
+        feat1_l3, feat2_l3 = h(f_l3)
+
+        # ---- l3 -------------------------------------------------------------------------------
+        c_feat1_l3, c_feat2_l3 = h(cat_c(f_l3, f_l4_3))
+        feat1_new_l3, feat2_new_l3, cross3 = self.cross3.forward_pm(pc1_l3, pc2_l3, c_feat1_l3, c_feat2_l3)
+        feat3, flow3 = self.flow3.forward_pm(pc1_l3, feat1_l3, cross3)
+
+        f_l3_2 = self.deconv3_2.forward_pm(up(pc_l2, pc_l3, both(feat1_new_l3, feat2_new_l3), idx=up32))
+        c_feat1_l2, c_feat2_l2 = h(cat_c(f_l2, f_l3_2))
+
+        # ---- l2 -------------------------------------------------------------------------------
+        up_flow2 = up(pc1_l2, pc1_l3, self.scale * flow3, idx=up32[:B])
+        pc2_l2_warp = self.warping.forward_pm(pc1_l2, pc2_l2, up_flow2)
+        feat1_new_l2, feat2_new_l2, cross2 = self.cross2.forward_pm(pc1_l2, pc2_l2_warp, c_feat1_l2, c_feat2_l2)
+        feat3_up = up(pc1_l2, pc1_l3, feat3, idx=up32[:B])
+        feat2, flow2 = self.flow2.forward_pm(pc1_l2, cat_c(feat1_l2, feat3_up), cross2, up_flow2)
+
+        f_l2_1 = self.deconv2_1.forward_pm(up(pc_l1, pc_l2, both(feat1_new_l2, feat2_new_l2), idx=up21))
+        c_feat1_l1, c_feat2_l1 = h(cat_c(f_l1, f_l2_1))
+
+        # ---- l1 -------------------------------------------------------------------------------
+        up_flow1 = up(pc1_l1, pc1_l2, self.scale * flow2, idx=up21[:B])
+        pc2_l1_warp = self.warping.forward_pm(pc1_l1, pc2_l1, up_flow1)
+        feat1_new_l1, feat2_new_l1, cross1 = self.cross1.forward_pm(pc1_l1, pc2_l1_warp, c_feat1_l1, c_feat2_l1)
+        feat2_up = up(pc1_l1, pc1_l2, feat2, idx=up21[:B])
+        feat1, flow1 = self.flow1.forward_pm(pc1_l1, cat_c(feat1_l1, feat2_up), cross1, up_flow1)
+
+        f_l1_0 = self.deconv1_0.forward_pm(up(pc_l0, pc_l1, both(feat1_new_l1, feat2_new_l1), idx=up10))
+        c_feat1_l0, c_feat2_l0 = h(cat_c(f_l0, f_l1_0))
+
+        # ---- l0 -------------------------------------------------------------------------------
+        up_flow0 = up(pc1_l0, pc1_l1, self.scale * flow1, idx=up10[:B])
+        pc2_l0_warp = self.warping.forward_pm(pc1_l0, pc2_l0, up_flow0)
+        _, _, cross0 = self.cross0.forward_pm(pc1_l0, pc2_l0_warp, c_feat1_l0, c_feat2_l0)
+        feat1_up = up(pc1_l0, pc1_l1, feat1, idx=up10[:B])
+        _, flow0 = self.flow0.forward_pm(pc1_l0, cat_c(feat1_l0, feat1_up), cross0, up_flow0)
+
+        # ---- outputs in the reference's [B,C,N] layout (models_bid_pointconv.py:198-207) ------
+        flows = [cm(flow0), cm(flow1), cm(flow2), cm(flow3)]
+        pc1 = [cm(pc1_l0), cm(pc1_l1), cm(pc1_l2), cm(pc1_l3)]
+        pc2 = [cm(pc2_l0), cm(pc2_l1), cm(pc2_l2), cm(pc2_l3)]
+        fps_pc1_idxs = [fps_l1[:B], fps_l2[:B], fps_l3[:B]]
+        fps_pc2_idxs = [fps_l1[B:], fps_l2[B:], fps_l3[B:]]
+        s = lambda t, i: cm(t[:B] if i == 0 else t[B:])
+        feat1s = [s(t, 0) for t in (f_l0_1, f_l1_2, f_l2_3, f_l3_4, f_l3_2, f_l2_1, f_l1_0)]
+        feat2s = [s(t, 1) for t in (f_l0_1, f_l1_2, f_l2_3, f_l3_4, f_l3_2, f_l2_1, f_l1_0)]
+        crosses = [cm(cross0), cm(cross1), cm(cross2), cm(cross3)]
+        return flows, fps_pc1_idxs, fps_pc2_idxs, pc1, pc2, feat1s, feat2s, crosses
+
+
+def teacher() -> PointConvBidirection:
+    """models_bid_pointconv.PointConvBidirection()"""
+    return PointConvBidirection(weightnet=16)
+
+
+def student(weightnet: int = 16) -> PointConvBidirection:
+    """models_bid_lighttoken_res.PointConvBidirection() (weightnet = 16, models_bid_lighttoken_res.py:20)"""
+    return PointConvBidirection(weightnet=weightnet)

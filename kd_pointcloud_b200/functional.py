@@ -1,0 +1,318 @@
+"""Differentiable, cached front-end over ``torch.ops.kdpc``.
+
+* Indices are constants for autograd (the reference returns ``None`` for them,
+  pointnet2_utils.py:31-33,100-102); gradients flow to features and — where the reference's
+  autograd would — to coordinates.
+* Every gather-type backward is a fixed-order segmented reduction over an inverse index (CSR)
+  instead of the reference's fp32 ``atomicAdd`` (sampling_gpu.cu:62, group_points_gpu.cu:24,
+  interpolate_gpu.cu:139-141): deterministic, and the CSR is cached per index tensor so layers
+  that share an index (the two flow-estimator PointConvs, cross call 1 and 3, the upsample calls
+  of one level) build it once.
+* ``knn_idx`` caches its result per (query, candidates, K) tensor identity + version: the
+  reference recomputes 45 kNNs per forward of which only 29 are distinct.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops  # noqa: F401  (registers torch.ops.kdpc)
+
+K = torch.ops.kdpc
+
+# ------------------------------------------------------------------------------------ caches
+
+
+def _tkey(t: torch.Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index)
+
+
+class _LRU:
+    def __init__(self, cap: int):
+        self.cap = cap
+        self.d: "OrderedDict" = OrderedDict()
+        self.hits = 0
+        self.misses = 0
+
+    def get(self, key):
+        v = self.d.get(key)
+        if v is not None:
+            self.d.move_to_end(key)
+            self.hits += 1
+        else:
+            self.misses += 1
+        return v
+
+    def put(self, key, value):
+        self.d[key] = value
+        if len(self.d) > self.cap:
+            self.d.popitem(last=False)
+
+    def clear(self):
+        self.d.clear()
+
+
+_KNN_CACHE = _LRU(48)
+_CSR_CACHE = _LRU(48)
+_CACHE_ENABLED = True
+
+
+def clear_caches() -> None:
+    """Drop cached kNN results and inverse indices (call between independent batches)."""
+    _KNN_CACHE.clear()
+    _CSR_CACHE.clear()
+
+
+def set_cache_enabled(flag: bool) -> None:
+    global _CACHE_ENABLED
+    _CACHE_ENABLED = bool(flag)
+    clear_caches()
+
+
+def cache_stats():
+    return {"knn_hits": _KNN_CACHE.hits, "knn_misses": _KNN_CACHE.misses,
+            "csr_hits": _CSR_CACHE.hits, "csr_misses": _CSR_CACHE.misses}
+
+
+def pm(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,N] -> contiguous point-major [B,N,C] (free when x is a permuted pm tensor)."""
+    return x.permute(0, 2, 1).contiguous()
+
+
+def cm(x: torch.Tensor) -> torch.Tensor:
+    """point-major [B,N,C] -> the reference's [B,C,N] as a permuted view."""
+    return x.permute(0, 2, 1)
+
+
+# --------------------------------------------------------------------------- kNN (a6, a7)
+def knn_idx(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """int32 [B,S,nsample] neighbours of new_xyz in xyz, ascending (distance, index)."""
+    xyz_d = xyz.detach()
+    new_d = new_xyz.detach()
+    if not xyz_d.is_contiguous():
+        xyz_d = xyz_d.contiguous()
+    if not new_d.is_contiguous():
+        new_d = new_d.contiguous()
+    if not _CACHE_ENABLED:
+        return K.knn(new_d, xyz_d, nsample)
+    key = (nsample, _tkey(xyz_d), _tkey(new_d))
+    hit = _KNN_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    idx = K.knn(new_d, xyz_d, nsample)
+    _KNN_CACHE.put(key, (idx, xyz_d, new_d))       # keep the keyed tensors alive: no address reuse
+    return idx
+
+
+def knn_point(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """pointconv_util.knn_point (pointconv_util.py:96-107): int64 [B,S,nsample]."""
+    return knn_idx(nsample, xyz, new_xyz).long()
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    return K.square_distance(src.detach().contiguous(), dst.detach().contiguous())
+
+
+def _csr(idx: torch.Tensor, n: int):
+    if not _CACHE_ENABLED:
+        return K.build_csr(idx, n)
+    key = (n, _tkey(idx))
+    hit = _CSR_CACHE.get(key)
+    if hit is not None:
+        return hit[0], hit[1]
+    off, perm = K.build_csr(idx, n)
+    _CSR_CACHE.put(key, (off, perm, idx))
+    return off, perm
+
+
+def _as_i32(idx: torch.Tensor) -> torch.Tensor:
+    if idx.dtype != torch.int32:
+        idx = idx.int()                            # the reference's `.int()` (pointconv_util.py:131)
+    return idx.contiguous()
+
+
+# --------------------------------------------------------------- channel-major pointnet2 ops
+class _GatherCM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = features.shape[2]
+        return K.gather_cm(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return K.gather_cm_grad(grad_out.contiguous(), idx, ctx.n), None
+
+
+class _GroupCM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = features.shape[2]
+        return K.group_cm(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return K.group_cm_grad(grad_out.contiguous(), idx, ctx.n), None
+
+
+class _ThreeInterpolateCM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        ctx.save_for_backward(idx, weight)
+        ctx.m = features.shape[2]
+        return K.three_interpolate_cm(features, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        return K.three_interpolate_cm_grad(grad_out.contiguous(), idx, weight, ctx.m), None, None
+
+
+def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    return K.fps(xyz.detach(), int(npoint))
+
+
+def gather_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return _GatherCM.apply(features, idx)
+
+
+def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return _GroupCM.apply(features, idx)
+
+
+def three_nn(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    dist2, idx = K.three_nn(unknown.detach(), known.detach())
+    return torch.sqrt(dist2), idx                  # pointnet2_utils.py:98
+
+
+def three_interpolate(features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    return _ThreeInterpolateCM.apply(features, idx, weight)
+
+
+def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    return K.ball_query(float(radius), int(nsample), xyz.detach(), new_xyz.detach())
+
+
+# ------------------------------------------------------------------- point-major gathers
+class _GatherRows(torch.autograd.Function):
+    """out[b, ..., :] = points[b, idx[b, ...], :]"""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = points.shape[1]
+        return K.gather_rows(points, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        off, perm = _csr(idx, ctx.n)
+        return K.scatter_rows_csr(grad_out.contiguous(), None, off, perm, ctx.n, 1), None
+
+
+def gather_rows(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """points [B,N,C], idx [B,...] -> [B,...,C]  (index_points_gather / index_points_group, pm)."""
+    return _GatherRows.apply(points.contiguous(), _as_i32(idx))
+
+
+class _GroupConcat(torch.autograd.Function):
+    """[cand_xyz[idx] - query_xyz (3) | feats[idx] (D)]  ->  [B,S,K,3+D]"""
+
+    @staticmethod
+    def forward(ctx, cand_xyz, query_xyz, feats, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = cand_xyz.shape[1]
+        ctx.has_feats = feats is not None
+        ctx.same_xyz = cand_xyz.data_ptr() == query_xyz.data_ptr() and cand_xyz.shape == query_xyz.shape
+        return K.group_concat(cand_xyz, query_xyz, feats, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        need_c, need_q, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g_c = g_q = g_f = None
+        off = perm = None
+        if need_f and ctx.has_feats:
+            off, perm = _csr(idx, ctx.n)
+            g_f = K.scatter_rows_csr(grad_out[..., 3:].contiguous(), None, off, perm, ctx.n, 1)
+        if need_c or need_q:
+            g_rel = grad_out[..., :3].contiguous()
+            if need_c:
+                if off is None:
+                    off, perm = _csr(idx, ctx.n)
+                g_c = K.scatter_rows_csr(g_rel, None, off, perm, ctx.n, 1)
+            if need_q:
+                g_q = -g_rel.sum(dim=2)
+        return g_c, g_q, g_f, None
+
+
+def group_concat(cand_xyz, query_xyz, feats: Optional[torch.Tensor], idx) -> torch.Tensor:
+    return _GroupConcat.apply(cand_xyz.contiguous(), query_xyz.contiguous(),
+                              None if feats is None else feats.contiguous(), _as_i32(idx))
+
+
+# ------------------------------------------------------------------- 3-NN interpolation
+class _Interp3(torch.autograd.Function):
+    """Inverse-distance interpolation; differentiable w.r.t. the interpolated features only
+    (coordinates never require grad in UpsampleFlow)."""
+
+    @staticmethod
+    def forward(ctx, q_xyz, c_xyz, idx, feat):
+        out, w = K.interp3(q_xyz, c_xyz, idx, feat)
+        ctx.save_for_backward(idx, w)
+        ctx.s = c_xyz.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, w = ctx.saved_tensors
+        off, perm = _csr(idx, ctx.s)
+        g = K.scatter_rows_csr(grad_out.contiguous(), w, off, perm, ctx.s, 3)
+        return None, None, None, g
+
+
+def interp3(q_xyz, c_xyz, idx, feat) -> torch.Tensor:
+    return _Interp3.apply(q_xyz.detach().contiguous(), c_xyz.detach().contiguous(), _as_i32(idx), feat.contiguous())
+
+
+def interp3_composite(q_xyz, c_xyz, idx, feat) -> torch.Tensor:
+    """Same arithmetic from differentiable primitives (used when the candidate coordinates
+    require grad, i.e. PointWarping in training: pointconv_util.py:2131-2139)."""
+    B, N, _ = q_xyz.shape
+    rel = gather_rows(c_xyz, idx) - q_xyz.view(B, N, 1, 3)
+    dist = torch.norm(rel, dim=3).clamp(min=1e-10)
+    inv = 1.0 / dist
+    weight = inv / torch.sum(inv, dim=2, keepdim=True)
+    return torch.sum(weight.view(B, N, 3, 1) * gather_rows(feat, idx), dim=2)
+
+
+# ------------------------------------------------------------------- PointConv pieces
+class _PointConvAgg(torch.autograd.Function):
+    """out[b,s,c*W+w] = sum_k grouped[b,s,k,c] * wn[b,s,k,w]   (pointconv_util.py:249)."""
+
+    @staticmethod
+    def forward(ctx, grouped, wn):
+        ctx.save_for_backward(grouped, wn)
+        return K.pointconv_agg(grouped, wn)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grouped, wn = ctx.saved_tensors
+        B, S, Kn, C = grouped.shape
+        W = wn.shape[3]
+        g = grad_out.reshape(B * S, C, W)
+        g_grouped = g_wn = None
+        if ctx.needs_input_grad[0]:
+            g_grouped = torch.bmm(wn.reshape(B * S, Kn, W), g.transpose(1, 2)).view(B, S, Kn, C)
+        if ctx.needs_input_grad[1]:
+            g_wn = torch.bmm(grouped.reshape(B * S, Kn, C), g).view(B, S, Kn, W)
+        return g_grouped, g_wn
+
+
+def pointconv_agg(grouped: torch.Tensor, wn: torch.Tensor) -> torch.Tensor:
+    return _PointConvAgg.apply(grouped.contiguous(), wn.contiguous())

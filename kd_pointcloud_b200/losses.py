@@ -1,0 +1,76 @@
+"""Multi-scale flow loss and distillation terms (reference loss_functions.py).
+
+    multiScaleLoss              loss_functions.py:6-25  (copies: models_bid_pointconv.py:545-563)
+    loss_fn_kd_2                loss_functions.py:27-36
+    biDirection_loss_ht         loss_functions.py:83-96
+    cross_biDirection_loss_ht   loss_functions.py:201-219  (the one distilTrain.py:174 calls; it raises
+                                for the shipped student because cat(t_feat1,t_feat2) has twice the
+                                student's channels — SURVEY 9.  ``hint_mode='first'`` gives the
+                                shape-valid sibling used by BASELINE config 4.)
+    epe3d                       distilTrain.py:229
+
+The GT pyramid is the chained FPS gather of the ground-truth flow; the per-scale term is
+``alpha_i * mean_b sum_n ||pred_i - gt_i||_2``.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+
+from . import functional as KF
+
+scale = 1.0
+ALPHA = (0.02, 0.04, 0.08, 0.16)
+
+
+def multiScaleLoss(pred_flows: Sequence[torch.Tensor], gt_flow: torch.Tensor, fps_idxs: Sequence[torch.Tensor],
+                   alpha: Sequence[float] = ALPHA) -> torch.Tensor:
+    """pred_flows: [B,3,N_i] per scale (finest first); gt_flow [B,N,3]; fps_idxs int32 [B,N_{i+1}]."""
+    num_scale = len(pred_flows)
+    offset = len(fps_idxs) - num_scale + 1
+    gts: List[torch.Tensor] = [gt_flow]
+    for idx in fps_idxs:
+        gts.append(KF.gather_rows(gts[-1], idx) / scale)
+    total = torch.zeros(1, device=gt_flow.device, dtype=gt_flow.dtype)
+    for i in range(num_scale):
+        diff = pred_flows[i].permute(0, 2, 1) - gts[i + offset]
+        total = total + alpha[i] * torch.norm(diff, dim=2).sum(dim=1).mean()
+    return total
+
+
+def epe3d(pred_flow0: torch.Tensor, gt_flow: torch.Tensor) -> torch.Tensor:
+    """distilTrain.py:229: mean over B*N of ||pred - gt||_2; pred_flow0 [B,3,N], gt [B,N,3]."""
+    return torch.norm(pred_flow0.permute(0, 2, 1) - gt_flow, dim=2).mean()
+
+
+def loss_fn_kd_2(outputs, fps_idxs, gt_flow, teacher_outputs, teacher_fps_idxs, gamma, alpha=ALPHA):
+    t0 = teacher_outputs[0].permute(0, 2, 1)
+    return gamma * multiScaleLoss(outputs, t0, fps_idxs, alpha) + (1 - gamma) * multiScaleLoss(outputs, gt_flow, fps_idxs, alpha)
+
+
+def biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, teacher_outputs, t_feat1s, t_feat2s,
+                        t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=0, alpha=ALPHA):
+    t0 = teacher_outputs[0].permute(0, 2, 1)
+    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
+    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
+    src = ((feat1s[layer] - t_feat1s[layer]) ** 2) / 2
+    tgt = ((feat2s[layer] - t_feat2s[layer]) ** 2) / 2
+    return beta * (gamma * loss1 + (1 - gamma) * loss2) + (1 - beta) * (0.5 * src.sum() + 0.5 * tgt.sum())
+
+
+def cross_biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, teacher_outputs, t_feat1s,
+                              t_feat2s, t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=(2, 3), alpha=ALPHA,
+                              hint_mode: str = "cat"):
+    """``hint_mode='cat'`` is the reference formula verbatim (student feature vs cat(teacher feat1,
+    teacher feat2) on channels — needs a student with twice the teacher's channels);
+    ``hint_mode='first'`` compares against the teacher's feat1 only (shape-valid for the shipped
+    student, same structure: MS-vs-teacher + MS-vs-GT + half squared hint error)."""
+    t0 = teacher_outputs[0].permute(0, 2, 1)
+    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
+    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
+    hint = torch.zeros(1, device=gt_flow.device, dtype=gt_flow.dtype)
+    for each in layer:
+        t = torch.cat([t_feat1s[each], t_feat2s[each]], dim=1) if hint_mode == "cat" else t_feat1s[each]
+        hint = hint + ((feat1s[each] - t) ** 2).sum() / 2
+    return beta * (gamma * loss1 + (1 - gamma) * loss2) + (1 - beta) * hint

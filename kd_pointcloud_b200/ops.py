@@ -1,0 +1,441 @@
+"""``torch.library`` registration of the libkdpc kernels as ``torch.ops.kdpc.*``.
+
+Each op is registered for the CUDA dispatch key ONLY: a CPU tensor makes the dispatcher raise
+("no kernel for the CPU backend") and a missing ``libkdpc.so`` raises ``KdpcError`` — there is no
+fallback path.  The implementations are thin: validate, allocate the outputs/workspaces with the
+torch allocator (the caller-allocates convention of the reference, pointnet2_utils.py:25-26), and
+pass raw device pointers + the current stream through the C ABI (include/kdpc.h).
+
+Differentiable wrappers live in ``functional.py``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_LIB = torch.library.Library("kdpc", "DEF")
+LAUNCHES = 0          # number of C-ABI calls issued (bench.py reports kernels launched)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, ndim=None, name="tensor"):
+    if t.dtype != dtype:
+        raise TypeError(f"kdpc: {name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"kdpc: {name} must be {ndim}-D, got shape {tuple(t.shape)}")
+    # same contract as the reference wrappers (`assert xyz.is_contiguous()`, pointnet2_utils.py:22)
+    assert t.is_contiguous(), f"kdpc: {name} must be contiguous"
+
+
+def _call(name: str, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(_lib.lib(), name)(*args), name)
+
+
+class _guard:
+    """Run on the device of the inputs (the reference uses the *current* device)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.dev = t.device
+        self.ctx = None
+
+    def __enter__(self):
+        if self.dev.index is not None and self.dev.index != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(self.dev)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def _register(schema: str, impl, fake):
+    name = schema.split("(")[0]
+    _LIB.define(schema)
+    _LIB.impl(name, impl, "CUDA")
+    torch.library.register_fake(f"kdpc::{name}")(fake)
+
+
+# ------------------------------------------------------------------------------------------ a1
+def _fps(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    _req(xyz, torch.float32, 3, "xyz")
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("kdpc: xyz must be [B,N,3]")
+    with _guard(xyz):
+        idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        temp = torch.empty((B, N), dtype=torch.float32, device=xyz.device)
+        if B > 0 and npoint > 0:
+            _call("kdpc_fps", B, N, npoint, _p(xyz), _p(temp), _p(idx), _stream())
+    return idx
+
+
+_register("fps(Tensor xyz, int npoint) -> Tensor", _fps,
+          lambda xyz, npoint: xyz.new_empty((xyz.shape[0], npoint), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------------ a2
+def _gather_cm(f: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _req(f, torch.float32, 3, "features")
+    _req(idx, torch.int32, 2, "idx")
+    B, C, N = f.shape
+    M = idx.shape[1]
+    with _guard(f):
+        out = torch.empty((B, C, M), dtype=torch.float32, device=f.device)
+        if out.numel():
+            _call("kdpc_gather", B, C, N, M, _p(f), _p(idx), _p(out), _stream())
+    return out
+
+
+def _gather_cm_grad(g: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    _req(g, torch.float32, 3, "grad_out")
+    _req(idx, torch.int32, 2, "idx")
+    B, C, M = g.shape
+    with _guard(g):
+        gf = torch.empty((B, C, n), dtype=torch.float32, device=g.device)
+        ws = torch.empty((B * (n + 1 + M),), dtype=torch.int32, device=g.device)
+        _call("kdpc_gather_grad", B, C, n, M, _p(g), _p(idx), _p(ws), _p(gf), _stream())
+    return gf
+
+
+_register("gather_cm(Tensor f, Tensor idx) -> Tensor", _gather_cm,
+          lambda f, idx: f.new_empty((f.shape[0], f.shape[1], idx.shape[1])))
+_register("gather_cm_grad(Tensor g, Tensor idx, int n) -> Tensor", _gather_cm_grad,
+          lambda g, idx, n: g.new_empty((g.shape[0], g.shape[1], n)))
+
+
+# ------------------------------------------------------------------------------------------ a3
+def _group_cm(f: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _req(f, torch.float32, 3, "features")
+    _req(idx, torch.int32, 3, "idx")
+    B, C, N = f.shape
+    _, S, K = idx.shape
+    with _guard(f):
+        out = torch.empty((B, C, S, K), dtype=torch.float32, device=f.device)
+        if out.numel():
+            _call("kdpc_group", B, C, N, S, K, _p(f), _p(idx), _p(out), _stream())
+    return out
+
+
+def _group_cm_grad(g: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
+    _req(g, torch.float32, 4, "grad_out")
+    _req(idx, torch.int32, 3, "idx")
+    B, C, S, K = g.shape
+    with _guard(g):
+        gf = torch.empty((B, C, n), dtype=torch.float32, device=g.device)
+        ws = torch.empty((B * (n + 1 + S * K),), dtype=torch.int32, device=g.device)
+        _call("kdpc_group_grad", B, C, n, S, K, _p(g), _p(idx), _p(ws), _p(gf), _stream())
+    return gf
+
+
+_register("group_cm(Tensor f, Tensor idx) -> Tensor", _group_cm,
+          lambda f, idx: f.new_empty((f.shape[0], f.shape[1], idx.shape[1], idx.shape[2])))
+_register("group_cm_grad(Tensor g, Tensor idx, int n) -> Tensor", _group_cm_grad,
+          lambda g, idx, n: g.new_empty((g.shape[0], g.shape[1], n)))
+
+
+# ------------------------------------------------------------------------------------- a4, a5
+def _three_nn(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(unknown, torch.float32, 3, "unknown")
+    _req(known, torch.float32, 3, "known")
+    B, N, _ = unknown.shape
+    M = known.shape[1]
+    with _guard(unknown):
+        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
+        idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
+        ws = torch.empty((B * M * 4,), dtype=torch.float32, device=unknown.device)
+        if dist2.numel():
+            _call("kdpc_three_nn", B, N, M, _p(unknown), _p(known), _p(ws), _p(dist2), _p(idx), _stream())
+    return dist2, idx
+
+
+def _three_interpolate_cm(f: torch.Tensor, idx: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    _req(f, torch.float32, 3, "features")
+    _req(idx, torch.int32, 3, "idx")
+    _req(w, torch.float32, 3, "weight")
+    B, C, M = f.shape
+    N = idx.shape[1]
+    with _guard(f):
+        out = torch.empty((B, C, N), dtype=torch.float32, device=f.device)
+        if out.numel():
+            _call("kdpc_three_interpolate", B, C, M, N, _p(f), _p(idx), _p(w), _p(out), _stream())
+    return out
+
+
+def _three_interpolate_cm_grad(g: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, m: int) -> torch.Tensor:
+    _req(g, torch.float32, 3, "grad_out")
+    _req(idx, torch.int32, 3, "idx")
+    _req(w, torch.float32, 3, "weight")
+    B, C, N = g.shape
+    with _guard(g):
+        gf = torch.empty((B, C, m), dtype=torch.float32, device=g.device)
+        ws = torch.empty((B * (m + 1 + 3 * N),), dtype=torch.int32, device=g.device)
+        _call("kdpc_three_interpolate_grad", B, C, N, m, _p(g), _p(idx), _p(w), _p(ws), _p(gf), _stream())
+    return gf
+
+
+_register("three_nn(Tensor unknown, Tensor known) -> (Tensor, Tensor)", _three_nn,
+          lambda u, k: (u.new_empty(u.shape), u.new_empty(u.shape, dtype=torch.int32)))
+_register("three_interpolate_cm(Tensor f, Tensor idx, Tensor w) -> Tensor", _three_interpolate_cm,
+          lambda f, idx, w: f.new_empty((f.shape[0], f.shape[1], idx.shape[1])))
+_register("three_interpolate_cm_grad(Tensor g, Tensor idx, Tensor w, int m) -> Tensor",
+          _three_interpolate_cm_grad, lambda g, idx, w, m: g.new_empty((g.shape[0], g.shape[1], m)))
+
+
+def _ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    _req(xyz, torch.float32, 3, "xyz")
+    _req(new_xyz, torch.float32, 3, "new_xyz")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    with _guard(xyz):
+        idx = torch.empty((B, M, nsample), dtype=torch.int32, device=xyz.device)
+        if idx.numel():
+            _call("kdpc_ball_query", B, N, M, float(radius), nsample, _p(new_xyz), _p(xyz), _p(idx), _stream())
+    return idx
+
+
+_register("ball_query(float radius, int nsample, Tensor xyz, Tensor new_xyz) -> Tensor", _ball_query,
+          lambda r, ns, xyz, new_xyz: xyz.new_empty((xyz.shape[0], new_xyz.shape[1], ns), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------- a6, a7
+def _square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    _req(src, torch.float32, 3, "src")
+    _req(dst, torch.float32, 3, "dst")
+    B, S, _ = src.shape
+    N = dst.shape[1]
+    with _guard(src):
+        out = torch.empty((B, S, N), dtype=torch.float32, device=src.device)
+        if out.numel():
+            _call("kdpc_square_distance", B, S, N, _p(src), _p(dst), _p(out), _stream())
+    return out
+
+
+def _knn_impl(query, cand, k, want64, want_dist):
+    _req(query, torch.float32, 3, "new_xyz")
+    _req(cand, torch.float32, 3, "xyz")
+    if query.shape[2] != 3 or cand.shape[2] != 3:
+        raise ValueError("kdpc: knn expects [B,*,3] coordinates")
+    B, S, _ = query.shape
+    N = cand.shape[1]
+    if k > N:
+        raise RuntimeError(f"kdpc: knn k={k} exceeds the number of candidates {N}")  # torch.topk raises too
+    dev = query.device
+    with _guard(query):
+        idx32 = torch.empty((B, S, k), dtype=torch.int32, device=dev)
+        idx64 = torch.empty((B, S, k), dtype=torch.int64, device=dev) if want64 else None
+        dist = torch.empty((B, S, k), dtype=torch.float32, device=dev) if want_dist else None
+        ws = torch.empty((B * N * 4,), dtype=torch.float32, device=dev)
+        if idx32.numel():
+            _call("kdpc_knn", B, S, N, k, _p(query), _p(cand), _p(ws), _p(idx32), _p(idx64), _p(dist), _stream())
+    return idx32, idx64, dist
+
+
+def _knn(query: torch.Tensor, cand: torch.Tensor, k: int) -> torch.Tensor:
+    return _knn_impl(query, cand, k, False, False)[0]
+
+
+def _knn64(query: torch.Tensor, cand: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    i32, i64, _ = _knn_impl(query, cand, k, True, False)
+    return i32, i64
+
+
+def _knn_dist(query: torch.Tensor, cand: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    i32, _, d = _knn_impl(query, cand, k, False, True)
+    return i32, d
+
+
+_register("square_distance(Tensor src, Tensor dst) -> Tensor", _square_distance,
+          lambda s, d: s.new_empty((s.shape[0], s.shape[1], d.shape[1])))
+_register("knn(Tensor query, Tensor cand, int k) -> Tensor", _knn,
+          lambda q, c, k: q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32))
+_register("knn64(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn64,
+          lambda q, c, k: (q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32),
+                           q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int64)))
+_register("knn_dist(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn_dist,
+          lambda q, c, k: (q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32),
+                           q.new_empty((q.shape[0], q.shape[1], k))))
+
+
+# ------------------------------------------------------------------------------------- a8, a9
+def _gather_rows(f: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """f [B,N,C], idx int32 [B,...] -> [B,...,C]."""
+    _req(f, torch.float32, 3, "points")
+    _req(idx, torch.int32, None, "idx")
+    B, N, C = f.shape
+    if idx.shape[0] != B:
+        raise ValueError("kdpc: idx batch size does not match points")
+    M = idx.numel() // max(B, 1)
+    with _guard(f):
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=f.device)
+        if out.numel():
+            _call("kdpc_gather_rows", B, N, M, C, _p(f), _p(idx), _p(out), _stream())
+    return out
+
+
+def _group_concat(cand_xyz: torch.Tensor, query_xyz: torch.Tensor, feats: Optional[torch.Tensor],
+                  idx: torch.Tensor) -> torch.Tensor:
+    _req(cand_xyz, torch.float32, 3, "xyz")
+    _req(query_xyz, torch.float32, 3, "new_xyz")
+    _req(idx, torch.int32, 3, "idx")
+    B, N, _ = cand_xyz.shape
+    _, S, K = idx.shape
+    D = 0
+    if feats is not None:
+        _req(feats, torch.float32, 3, "points")
+        D = feats.shape[2]
+    with _guard(cand_xyz):
+        out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=cand_xyz.device)
+        if out.numel():
+            _call("kdpc_group_concat", B, N, S, K, D, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx), _p(out),
+                  _stream())
+    return out
+
+
+_register("gather_rows(Tensor f, Tensor idx) -> Tensor", _gather_rows,
+          lambda f, idx: f.new_empty(tuple(idx.shape) + (f.shape[2],)))
+_register("group_concat(Tensor cand_xyz, Tensor query_xyz, Tensor? feats, Tensor idx) -> Tensor", _group_concat,
+          lambda c, q, f, idx: c.new_empty(tuple(idx.shape) + (3 + (0 if f is None else f.shape[2]),)))
+
+
+# ------------------------------------------------------------------------------------ a10, a11
+def _weightnet(x: torch.Tensor, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
+    """x [..., W>=3] contiguous (the first 3 of every row are the localized xyz) -> [..., wout]."""
+    _req(x, torch.float32, None, "localized_xyz")
+    for t in (w1, b1, w2, b2, w3, b3):
+        _req(t, torch.float32, None, "weightnet parameter")
+    W = x.shape[-1]
+    rows = x.numel() // W
+    h1, h2, wout = w1.shape[0], w2.shape[0], w3.shape[0]
+    with _guard(x):
+        out = torch.empty(tuple(x.shape[:-1]) + (wout,), dtype=torch.float32, device=x.device)
+        if out.numel():
+            _call("kdpc_weightnet", rows, _p(x), W, h1, h2, wout, _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
+                  _p(out), _stream())
+    return out
+
+
+def _pointconv_agg(grouped: torch.Tensor, wn: torch.Tensor) -> torch.Tensor:
+    _req(grouped, torch.float32, 4, "grouped")
+    _req(wn, torch.float32, 4, "weights")
+    B, S, K, C = grouped.shape
+    W = wn.shape[3]
+    with _guard(grouped):
+        out = torch.empty((B, S, C * W), dtype=torch.float32, device=grouped.device)
+        if out.numel():
+            _call("kdpc_pointconv_agg", B * S, K, C, W, _p(grouped), _p(wn), _p(out), _stream())
+    return out
+
+
+_register("weightnet(Tensor x, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor w3, Tensor b3) -> Tensor",
+          _weightnet, lambda x, w1, b1, w2, b2, w3, b3: x.new_empty(tuple(x.shape[:-1]) + (w3.shape[0],)))
+_register("pointconv_agg(Tensor grouped, Tensor wn) -> Tensor", _pointconv_agg,
+          lambda g, w: g.new_empty((g.shape[0], g.shape[1], g.shape[3] * w.shape[3])))
+
+
+# ----------------------------------------------------------------------------------------- a13
+def _costvol_pre(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, slope: float) -> torch.Tensor:
+    for t, nm in ((xyz1, "xyz1"), (xyz2, "xyz2"), (p1, "points1"), (p2, "points2")):
+        _req(t, torch.float32, 3, nm)
+    _req(idx, torch.int32, 3, "idx")
+    _req(pos_w, torch.float32, None, "pos weight")
+    _req(pos_b, torch.float32, 1, "pos bias")
+    B, S, _ = xyz1.shape
+    N = xyz2.shape[1]
+    K = idx.shape[2]
+    D = p1.shape[2]
+    with _guard(xyz1):
+        out = torch.empty((B, S, K, D), dtype=torch.float32, device=xyz1.device)
+        if out.numel():
+            _call("kdpc_costvol_pre", B, S, N, K, D, _p(xyz1), _p(xyz2), _p(p1), _p(p2), _p(idx), _p(pos_w),
+                  _p(pos_b), float(slope), _p(out), _stream())
+    return out
+
+
+def _max_over_k(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(x, torch.float32, 4, "x")
+    B, S, K, D = x.shape
+    with _guard(x):
+        out = torch.empty((B, S, D), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, S, D), dtype=torch.int32, device=x.device)
+        if out.numel():
+            _call("kdpc_max_over_k", B * S, K, D, _p(x), _p(out), _p(arg), _stream())
+    return out, arg
+
+
+_register("costvol_pre(Tensor xyz1, Tensor xyz2, Tensor p1, Tensor p2, Tensor idx, Tensor pos_w, Tensor pos_b, "
+          "float slope) -> Tensor", _costvol_pre,
+          lambda x1, x2, p1, p2, idx, pw, pb, s: p1.new_empty(tuple(idx.shape) + (p1.shape[2],)))
+_register("max_over_k(Tensor x) -> (Tensor, Tensor)", _max_over_k,
+          lambda x: (x.new_empty((x.shape[0], x.shape[1], x.shape[3])),
+                     x.new_empty((x.shape[0], x.shape[1], x.shape[3]), dtype=torch.int32)))
+
+
+# ------------------------------------------------------------------------------------ a14, a15
+def _interp3(q_xyz, c_xyz, idx, feat) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(q_xyz, torch.float32, 3, "xyz")
+    _req(c_xyz, torch.float32, 3, "sparse_xyz")
+    _req(idx, torch.int32, 3, "idx")
+    _req(feat, torch.float32, 3, "sparse_flow")
+    B, N, _ = q_xyz.shape
+    S = c_xyz.shape[1]
+    C = feat.shape[2]
+    with _guard(q_xyz):
+        out = torch.empty((B, N, C), dtype=torch.float32, device=q_xyz.device)
+        w = torch.empty((B, N, 3), dtype=torch.float32, device=q_xyz.device)
+        if out.numel():
+            _call("kdpc_interp3", B, N, S, C, _p(q_xyz), _p(c_xyz), _p(idx), _p(feat), _p(out), _p(w), _stream())
+    return out, w
+
+
+_register("interp3(Tensor q_xyz, Tensor c_xyz, Tensor idx, Tensor feat) -> (Tensor, Tensor)", _interp3,
+          lambda q, c, idx, f: (q.new_empty((q.shape[0], q.shape[1], f.shape[2])), q.new_empty(q.shape)))
+
+
+# --------------------------------------------------------------------------- backward plumbing
+def _build_csr(idx: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    _req(idx, torch.int32, None, "idx")
+    B = idx.shape[0]
+    M = idx.numel() // B
+    with _guard(idx):
+        offsets = torch.empty((B, n + 1), dtype=torch.int32, device=idx.device)
+        perm = torch.empty((B, M), dtype=torch.int32, device=idx.device)
+        _call("kdpc_build_csr", B, n, M, _p(idx), _p(offsets), _p(perm), _stream())
+    return offsets, perm
+
+
+def _scatter_rows_csr(g: torch.Tensor, wgt: Optional[torch.Tensor], offsets: torch.Tensor, perm: torch.Tensor,
+                      n: int, gdiv: int) -> torch.Tensor:
+    """g [B, M/gdiv, C] (any leading layout flattening to that) -> [B, n, C]."""
+    _req(g, torch.float32, None, "grad")
+    B = offsets.shape[0]
+    M = perm.shape[1]
+    C = g.shape[-1]
+    if g.numel() != B * (M // gdiv) * C:
+        raise ValueError("kdpc: scatter_rows_csr shape mismatch")
+    if wgt is not None:
+        _req(wgt, torch.float32, None, "weight")
+    with _guard(g):
+        out = torch.empty((B, n, C), dtype=torch.float32, device=g.device)
+        _call("kdpc_scatter_rows_csr", B, n, M, C, gdiv, _p(g), _p(wgt), _p(offsets), _p(perm), _p(out), 0, _stream())
+    return out
+
+
+_register("build_csr(Tensor idx, int n) -> (Tensor, Tensor)", _build_csr,
+          lambda idx, n: (idx.new_empty((idx.shape[0], n + 1)), idx.new_empty((idx.shape[0], idx.numel() // idx.shape[0]))))
+_register("scatter_rows_csr(Tensor g, Tensor? wgt, Tensor offsets, Tensor perm, int n, int gdiv) -> Tensor",
+          _scatter_rows_csr, lambda g, w, o, p, n, gdiv: g.new_empty((o.shape[0], n, g.shape[-1])))
+
+kdpc = torch.ops.kdpc

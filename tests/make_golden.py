@@ -1,0 +1,211 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python tests/make_golden.py
+
+The reference's torch layers (pointconv_util.py, loss_functions.py, models_bid_pointconv.py) are
+imported as they are.  Its three CUDA-only pointnet2 ops (furthest_point_sample, gather_operation,
+grouping_operation) have no CPU implementation in the reference, so a stub ``pointnet2`` module
+provides them from oracle/kdpc_oracle.c (FPS) and torch.gather; those are pinned separately
+against the reference's own CUDA kernels (oracle/_ref) in tests/test_ref_kernels_gpu.py.
+
+While generating, the script ASSERTS that oracle/layers_ref.py (the restatement used as checker
+and CPU baseline on the GPU box) reproduces the reference outputs, i.e. it pins the oracle.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle import layers_ref as O  # noqa: E402
+from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict  # noqa: E402
+
+
+def import_reference():
+    stub_pkg = types.ModuleType("pointnet2")
+    stub = types.ModuleType("pointnet2.pointnet2_utils")
+    stub.furthest_point_sample = lambda xyz, npoint: O.furthest_point_sample(xyz, npoint)
+    stub.gather_operation = lambda f, idx: O.gather_operation(f, idx)
+    stub.grouping_operation = lambda f, idx: O.grouping_operation(f, idx)
+    stub_pkg.pointnet2_utils = stub
+    sys.modules["pointnet2"] = stub_pkg
+    sys.modules["pointnet2.pointnet2_utils"] = stub
+    thop = types.ModuleType("thop")
+    thop.profile = thop.clever_format = lambda *a, **k: None
+    sys.modules["thop"] = thop
+    sys.path.insert(0, REF)
+    import pointconv_util as R          # the reference's
+    import pointconv_util3 as R3
+    R.BottleNeck = R3.BottleNeck        # models_bid_pointconv.py:7 imports a name pointconv_util lacks
+    import loss_functions as RL
+    import models_bid_pointconv as RM
+    # loss_functions.multiScaleLoss calls .cuda(); patch for CPU generation only
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    return R, RL, RM
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"  wrote {name}.npz  ({os.path.getsize(os.path.join(GOLD, name + '.npz')) / 1024:.0f} KB)")
+
+
+def close(a, b, tol=0.0, what=""):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    if a.dtype.is_floating_point:
+        err = (a - b).abs().max().item()
+        ref = b.abs().max().item()
+        assert err <= tol * max(ref, 1e-30) + (0 if tol else 0), f"{what}: oracle differs from reference, max err {err} (ref max {ref})"
+    else:
+        assert torch.equal(a.long(), b.long()), f"{what}: oracle index mismatch"
+
+
+def load_weights(module, seed=0):
+    sd = synthetic_state_dict(module.state_dict(), seed)
+    module.load_state_dict(sd)
+    module.eval()
+    return sd
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    R, RL, RM = import_reference()
+
+    # ---- a6/a7 square_distance, knn_point -------------------------------------------------
+    d = make_pairs(2, 512, seed=11, kind="kitti")
+    q, c = d["pos1"][:, :96].contiguous(), d["pos2"]
+    sq = R.square_distance(q, c)
+    close(O.square_distance(q, c), sq, 0.0, "square_distance (torch chain)")
+    close(O.square_distance_c(q, c), sq, 0.0, "square_distance (scalar C)")
+    ks = {}
+    for k in (3, 9, 16, 32):
+        idx = R.knn_point(k, c, q)
+        ks[f"knn{k}"] = torch.sort(idx, dim=-1)[0]
+        mine = torch.sort(O.knn_point(k, c, q), dim=-1)[0]
+        close(mine, ks[f"knn{k}"], what=f"knn_point k={k}")
+    save("knn", query=q, cand=c, sqdist=sq, **ks)
+
+    # ---- a8/a9 group / group_query --------------------------------------------------------
+    feats = torch.randn(2, 512, 20)
+    new_points, rel = R.group_query(16, c, q, feats)
+    o_np, o_rel = O.group_query(16, c, q, feats)
+    idx16 = R.knn_point(16, c, q)
+    # order inside K is unspecified in the reference: compare after sorting groups by index
+    order = torch.argsort(idx16, dim=-1)
+    o_order = torch.argsort(O.knn_point(16, c, q), dim=-1)
+    g_sorted = torch.gather(new_points, 2, order.unsqueeze(-1).expand_as(new_points))
+    close(torch.gather(o_np, 2, o_order.unsqueeze(-1).expand_as(o_np)), g_sorted, 0.0, "group_query")
+    save("group_query", xyz=c, new_xyz=q, points=feats, grouped_sorted_by_index=g_sorted)
+
+    # ---- a10-a12 WeightNet, PointConv, PointConvD ------------------------------------------
+    xyz = make_pairs(2, 256, seed=12)["pos1"].permute(0, 2, 1).contiguous()        # [B,3,N]
+    pts = torch.randn(2, 29, 256) * 0.5
+    wn = R.WeightNet(3, 16)
+    sd = load_weights(wn, 1)
+    loc = torch.randn(2, 3, 9, 40)
+    w_ref = wn(loc)
+    close(O.weightnet({"w." + k: v for k, v in sd.items()}, "w", loc), w_ref, 1e-6, "WeightNet")
+    save("weightnet", localized_xyz=loc, out=w_ref)
+
+    pcv = R.PointConv(9, 29 + 3, 24, bn=True)
+    sd = load_weights(pcv, 2)
+    y_ref = pcv(xyz, pts)
+    close(O.pointconv({"p." + k: v for k, v in sd.items()}, "p", 9, xyz, pts, bn=True), y_ref, 1e-5, "PointConv")
+    save("pointconv", xyz=xyz, points=pts, out=y_ref)
+
+    pcd = R.PointConvD(64, 16, 29 + 3, 40)
+    sd = load_weights(pcd, 3)
+    nx, ny, fidx = pcd(xyz, pts)
+    ox, oy, oi = O.pointconvd({"p." + k: v for k, v in sd.items()}, "p", 64, 16, xyz, pts)
+    close(oi, fidx, what="PointConvD fps")
+    close(ox, nx, 0.0, "PointConvD xyz")
+    close(oy, ny, 1e-5, "PointConvD feats")
+    save("pointconvd", xyz=xyz, points=pts, new_xyz=nx, out=ny, fps_idx=fidx)
+
+    # ---- a13 CrossLayerLight ---------------------------------------------------------------
+    d = make_pairs(2, 256, seed=13)
+    pc1, pc2 = d["pos1"].permute(0, 2, 1).contiguous(), d["pos2"].permute(0, 2, 1).contiguous()
+    f1, f2 = torch.randn(2, 24, 256) * 0.5, torch.randn(2, 24, 256) * 0.5
+    cl = R.CrossLayerLight(32, 24, [16, 16], [16, 16])
+    sd = load_weights(cl, 4)
+    a, b, cc = cl(pc1, pc2, f1, f2)
+    oa, ob, oc = O.cross_layer_light({"c." + k: v for k, v in sd.items()}, "c", 32, pc1, pc2, f1, f2)
+    for x, y, nm in ((oa, a, "f1"), (ob, b, "f2"), (oc, cc, "f3")):
+        close(x, y, 1e-5, "CrossLayerLight " + nm)
+    save("crosslayer", pc1=pc1, pc2=pc2, feat1=f1, feat2=f2, out1=a, out2=b, out3=cc)
+
+    # ---- a14/a15 PointWarping, UpsampleFlow ------------------------------------------------
+    flow1 = d["flow"].permute(0, 2, 1).contiguous() + 0.05 * torch.randn(2, 3, 256)
+    w_ref = R.PointWarping()(pc1, pc2, flow1)
+    close(O.point_warping(pc1, pc2, flow1), w_ref, 1e-6, "PointWarping")
+    sparse = pc1[:, :, ::4].contiguous()
+    sflow = torch.randn(2, 12, 64)
+    u_ref = R.UpsampleFlow()(pc1, sparse, sflow)
+    close(O.upsample_flow(pc1, sparse, sflow), u_ref, 1e-6, "UpsampleFlow")
+    save("warp_upsample", pc1=pc1, pc2=pc2, flow1=flow1, warped=w_ref, sparse_xyz=sparse, sparse_flow=sflow, up=u_ref)
+
+    # ---- a16 SceneFlowEstimatorResidual ----------------------------------------------------
+    est = R.SceneFlowEstimatorResidual(24, 16, channels=[32, 32], mlp=[32, 16])
+    sd = load_weights(est, 5)
+    cost = torch.randn(2, 16, 256) * 0.5
+    fl_in = torch.randn(2, 3, 256) * 0.1
+    e_feat, e_flow = est(pc1, f1, cost, fl_in)
+    o_feat, o_flow = O.scene_flow_estimator_residual({"e." + k: v for k, v in sd.items()}, "e", pc1, f1, cost, fl_in)
+    close(o_feat, e_feat, 1e-5, "SceneFlowEstimatorResidual feat")
+    close(o_flow, e_flow, 1e-5, "SceneFlowEstimatorResidual flow")
+    save("flow_estimator", xyz=pc1, feats=f1, cost=cost, flow=fl_in, out_feat=e_feat, out_flow=e_flow)
+
+    # ---- a18 multiScaleLoss ---------------------------------------------------------------
+    gt = torch.randn(2, 256, 3)
+    fidx1 = O.furthest_point_sample(d["pos1"], 64)
+    fidx2 = O.furthest_point_sample(R.index_points_gather(d["pos1"], fidx1), 16)
+    preds = [torch.randn(2, 3, 256), torch.randn(2, 3, 64), torch.randn(2, 3, 16)]
+    l_ref = RL.multiScaleLoss(preds, gt, [fidx1, fidx2])
+    close(O.multi_scale_loss(preds, gt, [fidx1, fidx2]), l_ref, 1e-6, "multiScaleLoss")
+    save("multiscale_loss", gt=gt, fps1=fidx1, fps2=fidx2, p0=preds[0], p1=preds[1], p2=preds[2], loss=l_ref)
+
+    # ---- a20 whole model (teacher), B=1, N=4096, synthetic weights ----------------------------
+    model = RM.PointConvBidirection()
+    sd = load_weights(model, 7)
+    keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0)
+    d = make_pairs(1, 4096, seed=21)
+    out = model(d["pos1"], d["pos2"], d["color1"], d["color2"])
+    flows, fps1, fps2, pcs1, pcs2, feat1s, feat2s, crosses = out
+    o = O.bid_pointconv_forward(sd, d["pos1"], d["pos2"], d["color1"], d["color2"])
+    for i in range(4):
+        close(o[0][i], flows[i], 2e-4, f"model flow{i}")
+    for i in range(3):
+        close(o[1][i], fps1[i], what=f"model fps1[{i}]")
+        close(o[2][i], fps2[i], what=f"model fps2[{i}]")
+    for i in range(7):
+        close(o[5][i], feat1s[i], 2e-4, f"model feat1s[{i}]")
+        close(o[6][i], feat2s[i], 2e-4, f"model feat2s[{i}]")
+    for i in range(4):
+        close(o[7][i], crosses[i], 2e-4, f"model cross{i}")
+    loss = RL.multiScaleLoss(flows, d["flow"], fps1)
+    epe = torch.norm(flows[0].permute(0, 2, 1) - d["flow"], dim=2).mean()
+    save("model_teacher_n4096", flow0=flows[0], flow1=flows[1], flow2=flows[2], flow3=flows[3],
+         fps1_0=fps1[0], fps1_1=fps1[1], fps1_2=fps1[2], fps2_0=fps2[0], fps2_1=fps2[1], fps2_2=fps2[2],
+         cross3=crosses[3], feat1_l3_4=feat1s[3], loss=loss, epe3d=epe)
+    print("golden vectors written; oracle/layers_ref.py reproduces the reference on every case")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,280 @@
+"""GPU parity tests, kernel level: every libkdpc kernel (called through torch.ops.kdpc -> C ABI)
+against the CPU oracle on the same seeded inputs.  Index/integer work must be bit-exact; fp32
+arithmetic that the reference pins (distances, three_interpolate) must be bit-exact too; the rest
+is checked to 1e-5 relative (tolerance stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as O
+from kd_pointcloud_b200 import functional as KF
+from kd_pointcloud_b200.synth import make_pairs
+
+pytestmark = pytest.mark.gpu
+K = torch.ops.kdpc
+DEV = "cuda:0"
+
+
+def _cloud(b, n, seed, mode):
+    if mode == "grid":                                   # integer grid: exact ties everywhere
+        g = torch.Generator().manual_seed(seed)
+        return torch.randint(0, 7, (b, n, 3), generator=g).float()
+    if mode == "dup":
+        return make_pairs(b, n, seed=seed, duplicates=0.05)["pos1"]
+    if mode == "cm":
+        return make_pairs(b, n, seed=seed, quantize=0.01)["pos1"]
+    if mode == "kitti":
+        return make_pairs(b, n, seed=seed, kind="kitti")["pos1"]
+    return make_pairs(b, n, seed=seed)["pos1"]
+
+
+# ------------------------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("n,m,mode", [
+    (8192, 2048, "ft3d"), (8192, 2048, "dup"), (2048, 512, "cm"), (512, 256, "grid"), (256, 64, "kitti"),
+    (1000, 100, "grid"), (3000, 64, "dup"), (5000, 33, "ft3d"), (37, 9, "grid"), (20, 20, "grid"), (10000, 50, "dup"),
+    (64, 1, "ft3d"),
+])
+def test_fps_bit_exact(n, m, mode):
+    xyz = _cloud(2, n, 100 + n, mode)
+    got = K.fps(xyz.to(DEV), m).cpu()
+    assert got.dtype == torch.int32 and got.shape == (2, m)
+    assert torch.equal(got, O.furthest_point_sample(xyz, m))
+
+
+def test_fps_batch_of_16_clouds_and_determinism():
+    xyz = _cloud(16, 2048, 7, "dup").to(DEV)
+    a, b = K.fps(xyz, 512), K.fps(xyz, 512)
+    assert torch.equal(a, b)
+    assert torch.equal(a[5:7].cpu(), O.furthest_point_sample(xyz[5:7].cpu(), 512))
+
+
+# ------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("s,n,k,mode", [
+    (8192, 8192, 32, "ft3d"), (2048, 8192, 16, "kitti"), (8192, 2048, 3, "ft3d"), (512, 512, 9, "grid"),
+    (300, 1000, 16, "dup"), (64, 256, 16, "cm"), (100, 777, 1, "ft3d"), (100, 777, 5, "grid"),
+    (100, 777, 10, "dup"), (50, 513, 7, "ft3d"), (50, 40, 20, "grid"), (33, 2000, 24, "kitti"), (4, 32, 32, "ft3d"),
+])
+def test_knn_bit_exact_indices_and_distances(s, n, k, mode):
+    cand = _cloud(1, n, 200 + n, mode)
+    if s == n:
+        query = cand.clone()                              # self-query (PointConv, flow estimator)
+    else:
+        query = _cloud(1, max(s, 8), 300 + s, mode)[:, :s].contiguous()
+    idx, dist = K.knn_dist(query.to(DEV), cand.to(DEV), k)
+    ref_i, ref_d = O.knn_with_dist(k, cand, query)
+    assert torch.equal(idx.cpu(), ref_i)                  # same order too: ascending (distance, index)
+    assert torch.equal(dist.cpu(), ref_d)                 # fp32 bit-exact: same rounding sequence
+    i32, i64 = K.knn64(query.to(DEV), cand.to(DEV), k)
+    assert i64.dtype == torch.int64 and torch.equal(i64.cpu(), ref_i.long()) and torch.equal(i32, idx)
+
+
+def test_knn_batched_and_cached():
+    d = make_pairs(3, 1024, seed=9)
+    xyz, q = d["pos1"].to(DEV), d["pos2"][:, :200].contiguous().to(DEV)
+    KF.clear_caches()
+    a = KF.knn_idx(16, xyz, q)
+    b = KF.knn_idx(16, xyz, q)
+    assert a.data_ptr() == b.data_ptr()                  # second call served from the cache
+    assert torch.equal(a.cpu().long(), O.knn_point(16, d["pos1"], q.cpu()))
+    q.add_(1.0)                                           # in-place change bumps the version: no stale hit
+    c = KF.knn_idx(16, xyz, q)
+    assert torch.equal(c.cpu().long(), O.knn_point(16, d["pos1"], q.cpu()))
+    assert KF.knn_point(16, xyz, q).dtype == torch.int64
+
+
+def test_knn_matches_torch_cuda_matmul_topk_chain():
+    """The reference op chain itself, run by torch on this GPU (cuBLAS sgemm + topk): index SETS must
+    agree except where the cuBLAS dot-product rounding flips an exact K-th boundary."""
+    d = make_pairs(2, 4096, seed=17, kind="kitti")
+    xyz, q = d["pos1"].to(DEV), d["pos2"].to(DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dist = -2 * torch.matmul(q, xyz.permute(0, 2, 1))
+    dist += torch.sum(q ** 2, -1).view(2, -1, 1)
+    dist += torch.sum(xyz ** 2, -1).view(2, 1, -1)
+    ref = torch.sort(torch.topk(dist, 16, dim=-1, largest=False, sorted=False)[1], dim=-1)[0]
+    mine = torch.sort(K.knn(q, xyz, 16).long(), dim=-1)[0]
+    bad_rows = (ref != mine).any(dim=-1).float().mean().item()
+    mine_sq = K.square_distance(q, xyz)
+    frac_bits = (mine_sq != dist).float().mean().item()
+    print(f"rows differing from torch-CUDA chain: {bad_rows:.2e}; distance entries differing in bits: {frac_bits:.2e}")
+    assert bad_rows < 2e-3
+
+
+def test_square_distance_bit_exact():
+    d = make_pairs(2, 700, seed=4, kind="kitti")
+    q = d["pos1"][:, :130].contiguous()
+    got = K.square_distance(q.to(DEV), d["pos2"].to(DEV)).cpu()
+    assert torch.equal(got, O.square_distance_c(q, d["pos2"]))
+
+
+# ----------------------------------------------------------------------- three_nn / interpolate
+@pytest.mark.parametrize("n,m,mode", [(8192, 2048, "ft3d"), (1000, 300, "grid"), (257, 2, "ft3d"), (64, 5000, "dup")])
+def test_three_nn_bit_exact(n, m, mode):
+    unknown, known = _cloud(2, n, 1, mode), _cloud(2, m, 2, mode)
+    dist, idx = KF.three_nn(unknown.to(DEV), known.to(DEV))
+    rd, ri = O.three_nn(unknown, known)
+    assert torch.equal(idx.cpu(), ri) and torch.equal(dist.cpu(), rd)
+
+
+def test_three_interpolate_bit_exact_and_grad():
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(2, 19, 300, generator=g)
+    idx = torch.randint(0, 300, (2, 1000, 3), generator=g).int()
+    w = torch.rand(2, 1000, 3, generator=g)
+    fd = f.to(DEV).requires_grad_(True)
+    out = KF.three_interpolate(fd, idx.to(DEV), w.to(DEV))
+    assert torch.equal(out.detach().cpu(), O.three_interpolate(f, idx, w))
+    go = torch.randn(2, 19, 1000, generator=g)
+    out.backward(go.to(DEV))
+    fr = f.clone().requires_grad_(True)
+    ref = (torch.gather(fr.unsqueeze(2).expand(2, 19, 1000, 300), 3, idx.long().unsqueeze(1).expand(2, 19, 1000, 3)) * w.unsqueeze(1)).sum(-1)
+    ref.backward(go)
+    assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------- gather / group (cm)
+def test_gather_and_group_channel_major_exact_and_grad():
+    g = torch.Generator().manual_seed(1)
+    f = torch.randn(3, 13, 500, generator=g)
+    idx = torch.randint(0, 500, (3, 77), generator=g).int()
+    fd = f.to(DEV).requires_grad_(True)
+    out = KF.gather_operation(fd, idx.to(DEV))
+    assert torch.equal(out.detach().cpu(), O.gather_operation(f, idx))
+    go = torch.randn(3, 13, 77, generator=g)
+    out.backward(go.to(DEV))
+    fr = f.clone().requires_grad_(True)
+    O.gather_operation(fr, idx).backward(go)
+    assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-5, atol=1e-6)
+
+    for (c, n, s, k) in [(64, 8192, 2048, 16), (3, 1000, 50, 9), (1, 64, 64, 4), (7, 60000, 10, 3)]:
+        f = torch.randn(2, c, n, generator=g)
+        idx = torch.randint(0, n, (2, s, k), generator=g).int()
+        fd = f.to(DEV).requires_grad_(True)
+        out = KF.grouping_operation(fd, idx.to(DEV))
+        assert torch.equal(out.detach().cpu(), O.grouping_operation(f, idx)), (c, n, s, k)
+        if n <= 8192:
+            go = torch.randn(2, c, s, k, generator=g)
+            out.backward(go.to(DEV))
+            fr = f.clone().requires_grad_(True)
+            O.grouping_operation(fr, idx).backward(go)
+            assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_ball_query_exact():
+    d = make_pairs(2, 1500, seed=6)
+    new_xyz = d["pos1"][:, :333].contiguous()
+    for r, ns in ((1.5, 16), (0.05, 8), (100.0, 32)):
+        got = KF.ball_query(r, ns, d["pos1"].to(DEV), new_xyz.to(DEV)).cpu()
+        assert torch.equal(got, O.ball_query(r, ns, d["pos1"], new_xyz)), (r, ns)
+
+
+# ----------------------------------------------------------------------- point-major gathers
+@pytest.mark.parametrize("c", [3, 64, 131, 20])
+def test_gather_rows_and_group_concat_exact(c):
+    g = torch.Generator().manual_seed(c)
+    d = make_pairs(2, 900, seed=c)
+    xyz, q = d["pos1"], d["pos2"][:, :150].contiguous()
+    feats = torch.randn(2, 900, c, generator=g)
+    idx = torch.randint(0, 900, (2, 150, 16), generator=g).int()
+    got = KF.gather_rows(feats.to(DEV), idx.to(DEV)).cpu()
+    ref = O.index_points_group(feats, idx)
+    assert torch.equal(got, ref)
+    fps = torch.randint(0, 900, (2, 40), generator=g).int()
+    assert torch.equal(KF.gather_rows(feats.to(DEV), fps.to(DEV)).cpu(), O.index_points_gather(feats, fps))
+    gc = KF.group_concat(xyz.to(DEV), q.to(DEV), feats.to(DEV), idx.to(DEV)).cpu()
+    rel = O.index_points_group(xyz, idx) - q.view(2, 150, 1, 3)
+    assert torch.equal(gc, torch.cat([rel, ref], dim=-1))
+    assert torch.equal(KF.group_concat(xyz.to(DEV), q.to(DEV), None, idx.to(DEV)).cpu(), rel)
+
+
+def test_group_concat_backward_is_deterministic_and_correct():
+    g = torch.Generator().manual_seed(3)
+    d = make_pairs(2, 600, seed=8)
+    xyz, q = d["pos1"], d["pos2"][:, :128].contiguous()
+    feats = torch.randn(2, 600, 24, generator=g)
+    idx = O.knn_point(16, xyz, q).int()
+    go = torch.randn(2, 128, 16, 27, generator=g)
+
+    def run():
+        a, b_, c_ = (t.clone().to(DEV).requires_grad_(True) for t in (xyz, q, feats))
+        KF.group_concat(a, b_, c_, idx.to(DEV)).backward(go.to(DEV))
+        return a.grad.cpu(), b_.grad.cpu(), c_.grad.cpu()
+
+    g1, g2 = run(), run()
+    for x, y in zip(g1, g2):
+        assert torch.equal(x, y)                          # bit-identical run to run (no float atomics)
+    a, b_, c_ = (t.clone().requires_grad_(True) for t in (xyz, q, feats))
+    ref = torch.cat([O.index_points_group(a, idx) - b_.view(2, 128, 1, 3), O.index_points_group(c_, idx)], dim=-1)
+    ref.backward(go)
+    for x, y in zip(g1, (a.grad, b_.grad, c_.grad)):
+        assert torch.allclose(x, y, rtol=1e-4, atol=1e-5)
+
+
+def test_build_csr_inverse_index():
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, 300, (3, 70, 9), generator=g).int()
+    off, perm = K.build_csr(idx.to(DEV), 300)
+    off, perm = off.cpu().numpy(), perm.cpu().numpy()
+    flat = idx.reshape(3, -1).numpy()
+    for b in range(3):
+        assert off[b, 0] == 0 and off[b, -1] == flat.shape[1]
+        for i in range(300):
+            seg = perm[b, off[b, i]:off[b, i + 1]]
+            assert np.array_equal(seg, np.nonzero(flat[b] == i)[0])     # ascending members
+
+
+# ----------------------------------------------------------------------- fused layer pieces
+def test_weightnet_and_aggregation():
+    g = torch.Generator().manual_seed(2)
+    for wout in (4, 8, 16):
+        x = torch.randn(2, 50, 9, 35, generator=g)
+        ws = [torch.randn(8, 3, generator=g), torch.randn(8, generator=g), torch.randn(8, 8, generator=g) * 0.5,
+              torch.randn(8, generator=g), torch.randn(wout, 8, generator=g) * 0.5, torch.randn(wout, generator=g)]
+        got = K.weightnet(x.to(DEV), *[w.to(DEV) for w in ws]).cpu()
+        h = torch.relu(x[..., :3] @ ws[0].t() + ws[1])
+        h = torch.relu(h @ ws[2].t() + ws[3])
+        ref = torch.relu(h @ ws[4].t() + ws[5])
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)         # fp32, different summation order
+        grouped = torch.randn(2, 50, 9, 35, generator=g)
+        agg = K.pointconv_agg(grouped.to(DEV), got.to(DEV)).cpu()
+        ref_agg = torch.matmul(grouped.permute(0, 1, 3, 2), got).reshape(2, 50, -1)   # pointconv_util.py:249
+        assert torch.allclose(agg, ref_agg, rtol=1e-5, atol=1e-5)
+
+
+def test_costvol_pre_and_max_over_k():
+    g = torch.Generator().manual_seed(4)
+    d = make_pairs(2, 400, seed=10)
+    x1, x2 = d["pos1"][:, :100].contiguous(), d["pos2"]
+    D = 32
+    p1, p2 = torch.randn(2, 100, D, generator=g), torch.randn(2, 400, D, generator=g)
+    idx = O.knn_point(16, x2, x1).int()
+    pw, pb = torch.randn(D, 3, generator=g), torch.randn(D, generator=g)
+    got = K.costvol_pre(*[t.to(DEV) for t in (x1, x2, p1, p2, idx, pw, pb)], 0.1).cpu()
+    rel = O.index_points_group(x2, idx) - x1.view(2, 100, 1, 3)
+    ref = torch.nn.functional.leaky_relu(O.index_points_group(p2, idx) + p1.view(2, 100, 1, D) + rel @ pw.t() + pb, 0.1)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    mx, arg = K.max_over_k(got.to(DEV))
+    rm, ra = ref.max(dim=2)
+    assert torch.allclose(mx.cpu(), rm, rtol=1e-5, atol=1e-5)
+    assert torch.equal(torch.gather(got, 2, arg.cpu().long().unsqueeze(2)).squeeze(2), mx.cpu())
+
+
+@pytest.mark.parametrize("c", [3, 64, 30])
+def test_interp3_matches_oracle_and_grad(c):
+    g = torch.Generator().manual_seed(c)
+    d = make_pairs(2, 800, seed=12)
+    dense = d["pos1"]
+    sparse = dense[:, ::4].contiguous()
+    feat = torch.randn(2, 200, c, generator=g)
+    idx = KF.knn_idx(3, sparse.to(DEV), dense.to(DEV))
+    fd = feat.to(DEV).requires_grad_(True)
+    out = KF.interp3(dense.to(DEV), sparse.to(DEV), idx, fd)
+    ref = O.upsample_flow(dense.permute(0, 2, 1), sparse.permute(0, 2, 1), feat.permute(0, 2, 1)).permute(0, 2, 1)
+    assert torch.allclose(out.detach().cpu(), ref, rtol=1e-5, atol=1e-6)    # tolerance: fp32 weights, 1 ulp sqrt/div
+    comp = KF.interp3_composite(dense.to(DEV), sparse.to(DEV), idx, feat.to(DEV))
+    assert torch.allclose(comp.cpu(), ref, rtol=1e-5, atol=1e-6)
+    go = torch.randn(2, 800, c, generator=g)
+    out.backward(go.to(DEV))
+    fr = feat.clone().requires_grad_(True)
+    O.upsample_flow(dense.permute(0, 2, 1), sparse.permute(0, 2, 1), fr.permute(0, 2, 1)).permute(0, 2, 1).backward(go)
+    assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-4, atol=1e-5)

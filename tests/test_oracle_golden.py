@@ -1,0 +1,122 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the unmodified
+reference (tests/make_golden.py), and the oracle's internal consistency."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as O
+from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+
+T = torch.from_numpy
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def test_square_distance_and_knn_match_reference(golden):
+    g = golden("knn")
+    q, c = T(g["query"]), T(g["cand"])
+    # bit-exact: the scalar-C evaluation order equals what torch's matmul expansion produced
+    assert np.array_equal(O.square_distance_c(q, c).numpy(), g["sqdist"])
+    for k in (3, 9, 16, 32):
+        mine = torch.sort(O.knn_point(k, c, q), dim=-1)[0].numpy()
+        assert np.array_equal(mine, g[f"knn{k}"])
+
+
+def test_knn_oracle_is_sorted_by_distance_then_index():
+    g = torch.Generator().manual_seed(3)
+    cloud = torch.randint(0, 6, (1, 300, 3), generator=g).float()   # integer grid: many exact ties
+    idx, dist = O.knn_with_dist(16, cloud, cloud[:, :50].contiguous())
+    dd, ii = dist.numpy(), idx.numpy()
+    assert np.all(np.diff(dd, axis=-1) >= 0)
+    tie = np.diff(dd, axis=-1) == 0
+    assert tie.any() and np.all(np.diff(ii, axis=-1)[tie] > 0)
+
+
+@pytest.mark.parametrize("n,m", [(256, 64), (512, 256), (1000, 100), (2048, 512), (37, 9)])
+def test_fps_literal_simulation_equals_closed_form_tie_rule(n, m):
+    # integer-grid clouds are full of exact distance ties; duplicates too
+    g = torch.Generator().manual_seed(n)
+    xyz = torch.randint(0, 4, (2, n, 3), generator=g).float()
+    a = O.furthest_point_sample(xyz, m)
+    b = O.furthest_point_sample(xyz, m, closed_form=True)
+    assert torch.equal(a, b)
+    assert (a[:, 0] == 0).all()
+
+
+def test_fps_tie_rule_is_not_lowest_index():
+    # the reference's left-biased tree picks bit-reversed thread order, not the lowest index
+    xyz = torch.zeros(1, 8, 3)
+    xyz[0, 1:, 0] = 1.0                                 # points 1..7 all at distance 1 from point 0
+    idx = O.furthest_point_sample(xyz, 2)
+    assert idx[0, 1].item() == 4                        # bitrev3: 4 -> 001 is the smallest non-zero key
+
+
+def test_three_nn_oracle_properties():
+    d = make_pairs(2, 128, seed=5)
+    dist, idx = O.three_nn(d["pos1"], d["pos2"])
+    assert dist.shape == (2, 128, 3) and idx.dtype == torch.int32
+    assert (dist[..., 0] <= dist[..., 1]).all() and (dist[..., 1] <= dist[..., 2]).all()
+    brute = torch.cdist(d["pos1"], d["pos2"]).topk(3, largest=False)[0]
+    assert torch.allclose(dist, brute, atol=1e-3)      # cdist uses the matmul expansion (less exact)
+
+
+def _sd(module_keys, seed, prefix):
+    ref = {k: torch.zeros(v) for k, v in module_keys.items()}
+    return {prefix + k: v for k, v in synthetic_state_dict(ref, seed).items()}
+
+
+def _shapes(module):
+    return {k: tuple(v.shape) for k, v in module.state_dict().items()}
+
+
+def test_layers_match_reference_golden(golden):
+    from kd_pointcloud_b200 import pointconv_util as P   # only used for parameter shapes (CPU, no kernels)
+
+    g = golden("weightnet")
+    sd = _sd(_shapes(P.WeightNet(3, 16)), 1, "w.")
+    assert _rel(O.weightnet(sd, "w", T(g["localized_xyz"])), g["out"]) < 1e-6
+
+    g = golden("pointconv")
+    sd = _sd(_shapes(P.PointConv(9, 32, 24, bn=True)), 2, "p.")
+    assert _rel(O.pointconv(sd, "p", 9, T(g["xyz"]), T(g["points"]), bn=True), g["out"]) < 1e-5
+
+    g = golden("pointconvd")
+    sd = _sd(_shapes(P.PointConvD(64, 16, 32, 40)), 3, "p.")
+    nx, ny, fi = O.pointconvd(sd, "p", 64, 16, T(g["xyz"]), T(g["points"]))
+    assert np.array_equal(fi.numpy(), g["fps_idx"]) and np.array_equal(nx.numpy(), g["new_xyz"])
+    assert _rel(ny, g["out"]) < 1e-5
+
+    g = golden("crosslayer")
+    sd = _sd(_shapes(P.CrossLayerLight(32, 24, [16, 16], [16, 16])), 4, "c.")
+    outs = O.cross_layer_light(sd, "c", 32, T(g["pc1"]), T(g["pc2"]), T(g["feat1"]), T(g["feat2"]))
+    for o, name in zip(outs, ("out1", "out2", "out3")):
+        assert _rel(o, g[name]) < 1e-5
+
+    g = golden("warp_upsample")
+    assert _rel(O.point_warping(T(g["pc1"]), T(g["pc2"]), T(g["flow1"])), g["warped"]) < 1e-6
+    assert _rel(O.upsample_flow(T(g["pc1"]), T(g["sparse_xyz"]), T(g["sparse_flow"])), g["up"]) < 1e-6
+
+    g = golden("flow_estimator")
+    sd = _sd(_shapes(P.SceneFlowEstimatorResidual(24, 16, channels=[32, 32], mlp=[32, 16])), 5, "e.")
+    f, fl = O.scene_flow_estimator_residual(sd, "e", T(g["xyz"]), T(g["feats"]), T(g["cost"]), T(g["flow"]))
+    assert _rel(f, g["out_feat"]) < 1e-5 and _rel(fl, g["out_flow"]) < 1e-5
+
+    g = golden("multiscale_loss")
+    l = O.multi_scale_loss([T(g["p0"]), T(g["p1"]), T(g["p2"])], T(g["gt"]), [T(g["fps1"]), T(g["fps2"])])
+    assert _rel(l, g["loss"]) < 1e-6
+
+
+def test_state_dict_keys_match_reference():
+    from kd_pointcloud_b200.flownet import PointConvBidirection
+    with open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")) as f:
+        ref = json.load(f)
+    mine = {k: list(v.shape) for k, v in PointConvBidirection().state_dict().items()}
+    assert list(mine) == list(ref)
+    assert mine == ref
+    assert sum(int(np.prod(v)) for k, v in mine.items() if "running" not in k and "tracked" not in k) == 7958604
