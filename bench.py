@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: scene-flow pairs/s @ 8192 points (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU arm (oracle port)
+
+Workload (configs[2]): Bi-PointFlowNet (teacher, models_bid_pointconv.PointConvBidirection) eval
+forward + EPE3D on FlyingThings3D-shaped synthetic 8192-point pairs, B = 8 per GPU, seeded
+synthetic weights.  One step = one forward over one batch.  N > 1: pairs are independent, so the
+batch is sharded over ranks with NO data-path collective (weak scaling); the only collective is
+the timing reduction.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scene-flow pairs/sec @8192 pts"
+UNIT = "pairs/s"
+NPOINTS = 8192
+MODEL_SEED = 7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kdpc", choices=["kdpc", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also print per-kernel roofline lines to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mx = float(parts[1])
+                if t0 - 0.1 <= t <= t1 + 0.1:
+                    sm.append(float(parts[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:                                       # timed region shorter than the sampling period
+            for t, line in self.rows[-3:]:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_reference_forward(steps: int, warmup: int, seed0: int = 1234):
+    """The reference's own algorithm on the host CPU: oracle/layers_ref.py (a restatement of
+    pointconv_util.py / models_bid_pointconv.py pinned against the unmodified reference by
+    tests/make_golden.py; kNN = matmul expansion + topk exactly as the reference does it;
+    FPS/gather/group from oracle/kdpc_oracle.c because the reference has no CPU version).
+    One step = ONE pair (B=1) at 8192 points — a bounded sample of the B=8 workload."""
+    import torch
+    from oracle import layers_ref as O
+    from kd_pointcloud_b200.flownet import PointConvBidirection
+    from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic_state_dict(PointConvBidirection().state_dict(), MODEL_SEED)
+    times = []
+    epe = None
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            d = make_pairs(1, NPOINTS, seed=seed0 + i)
+            t0 = time.perf_counter()
+            flows = O.bid_pointconv_forward(sd, d["pos1"], d["pos2"], d["color1"], d["color2"], knn_impl="torch")[0]
+            epe = torch.norm(flows[0].permute(0, 2, 1) - d["flow"], dim=2).mean().item()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / max(len(times), 1)
+    return 1.0 / sec, sec, torch.get_num_threads(), epe
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, sec, cores, _ = cpu_reference_forward(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: Bi-PointFlowNet teacher eval forward + EPE3D, FlyingThings3D-shaped synthetic "
+                               "8192-pt pairs, seeded synthetic weights", "npoints": NPOINTS, "pairs_per_step": 1,
+                   "host": "CPU only"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 pair (B=1) per step of the B=8 workload; oracle/layers_ref.py with torch matmul+topk kNN"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- our arm
+def kernel_rooflines(torch, dev, B, hbm_peak):
+    """Live CUDA-event timing of the HBM-bound kernels at their largest model shapes, and of the
+    kNN at l0.  Algorithmic bytes per SURVEY 8(d) / DESIGN.md."""
+    from kd_pointcloud_b200 import functional as KF
+    from kd_pointcloud_b200.synth import make_pairs
+    K = torch.ops.kdpc
+    d = make_pairs(B, NPOINTS, seed=99, device=dev)
+    xyz, xyz2 = d["pos1"], d["pos2"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=8):
+        fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()                                  # evict L2 (126 MB) between timed launches
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3
+
+    out = {}
+    N, Kn, D = NPOINTS, 9, 128                             # flow0 PointConv grouping: [8,8192,9,131]
+    idx9 = K.knn(xyz, xyz, Kn)
+    feats = torch.randn(B, N, D, device=dev)
+    t = timeit(lambda: K.group_concat(xyz, xyz, feats, idx9))
+    alg = B * (4 * N * Kn + 12 * (N + N) + 4 * N * D + 4 * N * Kn * (D + 3))
+    out["group_concat"] = {"shape": f"B={B} S=N={N} K={Kn} D={D}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    idx32 = None
+    for kk in (32, 16, 9, 3):
+        t = timeit(lambda: K.knn(xyz2, xyz, kk), iters=5)
+        algk = B * (12 * (N + N) + 4 * N * kk)
+        out[f"knn_k{kk}"] = {"shape": f"B={B} S=N={N} K={kk}", "bytes": algk, "sec": t, "gbs": algk / t / 1e9,
+                             "gpairs_per_s": B * N * N / t / 1e9}
+    idx32 = K.knn(xyz2, xyz, 32)
+    p1, p2 = torch.randn(B, N, 32, device=dev), torch.randn(B, N, 32, device=dev)
+    pw, pb = torch.randn(32, 3, device=dev), torch.randn(32, device=dev)
+    t = timeit(lambda: K.costvol_pre(xyz2, xyz, p1, p2, idx32, pw, pb, 0.1))
+    algc = B * (4 * N * 32 + 24 * N + 2 * 4 * N * 32 + 4 * N * 32 * 32)
+    out["costvol_pre"] = {"shape": f"B={B} N={N} K=32 D=32", "bytes": algc, "sec": t, "gbs": algc / t / 1e9}
+    t = timeit(lambda: K.fps(xyz, 2048), iters=3)
+    out["fps_8192_2048"] = {"shape": f"B={B} 8192->2048", "sec": t, "us_per_iter": t / 2047 * 1e6,
+                            "bytes": B * (12 * N + 4 * 2048), "gbs": B * (12 * N + 4 * 2048) / t / 1e9}
+    for k, v in out.items():
+        v["frac_hbm"] = v["gbs"] / hbm_peak
+    return out
+
+
+def run_kdpc(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=kdpc) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False          # fp32 parity with the reference
+    torch.backends.cudnn.allow_tf32 = False
+
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from kd_pointcloud_b200 import ops
+    from kd_pointcloud_b200.flownet import PointConvBidirection
+    from kd_pointcloud_b200.runner import FlowRunner, KEYS
+    from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+
+    B = args.batch
+    model = PointConvBidirection()
+    model.load_state_dict(synthetic_state_dict(model.state_dict(), MODEL_SEED))
+    model = model.to(dev).eval()
+
+    # a pool of DIFFERENT batches (per rank, per step) so nothing can be cached across steps
+    pool = 4
+    host = [{k: v.pin_memory() for k, v in make_pairs(B, NPOINTS, seed=1234 + 1000 * rank + i).items()} for i in range(pool)]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+
+    runner = FlowRunner(model, B, NPOINTS, dev, use_graph=not args.no_graph)
+    graphed = runner.warmup_and_capture(resident[0], warmup=2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (value) -------------------------------------
+    for i in range(args.warmup):
+        runner.load(resident[i % pool])
+        runner.step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    evs = []
+    launches0 = ops.LAUNCHES
+    for i in range(args.steps):
+        runner.load(resident[i % pool])                    # device->device, outside the timed events
+        flush.zero_()                                      # evict L2 between timed iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        runner.step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    eager_launches = ops.LAUNCHES - launches0
+    launches = runner.launches_per_step * args.steps if graphed else eager_launches
+    epe_last = float(runner.out_epe.item())
+
+    # ---------------- end to end through the public call, host buffers --------------------------
+    for i in range(min(2, args.warmup)):
+        runner.run_host(host[i % pool])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        runner.run_host(host[i % pool])
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
+    dev_ms, e2e_ms = t.tolist()
+
+    h2d = sum(host[0][k].numel() * 4 for k in KEYS)
+    line = None
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        ms_step = dev_ms / args.steps
+        value = B * world / (ms_step * 1e-3)
+        e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+        kr = kernel_rooflines(torch, dev, B, hbm_peak)
+        gc = kr["group_concat"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: Bi-PointFlowNet teacher eval forward + EPE3D, FlyingThings3D-shaped synthetic "
+                                   "8192-pt pairs, seeded synthetic weights", "npoints": NPOINTS, "pairs_per_gpu_per_step": B,
+                       "global_pairs_per_step": B * world, "sharding": "batch-sharded, no collectives",
+                       "cuda_graph": bool(graphed), "l2": "256 MB flush between timed iterations",
+                       "epe3d_last_step": epe_last},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "group_concat_kernel (kNN-indexed gather + rel-xyz + concat, flow0 shape)",
+                         "bound": "hbm", "achieved": gc["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gc["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": gc["bytes"]},
+            "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, sec, cores, _ = cpu_reference_forward(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "2 timed forwards of 1 pair (B=1, 8192 pts) after 1 warm-up; oracle/layers_ref.py"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_kdpc(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,20 @@
 #define KDPC_CHECK_ARGS(cond) do { if (!(cond)) return KDPC_EINVAL; } while (0)
 #define KDPC_RETURN_LAST() return (int)cudaGetLastError()
 
+// Opt in to > 48 KB dynamic shared memory ONCE per (kernel, device): keeps cudaFuncSetAttribute out of
+// the steady state (and out of CUDA-graph capture after the warm-up run).
+#define KDPC_ENSURE_SMEM(kern, bytes)                                                               \
+    do {                                                                                            \
+        static int done_[64];                                                                       \
+        int dev_ = 0;                                                                               \
+        cudaGetDevice(&dev_);                                                                       \
+        if (dev_ < 0 || dev_ >= 64 || !done_[dev_]) {                                               \
+            cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+            if (e_ != cudaSuccess) return (int)e_;                                                  \
+            if (dev_ >= 0 && dev_ < 64) done_[dev_] = 1;                                            \
+        }                                                                                           \
+    } while (0)
+
 static inline cudaStream_t to_stream(kdpc_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline long long div_up_ll(long long a, long long b) { return (a + b - 1) / b; }
@@ -57,7 +71,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    // bounded: a lost TMA completion traps (launch error) instead of hanging the GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {

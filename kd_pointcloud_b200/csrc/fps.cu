@@ -139,8 +139,7 @@ template <int PPT>
 static int launch_smem(int b, int n, int m, int bs, int lg, const float *xyz, float *temp, int *idx,
                        cudaStream_t st) {
     size_t smem = (size_t)3 * n * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(fps_smem_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    KDPC_ENSURE_SMEM((fps_smem_kernel<PPT>), 3 * 8192 * (int)sizeof(float));     // largest cloud of the register path
     fps_smem_kernel<PPT><<<b, bs, smem, st>>>(n, m, lg, xyz, temp, idx);
     return (int)cudaGetLastError();
 }

@@ -117,7 +117,7 @@ group_concat_kernel(long long rows, int n, int s, int k, int d, const float *__r
     }
     __syncthreads();
     if (d > 0) {
-        const long long b = r0 / ((long long)s * k);      // rows of one CTA may straddle a batch edge
+        // rows of one CTA may straddle a batch edge: the batch index is derived per row
         if ((d & 3) == 0) {
             const int dv = d >> 2;
             for (int e = tid; e < nr * dv; e += GC_THREADS) {
@@ -134,7 +134,6 @@ group_concat_kernel(long long rows, int n, int s, int k, int d, const float *__r
                 stage[rl * w + 3 + ci] = __ldg(feats + ((size_t)bb * n + src_s[rl]) * d + ci);
             }
         }
-        (void)b;
     }
     __syncthreads();
     const long long o0 = r0 * w;                          // multiple of 4 floats (GC_ROWS % 4 == 0)
@@ -212,8 +211,7 @@ KDPC_API int kdpc_group(int b, int c, int n, int s, int k, const float *f, const
     constexpr int CPB = 4;
     const size_t smem = (size_t)CPB * n * sizeof(float);
     if (smem <= 200 * 1024 && c >= 2) {
-        cudaError_t e = cudaFuncSetAttribute(group_cm_smem_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+        KDPC_ENSURE_SMEM((group_cm_smem_kernel<CPB>), 200 * 1024);
         const int cgroups = (c + CPB - 1) / CPB;
         // enough CTAs to cover the 148 SMs, but each one must amortise staging its channel rows
         int split = (2 * kNumSMs + cgroups * b - 1) / (cgroups * b);
@@ -252,8 +250,7 @@ KDPC_API int kdpc_group_concat(int b, int n, int s, int k, int d, const float *c
     const long long rows = (long long)b * s * k;
     const size_t smem = (size_t)GC_ROWS * (3 + d) * sizeof(float);
     if (smem > 200 * 1024) return KDPC_EUNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(group_concat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    KDPC_ENSURE_SMEM(group_concat_kernel, 200 * 1024);
     group_concat_kernel<<<(unsigned)div_up_ll(rows, GC_ROWS), GC_THREADS, smem, to_stream(stream)>>>(
         rows, n, s, k, d, cand_xyz, query_xyz, feats, idx, out);
     KDPC_RETURN_LAST();

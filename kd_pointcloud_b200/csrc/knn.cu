@@ -171,8 +171,7 @@ static int launch_knn(int b, int s, int n, int k, const float *query, const floa
     dim3 grid((s + KNN_THREADS - 1) / KNN_THREADS, b);
 #define KDPC_KNN_CASE(KT) \
     if (k <= KT) { \
-        cudaError_t e = cudaFuncSetAttribute(knn_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KNN_SMEM_BYTES); \
-        if (e != cudaSuccess) return (int)e; \
+        KDPC_ENSURE_SMEM((knn_kernel<KT, MODE>), KNN_SMEM_BYTES); \
         knn_kernel<KT, MODE><<<grid, KNN_THREADS, KNN_SMEM_BYTES, st>>>(s, n, k, query, c4, idx32, idx64, dist); \
         return (int)cudaGetLastError(); }
     KDPC_KNN_CASE(1)

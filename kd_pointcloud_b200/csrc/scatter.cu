@@ -140,8 +140,7 @@ scatter_cm_csr_kernel(int c, int n, int m, int gdiv, const float *__restrict__ g
 static int build_csr(int b, int n, int m, const int *idx, int *offsets, int *perm, cudaStream_t st) {
     const size_t smem = (size_t)n * sizeof(int);
     if (smem > 200 * 1024) return KDPC_EUNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(build_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    KDPC_ENSURE_SMEM(build_csr_kernel, 200 * 1024);
     build_csr_kernel<<<b, CSR_THREADS, smem, st>>>(n, m, idx, offsets, perm);
     return (int)cudaGetLastError();
 }
