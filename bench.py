@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernels", action="store_true", help="also print per-kernel roofline lines to stderr")
+    ap.add_argument("--profile-one", action="store_true",
+                    help="run ONE eager forward between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     return ap.parse_args()
 
 
@@ -71,10 +72,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout: float = 5.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.05)
+
     def stop(self, t0: float, t1: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         for t, line in self.rows:
@@ -226,6 +232,7 @@ def run_kdpc(args):
     from kd_pointcloud_b200.runner import FlowRunner, KEYS
     from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes ~1 s to emit
     B = args.batch
     model = PointConvBidirection()
     model.load_state_dict(synthetic_state_dict(model.state_dict(), MODEL_SEED))
@@ -235,6 +242,18 @@ def run_kdpc(args):
     pool = 4
     host = [{k: v.pin_memory() for k, v in make_pairs(B, NPOINTS, seed=1234 + 1000 * rank + i).items()} for i in range(pool)]
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+
+    if args.profile_one:
+        runner = FlowRunner(model, B, NPOINTS, dev, use_graph=False)
+        runner.warmup_and_capture(resident[0], warmup=2)
+        runner.load(resident[1])
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        runner.step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_one": True, "kdpc_calls": runner.launches_per_step, "epe3d": float(runner.out_epe.item())}))
+        return
 
     runner = FlowRunner(model, B, NPOINTS, dev, use_graph=not args.no_graph)
     graphed = runner.warmup_and_capture(resident[0], warmup=2)
@@ -251,7 +270,8 @@ def run_kdpc(args):
         runner.load(resident[i % pool])
         runner.step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     t_wall0 = time.time()
     evs = []
     launches0 = ops.LAUNCHES

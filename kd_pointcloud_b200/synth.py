@@ -83,7 +83,7 @@ def synthetic_state_dict(reference_state: Dict[str, torch.Tensor], seed: int = 0
             for s in shape[1:]:
                 fan_in *= s
             bound = 1.0 / math.sqrt(max(fan_in, 1))
-            out[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound * 1.7
+            out[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound          # torch's default U(-1/sqrt(fan_in), ..)
         else:
             # biases / BN affine
             if "bn" in key and key.endswith("weight"):

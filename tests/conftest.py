@@ -15,6 +15,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # fp32 parity: keep torch's own GEMMs/convs (test helpers, 1x1 convs) out of TF32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

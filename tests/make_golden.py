@@ -188,19 +188,27 @@ def main():
     d = make_pairs(1, 4096, seed=21)
     out = model(d["pos1"], d["pos2"], d["color1"], d["color2"])
     flows, fps1, fps2, pcs1, pcs2, feat1s, feat2s, crosses = out
-    o = O.bid_pointconv_forward(sd, d["pos1"], d["pos2"], d["color1"], d["color2"])
-    for i in range(4):
-        close(o[0][i], flows[i], 2e-4, f"model flow{i}")
+    # (1) same op chain incl. torch matmul+topk kNN: the restatement must be BIT-IDENTICAL to the reference
+    o = O.bid_pointconv_forward(sd, d["pos1"], d["pos2"], d["color1"], d["color2"], knn_impl="torch")
+    for grp in (0, 5, 6, 7):
+        for a, b in zip(o[grp], out[grp]):
+            close(a, b, 0.0, f"model output group {grp} (torch-kNN oracle)")
     for i in range(3):
         close(o[1][i], fps1[i], what=f"model fps1[{i}]")
         close(o[2][i], fps2[i], what=f"model fps2[{i}]")
-    for i in range(7):
-        close(o[5][i], feat1s[i], 2e-4, f"model feat1s[{i}]")
-        close(o[6][i], feat2s[i], 2e-4, f"model feat2s[{i}]")
-    for i in range(4):
-        close(o[7][i], crosses[i], 2e-4, f"model cross{i}")
+    # (2) with the (distance,index) kNN of the C oracle / CUDA kernel: identical except where the
+    # matmul-expansion rounding of torch's large-matrix sgemm flips a K-th-boundary neighbour
+    # (|q|^2 ~ 1e3 against d^2 ~ 1e-2: the expansion carries ~1e-4 absolute noise).  Those flips
+    # change isolated elements; require < 0.5 % of elements off by more than 1e-4 of the range.
+    o = O.bid_pointconv_forward(sd, d["pos1"], d["pos2"], d["color1"], d["color2"], knn_impl="c")
+    for grp in (0, 5, 6, 7):
+        for a, b in zip(o[grp], out[grp]):
+            bad = ((a - b).abs() > 1e-4 * b.abs().max()).float().mean().item()
+            assert bad < 5e-3, f"model output group {grp}: {bad:.2e} of elements differ"
+    o_epe = torch.norm(o[0][0].permute(0, 2, 1) - d["flow"], dim=2).mean()
     loss = RL.multiScaleLoss(flows, d["flow"], fps1)
     epe = torch.norm(flows[0].permute(0, 2, 1) - d["flow"], dim=2).mean()
+    assert abs(o_epe.item() - epe.item()) < 1e-4, "EPE3D of the (distance,index)-kNN oracle differs by more than 1e-4 m"
     save("model_teacher_n4096", flow0=flows[0], flow1=flows[1], flow2=flows[2], flow3=flows[3],
          fps1_0=fps1[0], fps1_1=fps1[1], fps1_2=fps1[2], fps2_0=fps2[0], fps2_1=fps2[1], fps2_2=fps2[2],
          cross3=crosses[3], feat1_l3_4=feat1s[3], loss=loss, epe3d=epe)

