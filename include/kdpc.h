@@ -126,6 +126,27 @@ int kdpc_max_over_k(long long rows, int k, int d, const float *in, float *out, i
 int kdpc_interp3(int b, int n, int s, int c, const float *q_xyz, const float *c_xyz, const int *idx,
                  const float *feat, float *out, float *w_out, kdpc_stream_t stream);
 
+/* ---- tensor-core (tcgen05) layers ------------------------------------------------------- */
+
+/* Pack fp32 weights [N, K_src] (nn.Linear / 1x1-conv layout) into the bf16 hi/lo SWIZZLE_128B chunk
+ * images the tcgen05 kernels stream with bulk TMA.  mode 0: plain (K_packed = K_src).  mode 1:
+ * PointConv.linear (pointconv_util.py:223,250) for the fused kernel: channel order [features(d),
+ * dx,dy,dz,0] x wn, K_src = (d+3)*wn, K_packed = (d+4)*wn.  out: kdpc_packed_weight_bytes(N, K_packed). N <= 256. */
+long long kdpc_packed_weight_bytes(int n, int k_packed);
+int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const float *w, void *out, kdpc_stream_t stream);
+
+/* y[M, ldo] = clamp(leaky(x[M, ldx(K)] W^T * scale + shift, slope), lo, hi) + residual    (N <= 256).
+ * scale / shift / residual may be NULL; slope = 1 disables the activation; lo > hi disables the clamp.
+ * Replaces nn.Linear / 1x1 Conv1d / Conv2d (+ eval BatchNorm + LeakyReLU) of pointconv_util.py:20-54,250-256,
+ * 1797-1821, 2229-2255.  x, out and wpacked must be 16-byte aligned. */
+int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const void *wpacked,
+                   const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
+                   const float *residual, float *out, int ldo, kdpc_stream_t stream);
+/* Same contract on CUDA cores, for layers too small for a 128-row MMA tile (K < 16 or N < 16). w fp32 [N,K]. */
+int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const float *w,
+                     const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
+                     const float *residual, float *out, int ldo, kdpc_stream_t stream);
+
 /* ---- deterministic backward plumbing ------------------------------------------------- */
 
 /* Inverse of an index list: idx int32 [B,M] with values in [0,N)  ->  offsets int32 [B,N+1] and

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libkdpc.so")
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "loss.cu", "pointconv_fused.cu"]
+           "scatter.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 
@@ -28,7 +28,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "kdpc.h")]
+    deps = sources() + [os.path.join(_HERE, "..", "include", "kdpc.h")]
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -66,6 +66,9 @@ _SIGNATURES = {
     "kdpc_costvol_pre": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
     "kdpc_max_over_k": [c_longlong, c_int, c_int, _P, _P, _P, _P],
     "kdpc_interp3": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_pack_weight": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "kdpc_linear_tc": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
+    "kdpc_linear_simt": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
 }
@@ -89,6 +92,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_abi_version.restype = c_int
         L.kdpc_error_string.restype = c_char_p
         L.kdpc_error_string.argtypes = [c_int]
+        L.kdpc_packed_weight_bytes.restype = c_longlong
+        L.kdpc_packed_weight_bytes.argtypes = [c_int, c_int]
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -98,7 +103,7 @@ def lib() -> ctypes.CDLL:
 
 
 def exported_symbols():
-    return ["kdpc_abi_version", "kdpc_error_string"] + list(_SIGNATURES)
+    return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -1,0 +1,144 @@
+// Fused linear layers on tcgen05 (sm_100a):  y = clamp(act((x W^T) * scale + shift)) (+ residual)
+//
+// Replaces the cuBLAS fp32 SIMT GEMMs behind the reference's 1x1 convolutions / nn.Linear
+// (Conv1d/Conv2d wrappers pointconv_util.py:20-54, PointConv.linear :250, cross_t* :1800-1811,
+// SceneFlowEstimatorResidual.fc :2234) with ONE kernel per layer: bias, eval-mode BatchNorm,
+// LeakyReLU, clamp and the residual add ride in the epilogue.  Accuracy: bf16 hi/lo split, three
+// MMAs per K-step, fp32 accumulation in TMEM (tc_common.cuh).
+//
+// Tiny layers (K < 16 or N < 16: level0 3->32, fc 64->3) are issue-/HBM-bound, not GEMM-shaped:
+// they use a SIMT kernel with the same epilogue.
+#include "tc_gemm.cuh"
+
+namespace kdpc {
+namespace tc {
+
+// Pack fp32 weights [N, K_src] (row-major, nn.Linear / 1x1 conv layout) into per-chunk SWIZZLE_128B
+// bf16 hi/lo tile images: out[chunk][part][n_pad][128 B].
+//   mode 0: packed column kc <- source column kc.
+//   mode 1 (PointConv, weightnet width wn): the fused kernel orders channels as
+//           [features 0..D-1, dx, dy, dz, zero] (so that feature rows gather as aligned float4),
+//           while the reference concatenates [dx,dy,dz, features] (pointconv_util.py:153,178) and
+//           flattens c-major with wn innermost (:249).  packed kc = c'*wn + w  <-  source (c*wn + w)
+//           with c = c'+3 for c' < D, c = c'-D for D <= c' < D+3, zero for c' = D+3.
+__global__ void pack_weight_kernel(int n, int k_src, int n_pad, int num_chunks, int mode, int d, int wn,
+                                   const float *__restrict__ w, unsigned char *__restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (chunk, row, unit)
+    const long long total = (long long)num_chunks * n_pad * 8;
+    if (e >= total) return;
+    const int u = (int)(e & 7);
+    const int row = (int)((e >> 3) % n_pad);
+    const int chunk = (int)((e >> 3) / n_pad);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kc = chunk * CHUNK_K + u * 8 + j;
+        int src = -1;
+        if (mode == 0) {
+            src = kc < k_src ? kc : -1;
+        } else {
+            const int cp = kc / wn, wi = kc - cp * wn;
+            if (cp < d) src = (cp + 3) * wn + wi;
+            else if (cp < d + 3) src = (cp - d) * wn + wi;
+        }
+        v[j] = (row < n && src >= 0) ? w[(size_t)row * k_src + src] : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    unsigned char *base = out + (size_t)chunk * (2 * n_pad * 128);
+    const uint32_t off = sw128_offset(row, u);
+    *reinterpret_cast<uint4 *>(base + off) = hi;
+    *reinterpret_cast<uint4 *>(base + (size_t)n_pad * 128 + off) = lo;
+}
+
+// SIMT path for tiny layers: thread = (row, group of 4 outputs).
+__global__ void __launch_bounds__(256)
+linear_simt_kernel(long long m, int n, int k, const float *__restrict__ x, int ldx, const float *__restrict__ w,
+                   const float *__restrict__ scale, const float *__restrict__ shift, float slope, float lo, float hi,
+                   const float *__restrict__ residual, float *__restrict__ out, int ldo) {
+    const int ng = (n + 3) >> 2;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m * ng) return;
+    const long long row = e / ng;
+    const int n0 = (int)(e - row * ng) * 4;
+    const float *xr = x + row * ldx;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kk = 0; kk < k; ++kk) {
+        const float xv = __ldg(xr + kk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n0 + j < n) acc[j] = fmaf(xv, __ldg(w + (size_t)(n0 + j) * k + kk), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int col = n0 + j;
+        if (col < n) {
+            float y = acc[j];
+            if (scale) y *= __ldg(scale + col);
+            if (shift) y += __ldg(shift + col);
+            y = y > 0.f ? y : y * slope;
+            if (lo <= hi) y = fminf(fmaxf(y, lo), hi);
+            if (residual) y += __ldg(residual + row * ldo + col);
+            out[row * ldo + col] = y;
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace kdpc
+
+using namespace kdpc;
+using namespace kdpc::tc;
+
+KDPC_API long long kdpc_packed_weight_bytes(int n, int k_packed) {
+    const int n_pad = (n + 15) / 16 * 16;
+    const int chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
+    return (long long)chunks * 2 * n_pad * 128;
+}
+
+KDPC_API int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const float *w, void *out,
+                              kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(w && out && n > 0 && k_src > 0);
+    if (n > 256) return KDPC_EUNSUPPORTED;
+    int k_packed = k_src;
+    if (mode == 1) {
+        KDPC_CHECK_ARGS(d >= 0 && wn > 0 && k_src == (d + 3) * wn);
+        k_packed = (d + 4) * wn;
+    }
+    if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return KDPC_EINVAL;
+    const int n_pad = (n + 15) / 16 * 16;
+    const int chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
+    const long long total = (long long)chunks * n_pad * 8;
+    pack_weight_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
+        n, k_src, n_pad, chunks, mode, d, wn, w, reinterpret_cast<unsigned char *>(out));
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const void *wpacked,
+                            const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
+                            const float *residual, float *out, int ldo, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(x && wpacked && out && m > 0 && n > 0 && k > 0 && ldx >= k && ldo >= n);
+    if (n > 256) return KDPC_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) % 16) != 0 || (reinterpret_cast<uintptr_t>(out) % 16) != 0 ||
+        (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0)
+        return KDPC_EINVAL;
+    GemmShape g = make_shape(m, n, k, wpacked);
+    const size_t smem = smem_bytes(g.n_pad, g.stages);
+    auto kern = tc_gemm_kernel<PlainProducer, StoreEpilogue>;
+    KDPC_ENSURE_SMEM(kern, 201 * 1024);
+    PlainProducer::Args pa{x, ldx, k};
+    StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo};
+    const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+    kern<<<grid, NUM_THREADS, smem, to_stream(stream)>>>(g, pa, ea);
+    KDPC_RETURN_LAST();
+}
+
+KDPC_API int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const float *w,
+                              const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
+                              const float *residual, float *out, int ldo, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(x && w && out && m > 0 && n > 0 && k > 0 && ldx >= k && ldo >= n);
+    const long long total = m * ((n + 3) / 4);
+    linear_simt_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
+        m, n, k, x, ldx, w, scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo);
+    KDPC_RETURN_LAST();
+}

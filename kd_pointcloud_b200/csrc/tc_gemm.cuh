@@ -1,0 +1,298 @@
+// Warp-specialised tcgen05 GEMM skeleton with pluggable A-producer and epilogue (sm_100a).
+//
+//   D[128 x N] (TMEM, fp32)  +=  A[128 x 64-chunk] (smem, bf16 hi/lo)  *  W[N x 64-chunk]^T (smem, bf16 hi/lo)
+//
+// Roles (320 threads, one CTA per SM, persistent over 128-row tiles):
+//   warps 0-3  A producers : build the 128x64 A chunk IN SHARED MEMORY (plain fp32 rows, or the
+//                            PointConv gather+aggregate, or the cost-volume gather+add+act), split
+//                            fp32 -> bf16 hi/lo, write it in the canonical SWIZZLE_128B layout
+//   warp  4    MMA issuer  : one elected thread, 3 tcgen05.mma per K-step (hi*hi, hi*lo, lo*hi)
+//   warp  5    W loader    : 1-D bulk TMA of pre-packed weight chunk images (+ TMEM alloc/dealloc)
+//   warps 6-9  epilogue    : tcgen05.ld the accumulator, scale/shift/activation, store
+// Pipelines: smem stages (full_a/full_b/empty mbarriers) and two TMEM accumulator buffers
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "tc_common.cuh"
+
+namespace kdpc {
+namespace tc {
+
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_STAGES = 4;
+
+struct GemmShape {
+    long long m;          // rows
+    int n;                // logical output columns
+    int n_pad;            // UMMA N: multiple of 16, 16..256
+    int acc_stride;       // TMEM columns per accumulator buffer: round_up(n_pad, 32)
+    int tmem_cols;        // power of two >= 2 * acc_stride
+    int num_chunks;       // K chunks of 64 (packed-weight K, zero padded)
+    int k_total;          // packed K (multiple of 16): K-steps beyond it are skipped
+    int stages;
+    long long num_tiles;
+    const unsigned char *wpacked;   // [chunk][hi|lo][n_pad][128 B]
+};
+
+static inline int b_stage_bytes(int n_pad) { return 2 * n_pad * 128; }
+
+static inline size_t smem_bytes(int n_pad, int stages) {
+    return (size_t)stages * (A_STAGE_BYTES + b_stage_bytes(n_pad)) + 1024;     // + alignment slack
+}
+
+static inline int pick_stages(int n_pad) {
+    int s = (int)((200 * 1024 - 1024) / (A_STAGE_BYTES + b_stage_bytes(n_pad)));
+    return s > MAX_STAGES ? MAX_STAGES : s;
+}
+
+static inline GemmShape make_shape(long long m, int n, int k_packed, const void *wpacked) {
+    GemmShape g;
+    g.m = m;
+    g.n = n;
+    g.n_pad = (n + 15) / 16 * 16;
+    g.acc_stride = (g.n_pad + 31) / 32 * 32;
+    int c = 32;
+    while (c < 2 * g.acc_stride) c <<= 1;
+    g.tmem_cols = c;
+    g.k_total = (k_packed + 15) / 16 * 16;
+    g.num_chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
+    g.stages = pick_stages(g.n_pad);
+    g.num_tiles = (m + TILE_M - 1) / TILE_M;
+    g.wpacked = reinterpret_cast<const unsigned char *>(wpacked);
+    return g;
+}
+
+// Producer concept:
+//   struct P { struct Args {...};
+//              __device__ P(const Args&, const GemmShape&);
+//              __device__ void begin_tile(long long tile, int r);                       // r = producer thread 0..127 = tile row
+//              __device__ void fill(int chunk, unsigned char *a_hi, unsigned char *a_lo, int r); };
+// Epilogue concept:
+//   struct E { struct Args {...};
+//              __device__ void tile(const Args&, const GemmShape&, long long tile, uint32_t tmem_acc, int quarter, int lane); };
+template <class Producer, class Epilogue>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);       // 1024-byte aligned tiles
+    const int bbytes = 2 * g.n_pad * 128;
+    unsigned char *a_base = smem;
+    unsigned char *b_base = smem + (size_t)g.stages * A_STAGE_BYTES;
+
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(&full_a[s], 4);        // one arrive per producer warp
+            mbar_init(&full_b[s], 1);        // expect_tx arrive of the W loader
+            mbar_init(&empty[s], 1);         // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);     // tcgen05.commit
+            mbar_init(&tmem_empty[a], 4);    // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < 4) {
+        // ================= A producers =================
+        Producer prod(pa, g);
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+            prod.begin_tile(tile, tid);
+            for (int c = 0; c < g.num_chunks; ++c, ++it) {
+                const int s = it % g.stages;
+                const uint32_t ph = (it / g.stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
+                prod.fill(c, a_hi, a_hi + A_PART_BYTES, tid);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[s]);
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
+        uint32_t it = 0, tcount = 0;
+        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1;
+            mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            fence_after_sync();
+            const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
+            for (int c = 0; c < g.num_chunks; ++c, ++it) {
+                const int s = it % g.stages;
+                const uint32_t ph = (it / g.stages) & 1;
+                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_b[s], ph);
+                fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_PART_BYTES;
+                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * bbytes);
+                    const uint32_t b_lo = b_hi + (uint32_t)g.n_pad * 128u;
+                    const int ksteps = min(CHUNK_K / UMMA_K, (g.k_total - c * CHUNK_K) / UMMA_K);
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint32_t off = (uint32_t)kk * (UMMA_K * 2);
+                        const uint64_t dah = make_smem_desc_sw128(a_hi + off), dal = make_smem_desc_sw128(a_lo + off);
+                        const uint64_t dbh = make_smem_desc_sw128(b_hi + off), dbl = make_smem_desc_sw128(b_lo + off);
+                        umma_bf16(d_addr, dah, dbh, idesc, (c | kk) != 0);
+                        umma_bf16(d_addr, dah, dbl, idesc, 1);
+                        umma_bf16(d_addr, dal, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
+                    if (c == g.num_chunks - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5) {
+        // ================= weight loader =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                for (int c = 0; c < g.num_chunks; ++c, ++it) {
+                    const int s = it % g.stages;
+                    const uint32_t ph = (it / g.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)c * bbytes, (uint32_t)bbytes, &full_b[s]);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
+        Epilogue epi;
+        uint32_t tcount = 0;
+        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1;
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            fence_after_sync();
+            const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
+            epi.tile(ea, g, tile, t_acc, quarter, lane);
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 5) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Epilogue: y = act(acc * scale[n] + shift[n]) stored row-major fp32 [M, ldo].
+// (Linear bias, and eval-mode BatchNorm folded on the host: scale = gamma/sqrt(var+eps),
+//  shift = (bias - mean) * scale + beta.)
+struct StoreEpilogue {
+    struct Args {
+        const float *scale;   // [n] or nullptr (= 1)
+        const float *shift;   // [n] or nullptr (= 0)
+        float slope;          // LeakyReLU slope; 1.0 = no activation
+        float lo, hi;         // clamp range (applied after the activation); lo > hi = none
+        const float *residual;   // optional [M, ldo] added last (flow = flow_local + up_flow)
+        float *out;
+        int ldo;
+    };
+    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, uint32_t t_acc, int quarter,
+                                         int lane) const {
+        const long long row = tile * TILE_M + quarter * 32 + lane;
+        const bool vec = (e.ldo & 3) == 0;
+        for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // warp-collective: no divergence around it
+            if (row < g.m) {
+                float *o = e.out + row * e.ldo + c0;
+                const float *res = e.residual ? e.residual + row * e.ldo + c0 : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c0 + j;
+                    if (col < g.n) {
+                        float y = v[j];
+                        if (e.scale) y *= __ldg(e.scale + col);
+                        if (e.shift) y += __ldg(e.shift + col);
+                        y = y > 0.f ? y : y * e.slope;
+                        if (e.lo <= e.hi) y = fminf(fmaxf(y, e.lo), e.hi);
+                        if (res) y += __ldg(res + j);
+                        v[j] = y;
+                    }
+                }
+                if (vec && c0 + 32 <= g.n) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && c0 + j < g.n; ++j) o[j] = v[j];
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Producer: plain fp32 rows x[M, ldx] (K contiguous).
+struct PlainProducer {
+    struct Args {
+        const float *x;
+        int ldx;
+        int k;
+    };
+    const Args &a;
+    const GemmShape &g;
+    const float *rowp;
+    bool valid;
+    __device__ PlainProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_), rowp(nullptr), valid(false) {}
+    __device__ __forceinline__ void begin_tile(long long tile, int r) {
+        const long long row = tile * TILE_M + r;
+        valid = row < g.m;
+        rowp = a.x + (valid ? row : 0) * a.ldx;
+    }
+    __device__ __forceinline__ void fill(int chunk, unsigned char *a_hi, unsigned char *a_lo, int r) {
+        const int k0 = chunk * CHUNK_K;
+        const bool fast = valid && (a.ldx & 3) == 0 && k0 + CHUNK_K <= a.k;
+        float4 ld[16];
+        if (fast) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(rowp + k0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ld[i] = __ldg(p4 + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + i * 4 + j;
+                    t[j] = (valid && k < a.k) ? __ldg(rowp + k) : 0.f;
+                }
+                ld[i] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float v[8] = {ld[2 * u].x, ld[2 * u].y, ld[2 * u].z, ld[2 * u].w,
+                                ld[2 * u + 1].x, ld[2 * u + 1].y, ld[2 * u + 1].z, ld[2 * u + 1].w};
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t off = sw128_offset(r, u);
+            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+        }
+    }
+};
+
+}  // namespace tc
+}  // namespace kdpc

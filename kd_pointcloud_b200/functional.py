@@ -59,10 +59,14 @@ _CSR_CACHE = _LRU(48)
 _CACHE_ENABLED = True
 
 
-def clear_caches() -> None:
-    """Drop cached kNN results and inverse indices (call between independent batches)."""
+def clear_caches(weights: bool = False) -> None:
+    """Drop cached kNN results and inverse indices (call between independent batches);
+    ``weights=True`` also drops the packed-weight / folded-affine caches."""
     _KNN_CACHE.clear()
     _CSR_CACHE.clear()
+    if weights:
+        _PACK_CACHE.clear()
+        _AFFINE_CACHE.clear()
 
 
 def set_cache_enabled(flag: bool) -> None:
@@ -289,6 +293,83 @@ def interp3_composite(q_xyz, c_xyz, idx, feat) -> torch.Tensor:
     inv = 1.0 / dist
     weight = inv / torch.sum(inv, dim=2, keepdim=True)
     return torch.sum(weight.view(B, N, 3, 1) * gather_rows(feat, idx), dim=2)
+
+
+# ------------------------------------------------------------------- fused linear layers
+_PACK_CACHE = _LRU(512)
+_AFFINE_CACHE = _LRU(512)
+
+
+def _packed_weight(w2d: torch.Tensor, mode: int = 0, d: int = 0, wn: int = 0) -> torch.Tensor:
+    """bf16 hi/lo chunk images of a [N,K] weight, cached per (storage, version)."""
+    key = (mode, d, wn, _tkey(w2d))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    packed = K.pack_weight(w2d.detach().contiguous(), mode, d, wn)
+    _PACK_CACHE.put(key, (packed, w2d))
+    return packed
+
+
+def _fold_affine(bias: Optional[torch.Tensor], bn: Optional[torch.nn.Module]):
+    """(scale, shift) of the epilogue: Linear bias and eval-mode BatchNorm folded together,
+    y = (x W^T + b - mean) * gamma / sqrt(var + eps) + beta."""
+    if bn is None:
+        return None, (None if bias is None else bias.detach())
+    parts = (bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple(None if t is None else _tkey(t) for t in parts) + (bn.eps,)
+    hit = _AFFINE_CACHE.get(key)
+    if hit is not None:
+        return hit[0], hit[1]
+    with torch.no_grad():
+        scale = torch.rsqrt(bn.running_var + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight
+        shift = -bn.running_mean * scale
+        if bias is not None:
+            shift = shift + bias * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias
+        scale, shift = scale.contiguous(), shift.contiguous()
+    _AFFINE_CACHE.put(key, (scale, shift, parts))
+    return scale, shift
+
+
+def fused_linear_available(x: torch.Tensor, weight: torch.Tensor, bias, bn) -> bool:
+    """The tcgen05 / SIMT fused layer is forward-only: use it when nothing needs a gradient and any
+    BatchNorm is in eval mode."""
+    if bn is not None and (bn.training or not bn.track_running_stats):
+        return False
+    if not x.is_cuda or x.dtype != torch.float32:
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return False
+    return True
+
+
+def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 bn: Optional[torch.nn.Module] = None, slope: float = 1.0, clamp=None,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[..., N] = clamp(leaky(bn(x[..., K] W^T + b), slope)) + residual in ONE kernel.
+    weight [N,K] (nn.Linear) or [N,K,1(,1)] (1x1 conv)."""
+    w2d = weight.reshape(weight.shape[0], -1)
+    n, k = w2d.shape
+    x = x.contiguous()
+    scale, shift = _fold_affine(bias, bn)
+    lo, hi = (1.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
+    res = None if residual is None else residual.contiguous()
+    if k < 16 or n < 16 or k % 4 != 0:
+        return K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
+    if n <= 256:
+        return K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
+    # wider layers: column blocks of 256 (level3_1: 256 -> 512)
+    outs = []
+    for c0 in range(0, n, 256):
+        c1 = min(n, c0 + 256)
+        outs.append(K.linear_tc(x, _packed_weight(w2d[c0:c1]), c1 - c0, None if scale is None else scale[c0:c1].contiguous(),
+                                None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi,
+                                None if res is None else res[..., c0:c1].contiguous()))
+    return torch.cat(outs, dim=-1)
 
 
 # ------------------------------------------------------------------- PointConv pieces

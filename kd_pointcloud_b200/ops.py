@@ -404,6 +404,68 @@ _register("interp3(Tensor q_xyz, Tensor c_xyz, Tensor idx, Tensor feat) -> (Tens
           lambda q, c, idx, f: (q.new_empty((q.shape[0], q.shape[1], f.shape[2])), q.new_empty(q.shape)))
 
 
+# ------------------------------------------------------------------- tensor-core linear layers
+def _pack_weight(w: torch.Tensor, mode: int, d: int, wn: int) -> torch.Tensor:
+    _req(w, torch.float32, 2, "weight")
+    n, k_src = w.shape
+    k_packed = (d + 4) * wn if mode == 1 else k_src
+    with _guard(w):
+        nbytes = _lib.lib().kdpc_packed_weight_bytes(n, k_packed)
+        out = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+        _call("kdpc_pack_weight", n, k_src, mode, d, wn, _p(w), _p(out), _stream())
+    return out
+
+
+def _linear_args(x, n, scale, shift, residual):
+    _req(x, torch.float32, None, "x")
+    k = x.shape[-1]
+    m = x.numel() // k
+    for t, nm in ((scale, "scale"), (shift, "shift")):
+        if t is not None:
+            _req(t, torch.float32, 1, nm)
+            if t.numel() != n:
+                raise ValueError(f"kdpc: {nm} must have {n} elements")
+    if residual is not None:
+        _req(residual, torch.float32, None, "residual")
+        if residual.numel() != m * n:
+            raise ValueError("kdpc: residual shape mismatch")
+    return m, k
+
+
+def _linear_tc(x, wpacked, n: int, scale, shift, slope: float, lo: float, hi: float, residual) -> torch.Tensor:
+    m, k = _linear_args(x, n, scale, shift, residual)
+    with _guard(x):
+        out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
+        if out.numel():
+            _call("kdpc_linear_tc", m, n, k, _p(x), k, _p(wpacked), _p(scale), _p(shift), float(slope), float(lo),
+                  float(hi), _p(residual), _p(out), n, _stream())
+    return out
+
+
+def _linear_simt(x, w, scale, shift, slope: float, lo: float, hi: float, residual) -> torch.Tensor:
+    _req(w, torch.float32, 2, "weight")
+    n = w.shape[0]
+    m, k = _linear_args(x, n, scale, shift, residual)
+    if w.shape[1] != k:
+        raise ValueError("kdpc: weight / input size mismatch")
+    with _guard(x):
+        out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
+        if out.numel():
+            _call("kdpc_linear_simt", m, n, k, _p(x), k, _p(w), _p(scale), _p(shift), float(slope), float(lo), float(hi),
+                  _p(residual), _p(out), n, _stream())
+    return out
+
+
+_register("pack_weight(Tensor w, int mode, int d, int wn) -> Tensor", _pack_weight,
+          lambda w, mode, d, wn: w.new_empty((1,), dtype=torch.uint8))
+_register("linear_tc(Tensor x, Tensor wpacked, int n, Tensor? scale, Tensor? shift, float slope, float lo, float hi, "
+          "Tensor? residual) -> Tensor", _linear_tc,
+          lambda x, wp, n, sc, sh, sl, lo, hi, r: x.new_empty(tuple(x.shape[:-1]) + (n,)))
+_register("linear_simt(Tensor x, Tensor w, Tensor? scale, Tensor? shift, float slope, float lo, float hi, "
+          "Tensor? residual) -> Tensor", _linear_simt,
+          lambda x, w, sc, sh, sl, lo, hi, r: x.new_empty(tuple(x.shape[:-1]) + (w.shape[0],)))
+
+
 # --------------------------------------------------------------------------- backward plumbing
 def _build_csr(idx: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
     _req(idx, torch.int32, None, "idx")

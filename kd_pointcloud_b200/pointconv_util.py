@@ -41,10 +41,27 @@ def _is_pointwise(conv) -> bool:
     return one(conv.kernel_size) and one(conv.stride) and zero(conv.padding) and conv.groups == 1
 
 
-def _linear_pm(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """A 1x1 nn.Conv1d / nn.Conv2d applied along the LAST axis of a point-major tensor."""
+def _linear_pm(conv: nn.Module, x: torch.Tensor, norm: Optional[nn.Module] = None, act: Optional[nn.Module] = None,
+               clamp=None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A 1x1 nn.Conv1d / nn.Conv2d / nn.Linear applied along the LAST axis of a point-major tensor,
+    followed by an optional BatchNorm (over all leading axes), activation, clamp and residual add.
+    Inference: ONE fused tcgen05 kernel (functional.fused_linear).  When a gradient is needed or
+    the BatchNorm is in training mode: the same math from torch ops (autograd)."""
     w = conv.weight
-    return F.linear(x, w.reshape(w.shape[0], w.shape[1]), conv.bias)
+    bn = None if (norm is None or isinstance(norm, nn.Identity)) else norm
+    slope = 1.0 if act is None else _slope(act)
+    if KF.fused_linear_available(x, w, conv.bias, bn):
+        return KF.fused_linear(x, w, conv.bias, bn, slope, clamp, residual)
+    y = F.linear(x, w.reshape(w.shape[0], -1), conv.bias)
+    if bn is not None:
+        y = bn(y.reshape(-1, y.shape[-1])).view(y.shape)
+    if act is not None:
+        y = F.leaky_relu(y, slope) if slope != 0.0 else F.relu(y)
+    if clamp is not None:
+        y = y.clamp(clamp[0], clamp[1])
+    if residual is not None:
+        y = y + residual
+    return y
 
 
 class _ComposedConv(nn.Module):
@@ -57,18 +74,14 @@ class _ComposedConv(nn.Module):
             return self.composed_module(x)
         # 1x1 conv == GEMM over channels; keep the result point-major and hand back a view
         perm_in = (0, 2, 1) if x.dim() == 3 else (0, 3, 2, 1)
-        y = act(_linear_pm(conv, x.permute(*perm_in)))
-        return y.permute(*perm_in)
+        return _linear_pm(conv, x.permute(*perm_in), None, act).permute(*perm_in)
 
     def forward_pm(self, x: torch.Tensor) -> torch.Tensor:
         """x [..., Cin] -> [..., Cout] (channels last)."""
         conv, norm, act = self.composed_module[0], self.composed_module[1], self.composed_module[2]
         if not _is_pointwise(conv):
             raise NotImplementedError("forward_pm needs a 1x1 convolution")
-        y = _linear_pm(conv, x)
-        if not isinstance(norm, nn.Identity):
-            y = norm(y.reshape(-1, y.shape[-1])).view(y.shape)
-        return act(y)
+        return _linear_pm(conv, x, norm, act)
 
 
 class Conv1d(_ComposedConv):
@@ -204,10 +217,8 @@ class _PointConvBase(nn.Module):
         grouped = KF.group_concat(s_xyz, q_xyz, s_points, idx)            # [B,S,K,3+D]
         wn = self.weightnet.forward_pm(grouped)                           # [B,S,K,W]
         agg = KF.pointconv_agg(grouped, wn)                               # [B,S,(3+D)*W]  (c-major)
-        y = self.linear(agg)
-        if self.bn:
-            y = self.bn_linear(y.reshape(-1, y.shape[-1])).view(y.shape)  # stats over B and S
-        return self.relu(y)
+        # Linear (+ BatchNorm1d over B and S) + activation
+        return _linear_pm(self.linear, agg, self.bn_linear if self.bn else None, self.relu)
 
 
 class PointConv(_PointConvBase):
@@ -377,8 +388,8 @@ class SceneFlowEstimatorResidual(nn.Module):
             x = pointconv.forward_pm(xyz, x)
         for conv in self.mlp_convs:
             x = conv.forward_pm(x)
-        flow_local = _linear_pm(self.fc, x).clamp(self.clamp[0], self.clamp[1])
-        return x, (flow_local if flow is None else flow_local + flow)
+        # flow = clamp(fc(x)) + up_flow      (pointconv_util.py:2250-2255)
+        return x, _linear_pm(self.fc, x, None, None, (self.clamp[0], self.clamp[1]), flow)
 
     def forward(self, xyz, feats, cost_volume, flow=None):
         x, f = self.forward_pm(pm(xyz), pm(feats), pm(cost_volume), None if flow is None else pm(flow))

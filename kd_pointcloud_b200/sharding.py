@@ -1,0 +1,77 @@
+"""Multi-GPU plumbing: one process per GPU, scene pairs sharded by batch.
+
+Inference needs NO collective (every kernel is per batch element).  Training adds exactly
+one: a sum all-reduce of the gradients.  The reference's only multi-GPU mechanism is single-process
+``nn.DataParallel`` (distilTrain.py:108-114: replicate weights + scatter + gather + reduce on GPU0
+every step); here each rank owns its shard end to end and the gradients travel once, as ONE flat
+fp32 buffer (7 958 604 elements = 31.8 MB for the student) over NCCL / NVLink.
+
+80 of the 306 parameter tensors never receive a gradient (CrossLayerLight.bias1/bias2,
+WeightNet.mlp_bns.*) — DistributedDataParallel would need find_unused_parameters; the
+flat reducer simply skips ``grad is None`` (the set is structural, hence identical on all ranks).
+BatchNorm1d statistics stay per replica, as with the reference's DataParallel.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``total`` independent items; the first ``total % world`` ranks
+    get one extra."""
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    n = next(iter(batch.values())).shape[0]
+    a, b = shard_range(n, rank, world)
+    return {k: v[a:b] for k, v in batch.items()}
+
+
+class FlatGradAllReduce:
+    """Average gradients across ranks with one all-reduce over a persistent flat buffer."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self.flat: Optional[torch.Tensor] = None
+        self.active: Optional[List[int]] = None
+
+    def _plan(self):
+        self.active = [i for i, p in enumerate(self.params) if p.grad is not None]
+        n = sum(self.params[i].numel() for i in self.active)
+        ref = self.params[self.active[0]]
+        self.flat = torch.zeros(n, dtype=torch.float32, device=ref.device)
+        if dist.is_initialized():
+            # the participating set is structural; verify once that all ranks agree on its size
+            sizes = torch.tensor([n, len(self.active)], dtype=torch.int64, device=ref.device)
+            lo, hi = sizes.clone(), sizes.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("FlatGradAllReduce: ranks disagree on which parameters have gradients")
+
+    @property
+    def numel(self) -> int:
+        return 0 if self.flat is None else self.flat.numel()
+
+    def __call__(self) -> None:
+        if self.active is None:
+            self._plan()
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return
+        grads = [self.params[i].grad for i in self.active]
+        if any(g is None for g in grads):
+            raise RuntimeError("FlatGradAllReduce: a parameter lost its gradient after planning")
+        torch._foreach_copy_(list(self.flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(world)
+        torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g for g in grads],
+                             [c.view_as(g) if not g.is_contiguous() else c for c, g in
+                              zip(self.flat.split([g.numel() for g in grads]), grads)])

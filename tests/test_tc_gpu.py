@@ -1,0 +1,98 @@
+"""GPU tests for the tcgen05 layers: the bf16 hi/lo split GEMM (fp32 accumulation in TMEM) against
+an fp64 reference.  Tolerance: 2e-5 of the output range (three-term split drops ~2^-18 relative
+terms); the north-star bound for fp32 layer outputs is 1e-4."""
+import pytest
+import torch
+
+from kd_pointcloud_b200 import functional as KF
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+K = torch.ops.kdpc
+
+
+def _ref(x, w, b=None, scale=None, shift=None, slope=1.0, clamp=None, residual=None):
+    y = x.double() @ w.double().t()
+    if scale is not None:
+        y = y * scale.double()
+    if shift is not None:
+        y = y + shift.double()
+    y = torch.where(y > 0, y, y * slope)
+    if clamp is not None:
+        y = y.clamp(*clamp)
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+def _err(a, b):
+    return ((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("m,n,k", [
+    (128, 64, 64), (128, 128, 128), (1000, 64, 64), (300, 32, 32), (4096, 128, 2096), (777, 96, 320), (129, 16, 16),
+    (65536, 128, 512), (5000, 256, 256), (200, 24, 100), (64, 256, 4144), (20000, 48, 80), (1, 64, 64),
+])
+def test_linear_tc_matches_fp64(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(DEV)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(DEV)
+    shift = torch.randn(n, generator=g).to(DEV)
+    wp = K.pack_weight(w, 0, 0, 0)
+    y = K.linear_tc(x, wp, n, None, shift, 0.1, 1.0, 0.0, None)
+    assert y.shape == (m, n)
+    assert _err(y, _ref(x, w, shift=shift, slope=0.1)) < 2e-5
+    # run-to-run determinism
+    assert torch.equal(y, K.linear_tc(x, wp, n, None, shift, 0.1, 1.0, 0.0, None))
+
+
+def test_linear_tc_epilogue_variants_and_large_magnitudes():
+    g = torch.Generator().manual_seed(0)
+    m, n, k = 3000, 64, 192
+    x = (torch.randn(m, k, generator=g) * 30).to(DEV)         # coordinates-scale activations
+    w = (torch.randn(n, k, generator=g) * 0.2).to(DEV)
+    scale, shift = torch.rand(n, generator=g).to(DEV) + 0.5, torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(m, n, generator=g).to(DEV)
+    wp = K.pack_weight(w, 0, 0, 0)
+    y = K.linear_tc(x, wp, n, scale, shift, 1.0, -20.0, 20.0, res)
+    assert _err(y, _ref(x, w, scale=scale, shift=shift, clamp=(-20, 20), residual=res)) < 2e-5
+    y = K.linear_tc(x, wp, n, None, None, 0.0, 1.0, 0.0, None)          # plain ReLU, no affine
+    assert _err(y, _ref(x, w, slope=0.0)) < 2e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(5000, 32, 3), (4096, 3, 64), (100, 5, 7), (1000, 64, 10)])
+def test_linear_simt_matches_fp64(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(DEV)
+    w = torch.randn(n, k, generator=g).to(DEV)
+    shift = torch.randn(n, generator=g).to(DEV)
+    res = torch.randn(m, n, generator=g).to(DEV)
+    y = K.linear_simt(x, w, None, shift, 1.0, -2.0, 2.0, res)
+    assert _err(y, _ref(x, w, shift=shift, clamp=(-2, 2), residual=res)) < 1e-6
+
+
+def test_fused_linear_frontend_matches_torch_modules():
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(320, 512).to(DEV)
+    bn = torch.nn.BatchNorm1d(512).to(DEV).eval()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.data.normal_(1, 0.1)
+    bn.bias.data.normal_()
+    x = torch.randn(4, 700, 320, device=DEV)
+    with torch.no_grad():
+        ref = torch.nn.functional.leaky_relu(bn(lin(x).reshape(-1, 512)).view(4, 700, 512).double(), 0.1)
+        y = KF.fused_linear(x, lin.weight, lin.bias, bn, 0.1)           # N = 512: two column blocks
+    assert y.shape == (4, 700, 512) and _err(y, ref) < 2e-5
+    conv = torch.nn.Conv1d(64, 3, 1).to(DEV)
+    res = torch.randn(4, 700, 3, device=DEV)
+    xin = torch.randn(4, 700, 64, device=DEV)
+    with torch.no_grad():
+        ref = conv(xin.permute(0, 2, 1)).permute(0, 2, 1).double().clamp(-200, 200) + res.double()
+        y = KF.fused_linear(xin, conv.weight, conv.bias, None, 1.0, (-200, 200), res)
+    assert _err(y, ref) < 1e-5
+    # weights are re-packed when they change in place
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+        y2 = KF.fused_linear(x, lin.weight, lin.bias, None, 1.0)
+        assert _err(y2, lin(x).double()) < 2e-5
