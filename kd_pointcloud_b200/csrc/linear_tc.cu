@@ -129,7 +129,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
     PlainProducer::Args pa{x, ldx, k};
     StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo};
     const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
-    kern<<<grid, NUM_THREADS, smem, to_stream(stream)>>>(g, pa, ea);
+    kern<<<grid, num_threads<PlainProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
     KDPC_RETURN_LAST();
 }
 

@@ -2,13 +2,14 @@
 //
 //   D[128 x N] (TMEM, fp32)  +=  A[128 x 64-chunk] (smem, bf16 hi/lo)  *  W[N x 64-chunk]^T (smem, bf16 hi/lo)
 //
-// Roles (320 threads, one CTA per SM, persistent over 128-row tiles):
-//   warps 0-3  A producers : build the 128x64 A chunk IN SHARED MEMORY (plain fp32 rows, or the
+// Roles (one CTA per SM, persistent over 128-row tiles; PW = 4 or 8 producer warps):
+//   warps 0..PW-1 A producers: build the 128x64 A chunk IN SHARED MEMORY (plain fp32 rows, or the
 //                            PointConv gather+aggregate, or the cost-volume gather+add+act), split
 //                            fp32 -> bf16 hi/lo, write it in the canonical SWIZZLE_128B layout
-//   warp  4    MMA issuer  : one elected thread, 3 tcgen05.mma per K-step (hi*hi, hi*lo, lo*hi)
-//   warp  5    W loader    : 1-D bulk TMA of pre-packed weight chunk images (+ TMEM alloc/dealloc)
-//   warps 6-9  epilogue    : tcgen05.ld the accumulator, scale/shift/activation, store
+//   warp  PW   MMA issuer  : one elected thread, 3 tcgen05.mma per K-step (hi*hi, hi*lo, lo*hi)
+//                            (producer thread 0 also issues the 1-D bulk TMA of the pre-packed weight chunk
+//                            for the stage it is about to fill: no separate loader warp, more registers per thread)
+//   warps PW+1..PW+4 epilogue: tcgen05.ld the accumulator, scale/shift/activation, store
 // Pipelines: smem stages (full_a/full_b/empty mbarriers) and two TMEM accumulator buffers
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -17,9 +18,9 @@
 namespace kdpc {
 namespace tc {
 
-constexpr int NUM_PRODUCER_THREADS = 128;
-constexpr int NUM_THREADS = 320;
 constexpr int MAX_STAGES = 4;
+// threads of a kernel instance: PW producer warps + MMA warp + 4 epilogue warps
+template <class Producer> constexpr int num_threads() { return (Producer::kWarps + 5) * 32; }
 
 struct GemmShape {
     long long m;          // rows
@@ -71,13 +72,14 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
 //   struct E { struct Args {...};
 //              __device__ void tile(const Args&, const GemmShape&, long long tile, uint32_t tmem_acc, int quarter, int lane); };
 template <class Producer, class Epilogue>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Producer::kWarps + 5) * 32, 1)
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
 
+    constexpr int PW = Producer::kWarps;                                     // 4 or 8: epilogue warps PW+1..PW+4 have (warp & 3) = 1,2,3,0
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);       // 1024-byte aligned tiles
@@ -87,7 +89,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full_a[s], 4);        // one arrive per producer warp
+            mbar_init(&full_a[s], PW);       // one arrive per producer warp
             mbar_init(&full_b[s], 1);        // expect_tx arrive of the W loader
             mbar_init(&empty[s], 1);         // tcgen05.commit
         }
@@ -97,13 +99,13 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
+    if (warp == PW) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < 4) {
+    if (warp < PW) {
         // ================= A producers =================
         Producer prod(pa, g);
         uint32_t it = 0;
@@ -113,6 +115,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 const int s = it % g.stages;
                 const uint32_t ph = (it / g.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (tid == 0) {                                   // weight chunk for this stage (bulk TMA, async)
+                    mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)c * bbytes, (uint32_t)bbytes, &full_b[s]);
+                }
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
                 prod.fill(c, a_hi, a_hi + A_PART_BYTES, tid);
                 fence_async_smem();
@@ -120,7 +126,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 if (lane == 0) mbar_arrive(&full_a[s]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == PW) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
         uint32_t it = 0, tcount = 0;
@@ -155,20 +161,6 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 __syncwarp();
             }
         }
-    } else if (warp == 5) {
-        // ================= weight loader =================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-                for (int c = 0; c < g.num_chunks; ++c, ++it) {
-                    const int s = it % g.stages;
-                    const uint32_t ph = (it / g.stages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)c * bbytes, (uint32_t)bbytes, &full_b[s]);
-                }
-            }
-        }
     } else {
         // ================= epilogue =================
         const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
@@ -188,7 +180,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
 
     fence_before_sync();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == PW) {
         fence_after_sync();
         tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
     }
@@ -246,6 +238,7 @@ struct StoreEpilogue {
 // ------------------------------------------------------------------------------------------
 // Producer: plain fp32 rows x[M, ldx] (K contiguous).
 struct PlainProducer {
+    static constexpr int kWarps = 4;
     struct Args {
         const float *x;
         int ldx;

@@ -54,8 +54,8 @@ def test_linear_tc_epilogue_variants_and_large_magnitudes():
     scale, shift = torch.rand(n, generator=g).to(DEV) + 0.5, torch.randn(n, generator=g).to(DEV)
     res = torch.randn(m, n, generator=g).to(DEV)
     wp = K.pack_weight(w, 0, 0, 0)
-    y = K.linear_tc(x, wp, n, scale, shift, 1.0, -20.0, 20.0, res)
-    assert _err(y, _ref(x, w, scale=scale, shift=shift, clamp=(-20, 20), residual=res)) < 2e-5
+    y = K.linear_tc(x, wp, n, scale, shift, 1.0, -150.0, 150.0, res)
+    assert _err(y, _ref(x, w, scale=scale, shift=shift, clamp=(-150, 150), residual=res)) < 2e-5
     y = K.linear_tc(x, wp, n, None, None, 0.0, 1.0, 0.0, None)          # plain ReLU, no affine
     assert _err(y, _ref(x, w, slope=0.0)) < 2e-5
 
