@@ -61,7 +61,7 @@ int kdpc_group_grad(int b, int c, int n, int s, int k, const float *grad_out, co
 
 /* three_nn_kernel_launcher_fast, interpolate_gpu.h. unknown [B,N,3], known [B,M,3] ->
  * dist2 [B,N,3] (SQUARED, ascending), idx int32 [B,N,3]; ties keep the lower index.
- * ws: workspace of B*M*16 bytes. */
+ * ws: kdpc_knn_workspace_bytes(b, n, m) bytes. */
 int kdpc_three_nn(int b, int n, int m, const float *unknown, const float *known, void *ws,
                   float *dist2, int *idx, kdpc_stream_t stream);
 /* three_interpolate_kernel_launcher_fast. f [B,C,M], idx/w [B,N,3] -> out [B,C,N] */
@@ -82,10 +82,29 @@ int kdpc_square_distance(int b, int s, int n, const float *src, const float *dst
 
 /* knn_point, pointconv_util.py:96-107, without materialising the [B,S,N] matrix.
  * query [B,S,3], cand [B,N,3] -> the k candidates with smallest square_distance, ordered
- * ascending by (distance, index).  idx32 / idx64 / dist may each be NULL.  ws: B*N*16 bytes.
- * k <= 32. */
+ * ascending by (distance, index).  idx32 / idx64 / dist may each be NULL.  k <= min(32, N).
+ * ws: kdpc_knn_workspace_bytes(b, s, n) bytes, 16-byte aligned.
+ * For 256 <= N <= 16384 this runs kdpc_spatial_sort on both clouds (once if query == cand) and then
+ * kdpc_knn_sorted; otherwise the brute-force kernel.  Results are identical either way. */
+long long kdpc_knn_workspace_bytes(int b, int s, int n);
 int kdpc_knn(int b, int s, int n, int k, const float *query, const float *cand, void *ws,
              int *idx32, long long *idx64, float *dist, kdpc_stream_t stream);
+/* The brute-force kernel alone (every query scans every candidate through TMA-staged shared-memory
+ * tiles).  ws: B*N*16 bytes. */
+int kdpc_knn_bruteforce(int b, int s, int n, int k, const float *query, const float *cand, void *ws,
+                        int *idx32, long long *idx64, float *dist, kdpc_stream_t stream);
+
+/* Spatial (Morton) sort of B clouds of n <= 16384 points: out receives, per cloud, the points in
+ * Morton order as float4 (x,y,z,|p|^2), one bounding box per tile of 64 consecutive points and the
+ * original indices.  out: kdpc_spatial_sort_bytes(b, n) bytes, 16-byte aligned.  A sorted cloud can be
+ * reused by any number of kdpc_knn_sorted calls (as queries or as candidates). */
+long long kdpc_spatial_sort_bytes(int b, int n);
+int kdpc_spatial_sort(int b, int n, const float *xyz, void *out, kdpc_stream_t stream);
+/* Exact kNN between two sorted clouds by best-first search over candidate tiles with a conservative
+ * distance bound (knn_bf.cu).  direct = 0: square_distance rounding (knn_point); direct = 1: the
+ * pointnet2 kernels' (dx^2+dy^2+dz^2) rounding (three_nn).  Output rows are in ORIGINAL query order. */
+int kdpc_knn_sorted(int b, int s, int n, int k, int direct, const void *query_sorted, const void *cand_sorted,
+                    int *idx32, long long *idx64, float *dist, kdpc_stream_t stream);
 
 /* index_points_gather, pointconv_util.py:109-120 (pm): out[b,j,:] = f[b,idx[b,j],:]; f [B,N,C].
  * With m = S*K this is also index_points_group (pointconv_util.py:122-133) producing
@@ -146,6 +165,26 @@ int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const voi
 int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const float *w,
                      const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
                      const float *residual, float *out, int ldo, kdpc_stream_t stream);
+
+/* PointConv (pointconv_util.py:231-258) fused end to end for inference: neighbour gather + relative xyz +
+ * WeightNet(3->8->8->16, ReLU) + sum over K + Linear(16(d+3) -> n_out) + scale/shift (bias, eval BatchNorm) +
+ * LeakyReLU(slope).  cand_xyz [B,N,3], query_xyz [B,S,3], feats [B,N,d] (d % 4 == 0), idx int32 [B,S,k]
+ * (k = 9 or 16) -> out [B,S,n_out].  wn_params: HOST array of 248 floats (w1[8x3] b1[8] w2[8x8] b2[8]
+ * w3[16x8] b3[16], nn.Conv2d layouts) passed to the kernel as launch parameters.  wpacked: the Linear
+ * weight packed with kdpc_pack_weight(mode 1, d, 16).  Neither [B,S,k,3+d] nor [B,S,16(d+3)] touches HBM. */
+int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
+                         const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
+                         const void *wpacked, const float *scale, const float *shift, float slope,
+                         float *out, kdpc_stream_t stream);
+
+/* CrossLayerLight.cross (pointconv_util.py:1826-1850) with a single-layer mlp, fused: out[b,i,:] =
+ * max_k leaky(W act(p2[idx[b,i,k]] + p1[b,i] + pos_w (xyz2[idx]-xyz1[i]) + pos_b) + bias, slope_post).
+ * k must be 32, d % 8 == 0, d, d_out <= 256.  wpacked: kdpc_pack_weight(mode 0) of W [d_out, d].
+ * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out]. */
+int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float *xyz1, const float *xyz2,
+                       const float *p1, const float *p2, const int *idx, const float *pos_w,
+                       const float *pos_b, float slope_pre, const void *wpacked, const float *bias,
+                       float slope_post, float *out, kdpc_stream_t stream);
 
 /* ---- deterministic backward plumbing ------------------------------------------------- */
 

@@ -15,9 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libkdpc.so")
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "loss.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+           "scatter.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
+LINK_FLAGS = ARCH_FLAGS + ["-shared"]
 
 
 def sources():
@@ -34,11 +35,30 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every kernel for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compile every kernel for sm_100a with nvcc (cross-compiles without a GPU): one object per
+    source (in parallel, rebuilt only when stale) under csrc/build/, then one link."""
     if not force and not needs_build():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    headers.append(os.path.join(_HERE, "..", "include", "kdpc.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers if os.path.exists(h))
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            cmd = [nvcc] + COMPILE_FLAGS + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)
@@ -59,6 +79,9 @@ _SIGNATURES = {
     "kdpc_ball_query": [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],
     "kdpc_square_distance": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_knn": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_knn_bruteforce": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "kdpc_spatial_sort": [c_int, c_int, _P, _P, _P],
+    "kdpc_knn_sorted": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_gather_rows": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_group_concat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_weightnet": [c_longlong, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -69,6 +92,8 @@ _SIGNATURES = {
     "kdpc_pack_weight": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
     "kdpc_linear_tc": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
     "kdpc_linear_simt": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
+    "kdpc_pointconv_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
+    "kdpc_costvol_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_float, _P, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
 }
@@ -94,6 +119,10 @@ def lib() -> ctypes.CDLL:
         L.kdpc_error_string.argtypes = [c_int]
         L.kdpc_packed_weight_bytes.restype = c_longlong
         L.kdpc_packed_weight_bytes.argtypes = [c_int, c_int]
+        L.kdpc_knn_workspace_bytes.restype = c_longlong
+        L.kdpc_knn_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        L.kdpc_spatial_sort_bytes.restype = c_longlong
+        L.kdpc_spatial_sort_bytes.argtypes = [c_int, c_int]
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -103,7 +132,8 @@ def lib() -> ctypes.CDLL:
 
 
 def exported_symbols():
-    return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes"] + list(_SIGNATURES)
+    return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
+            "kdpc_spatial_sort_bytes"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

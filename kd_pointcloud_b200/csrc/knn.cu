@@ -200,8 +200,46 @@ __global__ void square_distance_kernel(int s, int n, const float *__restrict__ s
 
 }  // namespace kdpc
 
+// Workspace of kdpc_knn / kdpc_three_nn: two spatially sorted clouds (knn_bf.cu) when the pruned search
+// applies, the float4-packed candidates of the brute-force kernel otherwise.
+static inline bool use_pruned(int s, int n) { return n >= 256 && n <= 16384 && s <= 16384; }
+
+KDPC_API long long kdpc_knn_workspace_bytes(int b, int s, int n) {
+    if (b <= 0 || s <= 0 || n <= 0) return 0;
+    if (use_pruned(s, n)) return kdpc_spatial_sort_bytes(b, n) + kdpc_spatial_sort_bytes(b, s);
+    return (long long)b * n * 16;
+}
+
+static int knn_dispatch(int b, int s, int n, int k, int direct, const float *query, const float *cand, void *ws,
+                        int *idx32, long long *idx64, float *dist, kdpc_stream_t stream) {
+    if (k > 32 || b > 65535) return KDPC_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(ws) % 16) != 0) return KDPC_EINVAL;
+    if (use_pruned(s, n) && k <= n) {
+        void *cws = ws;
+        void *qws = reinterpret_cast<unsigned char *>(ws) + kdpc_spatial_sort_bytes(b, n);
+        int rc = kdpc_spatial_sort(b, n, cand, cws, stream);
+        if (rc != 0) return rc;
+        if (query == cand && s == n) {
+            qws = cws;
+        } else {
+            rc = kdpc_spatial_sort(b, s, query, qws, stream);
+            if (rc != 0) return rc;
+        }
+        return kdpc_knn_sorted(b, s, n, k, direct, qws, cws, idx32, idx64, dist, stream);
+    }
+    if (direct)
+        return kdpc::launch_knn<kdpc::DIST_DIRECT>(b, s, n, k, query, cand, ws, idx32, idx64, dist, to_stream(stream));
+    return kdpc::launch_knn<kdpc::DIST_EXPANSION>(b, s, n, k, query, cand, ws, idx32, idx64, dist, to_stream(stream));
+}
+
 KDPC_API int kdpc_knn(int b, int s, int n, int k, const float *query, const float *cand, void *ws,
                       int *idx32, long long *idx64, float *dist, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(query && cand && ws && b > 0 && s > 0 && n > 0 && k > 0);
+    return knn_dispatch(b, s, n, k, 0, query, cand, ws, idx32, idx64, dist, stream);
+}
+
+KDPC_API int kdpc_knn_bruteforce(int b, int s, int n, int k, const float *query, const float *cand, void *ws,
+                                 int *idx32, long long *idx64, float *dist, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(query && cand && ws && b > 0 && s > 0 && n > 0 && k > 0);
     if (k > 32 || b > 65535) return KDPC_EUNSUPPORTED;
     return kdpc::launch_knn<kdpc::DIST_EXPANSION>(b, s, n, k, query, cand, ws, idx32, idx64, dist, to_stream(stream));
@@ -210,8 +248,7 @@ KDPC_API int kdpc_knn(int b, int s, int n, int k, const float *query, const floa
 KDPC_API int kdpc_three_nn(int b, int n, int m, const float *unknown, const float *known, void *ws,
                            float *dist2, int *idx, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(unknown && known && ws && dist2 && idx && b > 0 && n > 0 && m > 0);
-    if (b > 65535) return KDPC_EUNSUPPORTED;
-    return kdpc::launch_knn<kdpc::DIST_DIRECT>(b, n, m, 3, unknown, known, ws, idx, nullptr, dist2, to_stream(stream));
+    return knn_dispatch(b, n, m, 3, 1, unknown, known, ws, idx, nullptr, dist2, stream);
 }
 
 KDPC_API int kdpc_square_distance(int b, int s, int n, const float *src, const float *dst, float *out,

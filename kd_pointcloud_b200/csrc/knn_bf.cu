@@ -1,0 +1,415 @@
+// Exact k-nearest neighbours by best-first search over spatially sorted tiles (sm_100a).
+//
+// Same contract and bit-identical results as the brute-force kernel in knn.cu (ascending
+// (distance, index) with the reference's  -2 q.c + |q|^2 + |c|^2  rounding sequence,
+// pointconv_util.py:73-107), but the S x N distance matrix is never even *computed* in full:
+//
+//   1. spatial_sort_kernel (one CTA per cloud): Morton-orders the cloud (register/shuffle/shared-memory
+//      bitonic sort of 32-bit (18-bit code, index) keys), writes the points as float4 (x, y, z, |p|^2) in that
+//      order plus the original indices, and one bounding box per tile of 64 consecutive points.
+//   2. knn_bf_kernel: one WARP per query.  The warp ranks the candidate tiles by a lower bound of the
+//      distance between the query and the tile box, visits them nearest-first (64 candidates = two
+//      coalesced 32-wide steps, software-prefetched one tile ahead) and STOPS at the first tile whose
+//      bound exceeds the current K-th distance.  The K best are kept distributed over the lanes (lane j
+//      = j-th smallest), so an insertion is a ballot + shuffle-up.  At 8192 uniformly distributed
+//      points a query visits ~5 (K = 3) to ~10 (K = 32) of the 128 tiles.
+//
+// Exactness.  The bound is conservative w.r.t. the rounding of the expansion formula: for any
+// candidate c in a tile,  d_fp32(q, c) >= |q-c|^2 - 10u(|q|^2+|c|^2)  (u = 2^-24; derivation in
+// DESIGN.md), and the tile is skipped only if  boxdist^2 - 4e-6 (max|q|^2 + max|c|^2) > tau_max,
+// so no candidate that could enter the list (d <= tau) is ever skipped.  Ties are resolved
+// by the explicit (distance, index) order, independent of the visiting order.
+#include "common.cuh"
+
+namespace kdpc {
+
+constexpr int BF_TILE = 64;              // candidates per tile
+constexpr int BF_MAX_N = 16384;          // one CTA sorts a whole cloud in shared memory
+constexpr int SORT_THREADS = 1024;
+constexpr float BF_MARGIN = 4e-6f;
+
+// ---- 1. spatial sort -------------------------------------------------------------------------
+// ws layout per cloud b (all 16-byte aligned): sorted4 [n] float4 | boxes [ntiles] 2 x float4 | sidx [n] int
+struct SortedCloud {
+    float4 *p4;
+    float4 *boxes;
+    int *sidx;
+};
+static inline size_t sorted_cloud_bytes(int n) {
+    const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;
+    return (size_t)n * 16 + nt * 32 + (((size_t)n * 4 + 15) / 16) * 16;
+}
+__host__ __device__ static inline SortedCloud sorted_cloud_at(void *ws, int b, int n) {
+    const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;
+    const size_t per = (size_t)n * 16 + nt * 32 + (((size_t)n * 4 + 15) / 16) * 16;
+    unsigned char *base = reinterpret_cast<unsigned char *>(ws) + per * (size_t)b;
+    SortedCloud c;
+    c.p4 = reinterpret_cast<float4 *>(base);
+    c.boxes = reinterpret_cast<float4 *>(base + (size_t)n * 16);
+    c.sidx = reinterpret_cast<int *>(base + (size_t)n * 16 + nt * 32);
+    return c;
+}
+
+// Sort key: 18-bit Morton code (6 bits per axis, cubic cells) << 14 | point index (n <= 16384): 32-bit keys,
+// unique, so the order is deterministic.  Bitonic network with E consecutive elements per thread:
+// strides < E are exchanged in registers, strides < 32E by warp shuffles, only the longer ones through
+// shared memory (15 of the 91 sub-stages at n = 8192).
+__device__ __forceinline__ unsigned expand6(unsigned v) {      // 6 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000300Fu;
+    v = (v | (v << 4)) & 0x000030C3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+
+template <int E>
+__global__ void __launch_bounds__(SORT_THREADS)
+spatial_sort_kernel(int n, int n2 /* pow2 >= n, = E * blockDim.x */, const float *__restrict__ xyz, void *__restrict__ ws) {
+    extern __shared__ __align__(16) unsigned skeys[];                      // n2 keys
+    __shared__ float red[6][32];
+    __shared__ float bb[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int b = blockIdx.x;
+    const float *p = xyz + (size_t)b * n * 3;
+
+    // cloud bounding box
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < n; i += nthreads) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = p[i * 3 + c];
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float l = lane < nwarps ? red[c][lane] : INFINITY, h = lane < nwarps ? red[3 + c][lane] : -INFINITY;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+                h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+            }
+            if (lane == 0) { bb[c] = l; bb[3 + c] = h; }
+        }
+    }
+    __syncthreads();
+    const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), fmaxf(bb[5] - bb[2], 1e-30f));
+    const float scale = 63.f / ext;                                        // cubic cells
+
+    unsigned key[E];                                                       // elements tid*E .. tid*E+E-1
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int i = tid * E + r;
+        key[r] = 0xffffffffu;
+        if (i < n) {
+            const unsigned cx = (unsigned)fminf(fmaxf((p[i * 3 + 0] - bb[0]) * scale, 0.f), 63.f);
+            const unsigned cy = (unsigned)fminf(fmaxf((p[i * 3 + 1] - bb[1]) * scale, 0.f), 63.f);
+            const unsigned cz = (unsigned)fminf(fmaxf((p[i * 3 + 2] - bb[2]) * scale, 0.f), 63.f);
+            const unsigned code = (expand6(cx) << 2) | (expand6(cy) << 1) | expand6(cz);
+            key[r] = (code << 14) | (unsigned)i;
+        }
+    }
+    // ascending bitonic sort
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j >= E; j >>= 1) {
+            if (j >= 32 * E) {                                             // partner in another warp
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; ++r) skeys[tid * E + r] = key[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const int i = tid * E + r;
+                    const unsigned c = skeys[i ^ j];
+                    const bool keep_min = ((i & j) == 0) == ((i & kk) == 0);
+                    key[r] = keep_min ? min(key[r], c) : max(key[r], c);
+                }
+            } else {                                                       // partner in another lane, same slot
+                const bool keep_min = (((tid * E) & j) == 0) == (((tid * E) & kk) == 0);   // j, kk >= E: slot bits irrelevant
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned c = __shfl_xor_sync(0xffffffffu, key[r], j / E);
+                    key[r] = keep_min ? min(key[r], c) : max(key[r], c);
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = E >> 1; jj > 0; jj >>= 1) {                          // partner in this thread: static register pairs
+            if (jj < kk) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & jj) == 0) {
+                        const bool up = (((tid * E + r) & kk) == 0);
+                        const unsigned a = key[r], c = key[r | jj];
+                        const bool sw = (a > c) == up;
+                        key[r] = sw ? c : a;
+                        key[r | jj] = sw ? a : c;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; ++r) skeys[tid * E + r] = key[r];
+    __syncthreads();
+
+    SortedCloud out = sorted_cloud_at(ws, b, n);
+    for (int i = tid; i < n; i += nthreads) {
+        const int src = (int)(skeys[i] & 0x3fffu);
+        const float x = p[src * 3 + 0], y = p[src * 3 + 1], z = p[src * 3 + 2];
+        out.p4[i] = make_float4(x, y, z, sq_norm3(x, y, z));
+        out.sidx[i] = src;
+    }
+    // tile boxes: one warp per tile
+    const int ntiles = (n + BF_TILE - 1) / BF_TILE;
+    for (int t = warp; t < ntiles; t += nwarps) {
+        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY}, cc = 0.f;
+#pragma unroll
+        for (int e = 0; e < BF_TILE / 32; ++e) {
+            const int i = t * BF_TILE + e * 32 + lane;
+            if (i < n) {
+                const int src = (int)(skeys[i] & 0x3fffu);
+                const float x = p[src * 3 + 0], y = p[src * 3 + 1], z = p[src * 3 + 2];
+                l[0] = fminf(l[0], x); h[0] = fmaxf(h[0], x);
+                l[1] = fminf(l[1], y); h[1] = fmaxf(h[1], y);
+                l[2] = fminf(l[2], z); h[2] = fmaxf(h[2], z);
+                cc = fmaxf(cc, sq_norm3(x, y, z));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                l[c] = fminf(l[c], __shfl_xor_sync(0xffffffffu, l[c], o));
+                h[c] = fmaxf(h[c], __shfl_xor_sync(0xffffffffu, h[c], o));
+            }
+            cc = fmaxf(cc, __shfl_xor_sync(0xffffffffu, cc, o));
+        }
+        if (lane == 0) {
+            out.boxes[2 * t] = make_float4(l[0], l[1], l[2], cc);
+            out.boxes[2 * t + 1] = make_float4(h[0], h[1], h[2], 0.f);
+        }
+    }
+}
+
+// ---- 2. best-first search, one WARP per query ----------------------------------------------------
+// (d, i) < (e, j) in the (distance, index) order
+__device__ __forceinline__ bool lex_less(float d, int i, float e, int j) { return d < e || (d == e && i < j); }
+
+constexpr int BF_QPW = 4;                // max consecutive (Morton-adjacent) queries per warp
+constexpr int BF_CTA_WARPS = 8;
+constexpr unsigned BF_NONE = 0xffffffffu;
+
+// The K best of a query live DISTRIBUTED over the warp: lane j holds the j-th smallest (distance, index).
+// Candidates are tested 32 at a time (one per lane); the few that pass the current K-th distance are
+// inserted one by one with a ballot + shuffle-up (two dozen instructions, no divergence, no per-thread
+// sorted list).  No shared memory: tiles are 1 KB coalesced reads that stay in L1/L2.
+// Each lane ranks KEYS tiles (tile = e*32 + lane) by the query's own lower bound; the warp pops the
+// nearest remaining tile with one redux.min.
+template <int MODE, int KEYS>
+__global__ void __launch_bounds__(BF_CTA_WARPS * 32)
+knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const void *__restrict__ cws,
+              int *__restrict__ idx32, long long *__restrict__ idx64, float *__restrict__ dist_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const SortedCloud Q = sorted_cloud_at(const_cast<void *>(qws), b, s);
+    const SortedCloud C = sorted_cloud_at(const_cast<void *>(cws), b, n);
+    const int ntiles = (n + BF_TILE - 1) / BF_TILE;
+    const int qbeg = (blockIdx.x * BF_CTA_WARPS + warp) * qpw;
+    const int qend = min(s, qbeg + qpw);
+    const unsigned kbit = 1u << (k - 1);
+
+#pragma unroll 1
+    for (int qpos = qbeg; qpos < qend; ++qpos) {
+        const float4 q = __ldg(Q.p4 + qpos);
+        const int qorig = __ldg(Q.sidx + qpos);
+
+        // lower bound of the fp32 distance to every point of a tile (rounded DOWN to 24 bits) | tile id
+        unsigned keys[KEYS];
+#pragma unroll
+        for (int e = 0; e < KEYS; ++e) {
+            const int t = e * 32 + lane;
+            keys[e] = BF_NONE;
+            if (t < ntiles) {
+                const float4 bl = __ldg(C.boxes + 2 * t), bh = __ldg(C.boxes + 2 * t + 1);
+                const float dx = fmaxf(0.f, fmaxf(bl.x - q.x, q.x - bh.x));
+                const float dy = fmaxf(0.f, fmaxf(bl.y - q.y, q.y - bh.y));
+                const float dz = fmaxf(0.f, fmaxf(bl.z - q.z, q.z - bh.z));
+                const float lb = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - BF_MARGIN * (q.w + bl.w);
+                keys[e] = lb > 0.f ? ((__float_as_uint(lb) & 0xffffff00u) | (unsigned)t) : (unsigned)t;
+            }
+        }
+        auto pop_min = [&]() -> unsigned {                  // warp-uniform smallest remaining key
+            unsigned m = keys[0];
+#pragma unroll
+            for (int e = 1; e < KEYS; ++e) m = min(m, keys[e]);
+            m = __reduce_min_sync(0xffffffffu, m);
+#pragma unroll
+            for (int e = 0; e < KEYS; ++e) keys[e] = keys[e] == m ? BF_NONE : keys[e];
+            return m;
+        };
+        float4 pre[2];
+        int prei[2];
+        auto prefetch = [&](unsigned key) {
+            const int t = (int)(key & 0xffu);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = t * BF_TILE + h * 32 + lane;
+                const bool v = i < n;
+                pre[h] = v ? __ldg(C.p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                prei[h] = v ? __ldg(C.sidx + i) : 0x7fffffff;
+            }
+        };
+
+        float dj = INFINITY;                                // lane j: j-th best so far
+        int ij = 0x7fffffff;
+        float tau = INFINITY;                               // K-th best as of the last refresh (warp-uniform)
+        bool first = true;
+
+        unsigned cur = pop_min();
+        if (cur != BF_NONE) prefetch(cur);
+        while (cur != BF_NONE) {
+            // bound > 0 and beyond the K-th best: so is every remaining tile
+            if (cur >= 256u && __uint_as_float(cur & 0xffffff00u) > tau) break;
+            const float4 c0 = pre[0], c1 = pre[1];
+            const int ci0 = prei[0], ci1 = prei[1];
+            cur = pop_min();
+            if (cur != BF_NONE) prefetch(cur);              // next tile in flight while this one is scanned
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const float4 c = h ? c1 : c0;
+                float d = MODE == 0 ? expansion_dist(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w)
+                                    : direct_dist(q.x - c.x, q.y - c.y, q.z - c.z);
+                int i = h ? ci1 : ci0;
+                if (i == 0x7fffffff) d = INFINITY;          // slot beyond the cloud
+                if (first) {
+                    // the first 32 candidates: bitonic sort by (d, i) across the warp -> the initial list
+                    first = false;
+#pragma unroll
+                    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                        for (int j = kk >> 1; j > 0; j >>= 1) {
+                            const float pd = __shfl_xor_sync(0xffffffffu, d, j);
+                            const int pi = __shfl_xor_sync(0xffffffffu, i, j);
+                            const bool keep_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                            const bool take = keep_min ? lex_less(pd, pi, d, i) : lex_less(d, i, pd, pi);
+                            d = take ? pd : d;
+                            i = take ? pi : i;
+                        }
+                    }
+                    dj = d;
+                    ij = i;
+                } else {
+                    unsigned mask = __ballot_sync(0xffffffffu, d <= tau);
+                    while (mask) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float ds = __shfl_sync(0xffffffffu, d, l);
+                        const int is = __shfl_sync(0xffffffffu, i, l);
+                        // lanes whose entry comes after the candidate; it enters the list iff lane k-1 is one of them
+                        const bool before = lex_less(ds, is, dj, ij);
+                        const unsigned bm = __ballot_sync(0xffffffffu, before);
+                        if (bm & kbit) {                    // warp-uniform
+                            const int pos = __ffs(bm) - 1;
+                            const float ud = __shfl_up_sync(0xffffffffu, dj, 1);
+                            const int ui = __shfl_up_sync(0xffffffffu, ij, 1);
+                            if (before) {
+                                dj = lane == pos ? ds : ud;
+                                ij = lane == pos ? is : ui;
+                            }
+                        }
+                    }
+                }
+                tau = __shfl_sync(0xffffffffu, dj, k - 1);
+            }
+        }
+        if (lane < k) {
+            const size_t o = ((size_t)b * s + qorig) * k + lane;
+            if (idx32) idx32[o] = ij;
+            if (idx64) idx64[o] = ij;
+            if (dist_out) dist_out[o] = dj;
+        }
+    }
+}
+
+static inline int next_pow2(int n) {
+    int p = 64;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+static int launch_sort(int b, int n, const float *xyz, void *ws, cudaStream_t st) {
+    const int n2 = next_pow2(n);
+    const int threads = n2 < SORT_THREADS ? n2 : SORT_THREADS;
+    const size_t smem = (size_t)n2 * 4;
+    switch (n2 / threads) {
+        case 1: spatial_sort_kernel<1><<<b, threads, smem, st>>>(n, n2, xyz, ws); break;
+        case 2: spatial_sort_kernel<2><<<b, threads, smem, st>>>(n, n2, xyz, ws); break;
+        case 4: spatial_sort_kernel<4><<<b, threads, smem, st>>>(n, n2, xyz, ws); break;
+        case 8: spatial_sort_kernel<8><<<b, threads, smem, st>>>(n, n2, xyz, ws); break;
+        case 16:
+            KDPC_ENSURE_SMEM(spatial_sort_kernel<16>, BF_MAX_N * 4);
+            spatial_sort_kernel<16><<<b, threads, smem, st>>>(n, n2, xyz, ws);
+            break;
+        default: return KDPC_EUNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int MODE>
+static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cws, int *idx32, long long *idx64,
+                     float *dist, cudaStream_t st) {
+    // consecutive (Morton-adjacent) queries per warp: up to BF_QPW, fewer when the call is small so that the
+    // machine still gets ~48 warps per SM
+    int qpw = (int)(((long long)b * s) / (kNumSMs * 48));
+    qpw = qpw < 1 ? 1 : (qpw > BF_QPW ? BF_QPW : qpw);
+    const int per_cta = BF_CTA_WARPS * qpw;
+    dim3 grid((s + per_cta - 1) / per_cta, b);
+    const int ntiles = (n + BF_TILE - 1) / BF_TILE;
+#define KDPC_BF_CASE(KEYS) \
+    if (ntiles <= 32 * KEYS) { \
+        knn_bf_kernel<MODE, KEYS><<<grid, BF_CTA_WARPS * 32, 0, st>>>(s, n, k, qpw, qws, cws, idx32, idx64, dist); \
+        return (int)cudaGetLastError(); }
+    KDPC_BF_CASE(1)
+    KDPC_BF_CASE(2)
+    KDPC_BF_CASE(4)
+    KDPC_BF_CASE(8)
+#undef KDPC_BF_CASE
+    return KDPC_EUNSUPPORTED;
+}
+
+}  // namespace kdpc
+
+using namespace kdpc;
+
+KDPC_API long long kdpc_spatial_sort_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 0;
+    return (long long)sorted_cloud_bytes(n) * b;
+}
+
+KDPC_API int kdpc_spatial_sort(int b, int n, const float *xyz, void *ws, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(xyz && ws && b > 0 && n > 0);
+    if (n > BF_MAX_N) return KDPC_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(ws) % 16) != 0) return KDPC_EINVAL;
+    return launch_sort(b, n, xyz, ws, to_stream(stream));
+}
+
+KDPC_API int kdpc_knn_sorted(int b, int s, int n, int k, int direct, const void *query_sorted, const void *cand_sorted,
+                             int *idx32, long long *idx64, float *dist, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(query_sorted && cand_sorted && b > 0 && s > 0 && n > 0 && k > 0);
+    if (k > 32 || k > n || b > 65535 || n > BF_MAX_N) return KDPC_EUNSUPPORTED;
+    if (direct) return launch_bf<1>(b, s, n, k, query_sorted, cand_sorted, idx32, idx64, dist, to_stream(stream));
+    return launch_bf<0>(b, s, n, k, query_sorted, cand_sorted, idx32, idx64, dist, to_stream(stream));
+}

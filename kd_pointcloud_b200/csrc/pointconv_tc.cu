@@ -22,7 +22,7 @@ namespace tc {
 
 template <int KN>
 struct PointConvProducer {
-    static constexpr int kWarps = 8;
+    static constexpr int kWarps = 8, kGroups = 1;
     struct Args {
         const float *cand_xyz;    // [B,N,3]
         const float *query_xyz;   // [B,S,3]
@@ -31,6 +31,7 @@ struct PointConvProducer {
         int n_cand, s, d;
         float w1[24], b1[8], w2[64], b2[8], w3[128], b3[16];    // WeightNet 3 -> 8 -> 8 -> 16, ReLU after each
     };
+    static __device__ __forceinline__ void prologue(const Args &, int, int) {}
     const Args &a;
     const GemmShape &g;
     float wn[KN][8];

@@ -65,6 +65,8 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
 
 // Producer concept:
 //   struct P { struct Args {...};
+//              static constexpr int kWarps, kGroups;   // producer warps, independent groups (kWarps/kGroups warps fill one stage)
+//              static __device__ void prologue(const Args&, int tid, int nthreads);      // all threads, before the role split
 //              __device__ P(const Args&, const GemmShape&);
 //              __device__ void begin_tile(long long tile, int r);                       // r = producer thread 0..127 = tile row
 //              __device__ void fill(int chunk, unsigned char *a_hi, unsigned char *a_lo, int r); };
@@ -89,7 +91,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
-            mbar_init(&full_a[s], PW);       // one arrive per producer warp
+            mbar_init(&full_a[s], PW / Producer::kGroups);   // one arrive per producer warp of the filling group
             mbar_init(&full_b[s], 1);        // expect_tx arrive of the W loader
             mbar_init(&empty[s], 1);         // tcgen05.commit
         }
@@ -99,6 +101,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         }
         mbar_fence_init();
     }
+    Producer::prologue(pa, tid, (int)blockDim.x);                            // optional CTA-wide staging (before the role split)
     if (warp == PW) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
     fence_before_sync();
     __syncthreads();
@@ -107,20 +110,27 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
 
     if (warp < PW) {
         // ================= A producers =================
+        // PG independent groups of GW warps; group g fills pipeline iterations it = g (mod PG), so PG
+        // gather round-trips are in flight per SM.
+        constexpr int PG = Producer::kGroups, GW = PW / PG;
+        const int grp = warp / GW;
+        const int ptid = tid - grp * GW * 32;
         Producer prod(pa, g);
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-            prod.begin_tile(tile, tid);
+            bool began = false;
             for (int c = 0; c < g.num_chunks; ++c, ++it) {
+                if (PG > 1 && (int)(it % PG) != grp) continue;
+                if (!began) { prod.begin_tile(tile, ptid); began = true; }
                 const int s = it % g.stages;
                 const uint32_t ph = (it / g.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                if (tid == 0) {                                   // weight chunk for this stage (bulk TMA, async)
+                if (ptid == 0) {                                  // weight chunk for this stage (bulk TMA, async)
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
                     tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)c * bbytes, (uint32_t)bbytes, &full_b[s]);
                 }
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
-                prod.fill(c, a_hi, a_hi + A_PART_BYTES, tid);
+                prod.fill(c, a_hi, a_hi + A_PART_BYTES, ptid);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_a[s]);
@@ -238,12 +248,13 @@ struct StoreEpilogue {
 // ------------------------------------------------------------------------------------------
 // Producer: plain fp32 rows x[M, ldx] (K contiguous).
 struct PlainProducer {
-    static constexpr int kWarps = 4;
+    static constexpr int kWarps = 8, kGroups = 2;        // two groups of 4 warps alternate K-chunks
     struct Args {
         const float *x;
         int ldx;
         int k;
     };
+    static __device__ __forceinline__ void prologue(const Args &, int, int) {}
     const Args &a;
     const GemmShape &g;
     const float *rowp;

@@ -64,9 +64,11 @@ def clear_caches(weights: bool = False) -> None:
     ``weights=True`` also drops the packed-weight / folded-affine caches."""
     _KNN_CACHE.clear()
     _CSR_CACHE.clear()
+    _SORT_CACHE.clear()
     if weights:
         _PACK_CACHE.clear()
         _AFFINE_CACHE.clear()
+        _WN_CACHE.clear()
 
 
 def set_cache_enabled(flag: bool) -> None:
@@ -91,6 +93,46 @@ def cm(x: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- kNN (a6, a7)
+_SORT_CACHE = _LRU(48)
+
+
+def _sorted_cloud(xyz_d: torch.Tensor) -> torch.Tensor:
+    """Morton-sorted copy of a contiguous [B,N,3] cloud, cached per tensor (storage, version): every point
+    set of the pyramid takes part in several kNN calls (as queries and as candidates)."""
+    if not _CACHE_ENABLED:
+        return K.spatial_sort(xyz_d)
+    key = _tkey(xyz_d)
+    hit = _SORT_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    # a batch slice of an already sorted batch (pc1 / pc2 halves of the 2B-cloud encoder batch): clouds are
+    # sorted independently and stored back to back, so the slice of the buffer is the sorted slice
+    B, N, _ = xyz_d.shape
+    per = N * 12
+    for pkey, (buf, parent) in list(_SORT_CACHE.d.items()):
+        if parent.shape[1] != N or parent._version != pkey[1] or parent.device != xyz_d.device:
+            continue
+        off = xyz_d.data_ptr() - parent.data_ptr()
+        if off >= 0 and off % per == 0 and off // per + B <= parent.shape[0]:
+            each = buf.numel() // parent.shape[0]
+            out = buf[(off // per) * each:(off // per + B) * each]
+            _SORT_CACHE.put(key, (out, xyz_d))
+            return out
+    out = K.spatial_sort(xyz_d)
+    _SORT_CACHE.put(key, (out, xyz_d))
+    return out
+
+
+def _knn_compute(nsample: int, xyz_d: torch.Tensor, new_d: torch.Tensor) -> torch.Tensor:
+    n, s = xyz_d.shape[1], new_d.shape[1]
+    if ops.SORT_MIN_N <= n <= ops.SORT_MAX_N and s <= ops.SORT_MAX_N and xyz_d.shape[0] > 0:
+        cs = _sorted_cloud(xyz_d)
+        same = new_d.data_ptr() == xyz_d.data_ptr() and new_d.shape == xyz_d.shape
+        qs = cs if same else _sorted_cloud(new_d)
+        return K.knn_sorted(qs, cs, xyz_d.shape[0], s, n, nsample)
+    return K.knn(new_d, xyz_d, nsample)
+
+
 def knn_idx(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
     """int32 [B,S,nsample] neighbours of new_xyz in xyz, ascending (distance, index)."""
     xyz_d = xyz.detach()
@@ -100,12 +142,12 @@ def knn_idx(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Ten
     if not new_d.is_contiguous():
         new_d = new_d.contiguous()
     if not _CACHE_ENABLED:
-        return K.knn(new_d, xyz_d, nsample)
+        return _knn_compute(nsample, xyz_d, new_d)
     key = (nsample, _tkey(xyz_d), _tkey(new_d))
     hit = _KNN_CACHE.get(key)
     if hit is not None:
         return hit[0]
-    idx = K.knn(new_d, xyz_d, nsample)
+    idx = _knn_compute(nsample, xyz_d, new_d)
     _KNN_CACHE.put(key, (idx, xyz_d, new_d))       # keep the keyed tensors alive: no address reuse
     return idx
 
@@ -370,6 +412,61 @@ def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
                                 None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi,
                                 None if res is None else res[..., c0:c1].contiguous()))
     return torch.cat(outs, dim=-1)
+
+
+# ------------------------------------------------------------------- fused PointConv / cost volume
+_WN_CACHE = _LRU(256)
+
+
+def _weightnet_host_params(convs):
+    """The 248 parameters of a WeightNet(3, 16, hidden=[8, 8]) as a host float list in kernel-launch order
+    (w1 b1 w2 b2 w3 b3); one device->host copy per weight version (the fused kernel takes them as
+    launch parameters so that every FFMA reads its weight from the constant bank)."""
+    ts = [t for c in convs for t in (c.weight, c.bias)]
+    key = tuple(_tkey(t) for t in ts)
+    hit = _WN_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    with torch.no_grad():
+        flat = torch.cat([t.detach().reshape(-1).float() for t in ts]).cpu().tolist()
+    _WN_CACHE.put(key, (flat, ts))
+    return flat
+
+
+def fused_pointconv_available(weightnet, linear, bn, nsample: int, feats: torch.Tensor) -> bool:
+    """Inference-only fused PointConv: K in {9, 16}, WeightNet(3->8->8->16) without BN, D % 4 == 0, Cout <= 256."""
+    c = weightnet.mlp_convs
+    if weightnet.bn or len(c) != 3 or (c[0].in_channels, c[0].out_channels, c[1].out_channels, c[2].out_channels) != (3, 8, 8, 16):
+        return False
+    if nsample not in FUSED_POINTCONV_K or feats is None or feats.shape[2] % 4 != 0 or linear.out_features > 256:
+        return False
+    if linear.in_features != 16 * (feats.shape[2] + 3):
+        return False
+    if torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in weightnet.parameters())):
+        return False
+    return fused_linear_available(feats, linear.weight, linear.bias, bn)
+
+
+FUSED_POINTCONV_K = (9,)
+
+
+def fused_pointconv(cand_xyz, query_xyz, feats, idx, weightnet, linear, bn, slope: float) -> torch.Tensor:
+    """[B,S,Cout] = act(bn(Linear(sum_k [feats[idx], rel_xyz] (x) WeightNet(rel_xyz)))) in ONE kernel."""
+    d = feats.shape[2]
+    wp = _packed_weight(linear.weight, 1, d, 16)
+    scale, shift = _fold_affine(linear.bias, bn)
+    return K.pointconv_fused(cand_xyz.contiguous(), query_xyz.contiguous(), feats.contiguous(), _as_i32(idx),
+                             _weightnet_host_params(weightnet.mlp_convs), wp, linear.out_features, scale, shift, slope)
+
+
+def fused_costvol(xyz1, xyz2, p1, p2, idx, pos, slope_pre: float, conv, slope_post: float) -> torch.Tensor:
+    """max_k act(conv(act(p2[idx] + p1 + pos(xyz2[idx] - xyz1)))) -> [B,N1,Dout] in ONE kernel."""
+    d = p1.shape[2]
+    w2d = conv.weight.reshape(conv.weight.shape[0], -1)
+    return K.costvol_fused(xyz1.contiguous(), xyz2.contiguous(), p1.contiguous(), p2.contiguous(), _as_i32(idx),
+                           pos.weight.detach().reshape(d, 3).contiguous(), pos.bias.detach(), slope_pre,
+                           _packed_weight(w2d), w2d.shape[0], None if conv.bias is None else conv.bias.detach(),
+                           slope_post)
 
 
 # ------------------------------------------------------------------- PointConv pieces

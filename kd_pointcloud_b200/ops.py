@@ -155,7 +155,7 @@ def _three_nn(unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor,
     with _guard(unknown):
         dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
         idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
-        ws = torch.empty((B * M * 4,), dtype=torch.float32, device=unknown.device)
+        ws = torch.empty((_lib.lib().kdpc_knn_workspace_bytes(B, N, M),), dtype=torch.uint8, device=unknown.device)
         if dist2.numel():
             _call("kdpc_three_nn", B, N, M, _p(unknown), _p(known), _p(ws), _p(dist2), _p(idx), _stream())
     return dist2, idx
@@ -237,7 +237,7 @@ def _knn_impl(query, cand, k, want64, want_dist):
         idx32 = torch.empty((B, S, k), dtype=torch.int32, device=dev)
         idx64 = torch.empty((B, S, k), dtype=torch.int64, device=dev) if want64 else None
         dist = torch.empty((B, S, k), dtype=torch.float32, device=dev) if want_dist else None
-        ws = torch.empty((B * N * 4,), dtype=torch.float32, device=dev)
+        ws = torch.empty((_lib.lib().kdpc_knn_workspace_bytes(B, S, N),), dtype=torch.uint8, device=dev)
         if idx32.numel():
             _call("kdpc_knn", B, S, N, k, _p(query), _p(cand), _p(ws), _p(idx32), _p(idx64), _p(dist), _stream())
     return idx32, idx64, dist
@@ -267,6 +267,54 @@ _register("knn64(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn64,
 _register("knn_dist(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn_dist,
           lambda q, c, k: (q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32),
                            q.new_empty((q.shape[0], q.shape[1], k))))
+
+
+def _knn_bruteforce(query: torch.Tensor, cand: torch.Tensor, k: int) -> torch.Tensor:
+    _req(query, torch.float32, 3, "new_xyz")
+    _req(cand, torch.float32, 3, "xyz")
+    B, S, _ = query.shape
+    N = cand.shape[1]
+    with _guard(query):
+        idx32 = torch.empty((B, S, k), dtype=torch.int32, device=query.device)
+        ws = torch.empty((B * N * 4,), dtype=torch.float32, device=query.device)
+        _call("kdpc_knn_bruteforce", B, S, N, k, _p(query), _p(cand), _p(ws), _p(idx32), None, None, _stream())
+    return idx32
+
+
+SORT_MAX_N = 16384
+SORT_MIN_N = 256
+
+
+def _spatial_sort(xyz: torch.Tensor) -> torch.Tensor:
+    """xyz [B,N,3] -> opaque uint8 buffer holding the Morton-sorted clouds (kdpc_spatial_sort)."""
+    _req(xyz, torch.float32, 3, "xyz")
+    B, N, _ = xyz.shape
+    with _guard(xyz):
+        out = torch.empty((_lib.lib().kdpc_spatial_sort_bytes(B, N),), dtype=torch.uint8, device=xyz.device)
+        _call("kdpc_spatial_sort", B, N, _p(xyz), _p(out), _stream())
+    return out
+
+
+def _knn_sorted(qsorted: torch.Tensor, csorted: torch.Tensor, b: int, s: int, n: int, k: int) -> torch.Tensor:
+    _req(qsorted, torch.uint8, 1, "sorted queries")
+    _req(csorted, torch.uint8, 1, "sorted candidates")
+    if k > n:
+        raise RuntimeError(f"kdpc: knn k={k} exceeds the number of candidates {n}")
+    L = _lib.lib()
+    if qsorted.numel() != L.kdpc_spatial_sort_bytes(b, s) or csorted.numel() != L.kdpc_spatial_sort_bytes(b, n):
+        raise ValueError("kdpc: sorted-cloud buffer does not match (b, s, n)")
+    with _guard(qsorted):
+        idx32 = torch.empty((b, s, k), dtype=torch.int32, device=qsorted.device)
+        if idx32.numel():
+            _call("kdpc_knn_sorted", b, s, n, k, 0, _p(qsorted), _p(csorted), _p(idx32), None, None, _stream())
+    return idx32
+
+
+_register("knn_bruteforce(Tensor query, Tensor cand, int k) -> Tensor", _knn_bruteforce,
+          lambda q, c, k: q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32))
+_register("spatial_sort(Tensor xyz) -> Tensor", _spatial_sort, lambda xyz: xyz.new_empty((1,), dtype=torch.uint8))
+_register("knn_sorted(Tensor qsorted, Tensor csorted, int b, int s, int n, int k) -> Tensor", _knn_sorted,
+          lambda q, c, b, s, n, k: q.new_empty((b, s, k), dtype=torch.int32))
 
 
 # ------------------------------------------------------------------------------------- a8, a9
@@ -464,6 +512,55 @@ _register("linear_tc(Tensor x, Tensor wpacked, int n, Tensor? scale, Tensor? shi
 _register("linear_simt(Tensor x, Tensor w, Tensor? scale, Tensor? shift, float slope, float lo, float hi, "
           "Tensor? residual) -> Tensor", _linear_simt,
           lambda x, w, sc, sh, sl, lo, hi, r: x.new_empty(tuple(x.shape[:-1]) + (w.shape[0],)))
+
+
+# ------------------------------------------------------------------- fused tcgen05 layers
+def _pointconv_fused(cand_xyz, query_xyz, feats, idx, wn_params, wpacked, n_out: int, scale, shift,
+                     slope: float) -> torch.Tensor:
+    import ctypes
+    _req(cand_xyz, torch.float32, 3, "xyz")
+    _req(query_xyz, torch.float32, 3, "new_xyz")
+    _req(feats, torch.float32, 3, "points")
+    _req(idx, torch.int32, 3, "idx")
+    B, N, _ = cand_xyz.shape
+    _, S, K = idx.shape
+    D = feats.shape[2]
+    if len(wn_params) != 248:
+        raise ValueError("kdpc: pointconv_fused expects the 248 WeightNet(3,8,8,16) parameters")
+    host = (ctypes.c_float * 248)(*wn_params)
+    with _guard(feats):
+        out = torch.empty((B, S, n_out), dtype=torch.float32, device=feats.device)
+        if out.numel():
+            _call("kdpc_pointconv_fused", B, N, S, K, D, n_out, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx),
+                  ctypes.cast(host, ctypes.c_void_p), _p(wpacked), _p(scale), _p(shift), float(slope), _p(out), _stream())
+    return out
+
+
+def _costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, slope_pre: float, wpacked, n_out: int, bias,
+                   slope_post: float) -> torch.Tensor:
+    for t, nm in ((xyz1, "xyz1"), (xyz2, "xyz2"), (p1, "points1"), (p2, "points2")):
+        _req(t, torch.float32, 3, nm)
+    _req(idx, torch.int32, 3, "idx")
+    _req(pos_w, torch.float32, None, "pos weight")
+    _req(pos_b, torch.float32, 1, "pos bias")
+    B, S, _ = xyz1.shape
+    N = xyz2.shape[1]
+    K = idx.shape[2]
+    D = p1.shape[2]
+    with _guard(p1):
+        out = torch.empty((B, S, n_out), dtype=torch.float32, device=p1.device)
+        if out.numel():
+            _call("kdpc_costvol_fused", B, S, N, K, D, n_out, _p(xyz1), _p(xyz2), _p(p1), _p(p2), _p(idx), _p(pos_w),
+                  _p(pos_b), float(slope_pre), _p(wpacked), _p(bias), float(slope_post), _p(out), _stream())
+    return out
+
+
+_register("pointconv_fused(Tensor cand_xyz, Tensor query_xyz, Tensor feats, Tensor idx, float[] wn_params, "
+          "Tensor wpacked, int n_out, Tensor? scale, Tensor? shift, float slope) -> Tensor", _pointconv_fused,
+          lambda c, q, f, idx, wn, wp, n, sc, sh, sl: f.new_empty((idx.shape[0], idx.shape[1], n)))
+_register("costvol_fused(Tensor xyz1, Tensor xyz2, Tensor p1, Tensor p2, Tensor idx, Tensor pos_w, Tensor pos_b, "
+          "float slope_pre, Tensor wpacked, int n_out, Tensor? bias, float slope_post) -> Tensor", _costvol_fused,
+          lambda x1, x2, p1, p2, idx, pw, pb, s0, wp, n, b, s1: p1.new_empty((p1.shape[0], p1.shape[1], n)))
 
 
 # --------------------------------------------------------------------------- backward plumbing

@@ -25,6 +25,7 @@ LEAKY_RATE = 0.1
 use_bn = False
 
 K = torch.ops.kdpc
+FUSED_COSTVOL = True      # tests flip this to compare the fused kernel with the op chain
 
 
 def _act(use_leaky: bool) -> nn.Module:
@@ -214,6 +215,9 @@ class _PointConvBase(nn.Module):
     def _contract(self, s_xyz, q_xyz, s_points, idx) -> torch.Tensor:
         """grouping + WeightNet + sum over K + Linear (+BN) + activation; everything point-major.
         s_xyz [B,N,3] support, q_xyz [B,S,3] queries, s_points [B,N,D] -> [B,S,Cout]."""
+        bn = self.bn_linear if self.bn else None
+        if KF.fused_pointconv_available(self.weightnet, self.linear, bn, idx.shape[2], s_points):
+            return KF.fused_pointconv(s_xyz, q_xyz, s_points, idx, self.weightnet, self.linear, bn, _slope(self.relu))
         grouped = KF.group_concat(s_xyz, q_xyz, s_points, idx)            # [B,S,K,3+D]
         wn = self.weightnet.forward_pm(grouped)                           # [B,S,K,W]
         agg = KF.pointconv_agg(grouped, wn)                               # [B,S,(3+D)*W]  (c-major)
@@ -291,6 +295,12 @@ class CrossLayerLight(nn.Module):
         D = points1.shape[2]
         needs_grad = torch.is_grad_enabled() and any(
             t.requires_grad for t in (xyz1, xyz2, points1, points2, pos.weight, pos.bias))
+        if (FUSED_COSTVOL and isinstance(bn, nn.Identity) and not needs_grad and self.nsample == 32 and D % 8 == 0 and D <= 256
+                and points2.shape[2] == D and len(mlp) == 1 and _is_pointwise(mlp[0].composed_module[0])
+                and isinstance(mlp[0].composed_module[1], nn.Identity) and mlp[0].out_channels <= 256
+                and KF.fused_linear_available(points1, mlp[0].composed_module[0].weight, mlp[0].composed_module[0].bias, None)):
+            return KF.fused_costvol(xyz1, xyz2, points1, points2, idx, pos, _slope(self.relu), mlp[0].composed_module[0],
+                                    _slope(mlp[0].composed_module[2]))
         if isinstance(bn, nn.Identity) and D % 4 == 0 and points2.shape[2] == D and not needs_grad:
             x = K.costvol_pre(xyz1.contiguous(), xyz2.contiguous(), points1.contiguous(), points2.contiguous(), idx,
                               pos.weight.reshape(D, 3), pos.bias, _slope(self.relu))

@@ -68,6 +68,35 @@ def test_knn_bit_exact_indices_and_distances(s, n, k, mode):
     assert i64.dtype == torch.int64 and torch.equal(i64.cpu(), ref_i.long()) and torch.equal(i32, idx)
 
 
+@pytest.mark.parametrize("b,s,n,k,mode", [
+    (8, 8192, 8192, 32, "ft3d"), (4, 8192, 8192, 32, "dup"), (4, 8192, 8192, 9, "cm"), (2, 8192, 8192, 3, "grid"),
+    (4, 2048, 8192, 16, "kitti"), (4, 8192, 2048, 3, "ft3d"), (3, 1000, 5000, 10, "dup"), (2, 16384, 16384, 16, "ft3d"),
+    (2, 300, 256, 32, "grid"), (2, 257, 999, 5, "cm"),
+])
+def test_knn_pruned_search_equals_brute_force(b, s, n, k, mode):
+    """Size-independent property at full size: the best-first tile-pruned search (sorted clouds, conservative
+    bound) returns exactly what scanning every candidate returns - including clouds full of exact ties."""
+    cand = _cloud(b, n, 400 + n, mode).to(DEV)
+    query = cand if s == n else _cloud(b, s, 500 + s, mode).to(DEV)
+    brute = K.knn_bruteforce(query, cand, k)
+    assert torch.equal(K.knn(query, cand, k), brute)
+    qs, cs = K.spatial_sort(query), K.spatial_sort(cand)
+    assert torch.equal(K.knn_sorted(qs, cs, b, s, n, k), brute)
+    # cross-frame queries far from the candidates (warped clouds): bounds stay conservative
+    far = (query + torch.tensor([3.0, -2.0, 5.0], device=DEV)).contiguous()
+    assert torch.equal(K.knn(far, cand, k), K.knn_bruteforce(far, cand, k))
+
+
+def test_knn_pruned_degenerate_clouds():
+    one = torch.ones(2, 1024, 3, device=DEV) * 3.25                      # all points identical
+    assert torch.equal(K.knn(one, one, 16), K.knn_bruteforce(one, one, 16))
+    line = torch.zeros(1, 4096, 3, device=DEV)
+    line[0, :, 0] = torch.arange(4096, device=DEV) * 0.5                  # collinear
+    assert torch.equal(K.knn(line, line, 9), K.knn_bruteforce(line, line, 9))
+    big = _cloud(1, 2048, 1, "kitti").to(DEV) * 100.0                     # large coordinates: large rounding noise
+    assert torch.equal(K.knn(big, big, 32), K.knn_bruteforce(big, big, 32))
+
+
 def test_knn_batched_and_cached():
     d = make_pairs(3, 1024, seed=9)
     xyz, q = d["pos1"].to(DEV), d["pos2"][:, :200].contiguous().to(DEV)

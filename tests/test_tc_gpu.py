@@ -96,3 +96,91 @@ def test_fused_linear_frontend_matches_torch_modules():
         lin.weight.mul_(2.0)
         y2 = KF.fused_linear(x, lin.weight, lin.bias, None, 1.0)
         assert _err(y2, lin(x).double()) < 2e-5
+
+
+# ------------------------------------------------------------------ fused PointConv / cost volume
+def _gather(points, idx):
+    B = points.shape[0]
+    return points[torch.arange(B, device=points.device).view(B, 1, 1), idx.long()]
+
+
+def _pointconv_ref64(cand, query, feats, idx, wn_convs, lin_w, scale, shift, slope):
+    rel = _gather(cand, idx).double() - query.double().unsqueeze(2)                   # [B,S,K,3]
+    grouped = torch.cat([rel, _gather(feats, idx).double()], dim=-1)                  # [B,S,K,3+D]
+    w = rel
+    for c in wn_convs:
+        w = torch.relu(w @ c.weight.double().reshape(c.out_channels, -1).t() + c.bias.double())
+    agg = torch.einsum("bskc,bskw->bscw", grouped, w).reshape(grouped.shape[0], grouped.shape[1], -1)
+    y = agg @ lin_w.double().t()
+    y = y * scale.double() + shift.double()
+    return torch.where(y > 0, y, y * slope)
+
+
+@pytest.mark.parametrize("B,N,S,D,Cout", [(2, 1024, 1024, 32, 64), (1, 700, 300, 128, 128), (3, 512, 512, 320, 128),
+                                          (1, 8192, 8192, 128, 128)])
+def test_pointconv_fused_matches_fp64(B, N, S, D, Cout):
+    from kd_pointcloud_b200 import pointconv_util as P
+    torch.manual_seed(B * 1000 + D)
+    cand = (torch.rand(B, N, 3, device=DEV) * 4 - 2)
+    query = cand[:, :S].contiguous() if S <= N else torch.rand(B, S, 3, device=DEV)
+    feats = torch.randn(B, N, D, device=DEV)
+    idx = K.knn(query, cand, 9)
+    wn = P.WeightNet(3, 16).to(DEV)
+    lin = torch.nn.Linear(16 * (D + 3), Cout).to(DEV)
+    scale, shift = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
+    wp = K.pack_weight(lin.weight.detach(), 1, D, 16)
+    params = KF._weightnet_host_params(wn.mlp_convs)
+    with torch.no_grad():
+        y = K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, scale, shift, 0.1)
+        ref = _pointconv_ref64(cand, query, feats, idx, wn.mlp_convs, lin.weight, scale, shift, 0.1)
+    assert y.shape == (B, S, Cout)
+    assert _err(y, ref) < 2e-5
+    assert torch.equal(y, K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, scale, shift, 0.1))
+
+
+@pytest.mark.parametrize("B,N1,N2,D", [(2, 1024, 1024, 32), (1, 333, 500, 64), (2, 256, 256, 256), (1, 8192, 8192, 32),
+                                        (1, 2048, 2048, 128)])
+def test_costvol_fused_matches_fp64(B, N1, N2, D):
+    torch.manual_seed(N1 + D)
+    xyz1 = torch.rand(B, N1, 3, device=DEV) * 4
+    xyz2 = torch.rand(B, N2, 3, device=DEV) * 4
+    p1, p2 = torch.randn(B, N1, D, device=DEV), torch.randn(B, N2, D, device=DEV)
+    idx = K.knn(xyz1, xyz2, 32)
+    pos_w, pos_b = torch.randn(D, 3, device=DEV), torch.randn(D, device=DEV)
+    w, b = torch.randn(D, D, device=DEV) / D ** 0.5, torch.randn(D, device=DEV)
+    wp = K.pack_weight(w, 0, 0, 0)
+    y = K.costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, 0.1, wp, D, b, 0.1)
+    rel = _gather(xyz2, idx).double() - xyz1.double().unsqueeze(2)
+    x = _gather(p2, idx).double() + p1.double().unsqueeze(2) + rel @ pos_w.double().t() + pos_b.double()
+    x = torch.where(x > 0, x, x * 0.1)
+    z = x @ w.double().t() + b.double()
+    z = torch.where(z > 0, z, z * 0.1)
+    ref = z.max(dim=2)[0]
+    assert y.shape == (B, N1, D)
+    assert _err(y, ref) < 2e-5
+    assert torch.equal(y, K.costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, 0.1, wp, D, b, 0.1))
+
+
+def test_fused_layers_match_unfused_modules():
+    """CrossLayerLight and the flow estimator through the fused kernels vs the same modules with the fused
+    paths disabled (the kdpc op chain that the golden-vector tests pin against the reference)."""
+    from kd_pointcloud_b200 import pointconv_util as P
+    from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+    d = make_pairs(2, 2048, seed=3, device=DEV)
+    torch.manual_seed(1)
+    cross = P.CrossLayerLight(32, 96, [64, 64], [64, 64]).to(DEV).eval()
+    est = P.SceneFlowEstimatorResidual(128, 64).to(DEV).eval()
+    for m in (cross, est):
+        m.load_state_dict(synthetic_state_dict(m.state_dict(), 11))
+    f1, f2 = torch.randn(2, 2048, 96, device=DEV), torch.randn(2, 2048, 96, device=DEV)
+    feats, cost = torch.randn(2, 2048, 128, device=DEV), torch.randn(2, 2048, 64, device=DEV)
+    with torch.no_grad():
+        fused = cross.forward_pm(d["pos1"], d["pos2"], f1, f2) + est.forward_pm(d["pos1"], feats, cost)
+        saved = KF.FUSED_POINTCONV_K, P.FUSED_COSTVOL
+        KF.FUSED_POINTCONV_K, P.FUSED_COSTVOL = (), False
+        try:
+            plain = cross.forward_pm(d["pos1"], d["pos2"], f1, f2) + est.forward_pm(d["pos1"], feats, cost)
+        finally:
+            KF.FUSED_POINTCONV_K, P.FUSED_COSTVOL = saved
+    for a, b in zip(fused, plain):
+        assert _err(a, b.double()) < 5e-5
