@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kdpc", choices=["kdpc", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--workload", default="infer", choices=["infer", "kd_train"],
+                    help="infer = configs[2] (the headline); kd_train = configs[3]/[4]: teacher fwd + student fwd/bwd + "
+                         "fused KD loss + Adam, gradients all-reduced over NCCL when N > 1")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one", action="store_true",
@@ -344,10 +347,86 @@ def run_kdpc(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------- training workload
+def run_train(args):
+    """configs[3] / configs[4]: the distilTrain.py step (teacher forward under no_grad, student forward +
+    backward, fused multi-scale + distillation loss, Adam), batch-sharded over ranks with ONE flat NCCL
+    gradient all-reduce per step.  Reported beside the headline, not instead of it."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from kd_pointcloud_b200 import ops
+    from kd_pointcloud_b200.flownet import student, teacher
+    from kd_pointcloud_b200.sharding import FlatGradAllReduce
+    from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+    from kd_pointcloud_b200.training import kd_step
+
+    B = args.batch
+    t = teacher()
+    t.load_state_dict(synthetic_state_dict(t.state_dict(), MODEL_SEED))
+    s = student()
+    s.load_state_dict(synthetic_state_dict(s.state_dict(), MODEL_SEED + 1))
+    t, s = t.to(dev), s.to(dev)
+    opt = torch.optim.Adam(s.parameters(), lr=1e-3)
+    reducer = FlatGradAllReduce(s.parameters()) if world > 1 else None
+    kind = "kitti" if world > 1 else "ft3d"
+    pool = [make_pairs(B, NPOINTS, seed=4321 + 1000 * rank + i, kind=kind, device=dev) for i in range(2)]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        kd_step(t, s, pool[i % 2], opt, reducer)
+    barrier()
+    n0 = ops.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        loss = kd_step(t, s, pool[i % 2], opt, reducer)
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_step = ms.item() / args.steps
+        print(json.dumps({
+            "metric": "KD training pairs/sec @8192 pts", "value": B * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[3]/[4]: teacher fwd (no grad) + student fwd/bwd + fused KD loss + Adam; "
+                                   f"{kind}-shaped synthetic 8192-pt pairs", "pairs_per_gpu_per_step": B,
+                       "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else "none",
+                       "grad_elements": None if reducer is None else reducer.numel, "final_loss": float(loss.item())},
+            "gpu_launches": int(ops.LAUNCHES - n0)}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "kd_train":
+        run_train(args)
     else:
         run_kdpc(args)
 

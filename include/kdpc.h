@@ -186,6 +186,27 @@ int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float
                        const float *pos_b, float slope_pre, const void *wpacked, const float *bias,
                        float slope_post, float *out, kdpc_stream_t stream);
 
+/* ---- losses (loss_functions.py) ------------------------------------------------------ */
+
+/* multiScaleLoss (loss_functions.py:6-25) against up to two targets at once, forward + gradient:
+ *   *loss += sum_t weight[t] * sum_s alpha[s] * sum_{b,p} || pred_s[b,:,p] - target_t[b, chain_s(p), :] ||_2
+ * where chain_s composes the FPS index lists fps_idx[s-1] .. fps_idx[0] (the reference's chained
+ * index_points_gather of the ground truth, never materialised here).  weight[t] carries the 1/B of the
+ * reference's mean over the batch (and gamma / beta of the distillation losses).
+ * n, pred, grad_pred, fps_idx, alpha, target, weight are HOST arrays (of device pointers where applicable);
+ * pred[s] / grad_pred[s]: [B,3,n[s]] (point_major = 0) or [B,n[s],3] (1); grad_pred may be NULL, otherwise
+ * grad_pred[s] is OVERWRITTEN with d loss / d pred_s.  fps_idx[s]: int32 [B,n[s+1]], s < nscales-1.
+ * target[t]: [B,n[0],3].  nscales <= 4, ntargets <= 2.  ws: kdpc_loss_workspace_bytes() bytes, zeroed ONCE
+ * before its first use.  Deterministic (no floating-point atomics). */
+long long kdpc_loss_workspace_bytes(void);
+int kdpc_flow_loss(int b, int nscales, int point_major, const int *n, const float *const *pred,
+                   float *const *grad_pred, const int *const *fps_idx, const float *alpha, int ntargets,
+                   const float *const *target, const float *weight, void *ws, float *loss, kdpc_stream_t stream);
+/* distillation hint term (loss_functions.py:92-93, 213-216): *loss += 0.5 * weight * sum (fs - ft)^2;
+ * grad_fs (may be NULL) = weight * (fs - ft).  fs, ft, grad_fs: n floats in the same order. */
+int kdpc_hint_loss(long long n, const float *fs, const float *ft, float weight, float *grad_fs, void *ws,
+                   float *loss, kdpc_stream_t stream);
+
 /* ---- deterministic backward plumbing ------------------------------------------------- */
 
 /* Inverse of an index list: idx int32 [B,M] with values in [0,N)  ->  offsets int32 [B,N+1] and

@@ -94,6 +94,8 @@ _SIGNATURES = {
     "kdpc_linear_simt": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
     "kdpc_pointconv_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
     "kdpc_costvol_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_float, _P, _P],
+    "kdpc_flow_loss": [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
+    "kdpc_hint_loss": [c_longlong, _P, _P, c_float, _P, _P, _P, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
 }
@@ -123,6 +125,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_knn_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.kdpc_spatial_sort_bytes.restype = c_longlong
         L.kdpc_spatial_sort_bytes.argtypes = [c_int, c_int]
+        L.kdpc_loss_workspace_bytes.restype = c_longlong
+        L.kdpc_loss_workspace_bytes.argtypes = []
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -133,7 +137,7 @@ def lib() -> ctypes.CDLL:
 
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
-            "kdpc_spatial_sort_bytes"] + list(_SIGNATURES)
+            "kdpc_spatial_sort_bytes", "kdpc_loss_workspace_bytes"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

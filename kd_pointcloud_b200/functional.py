@@ -494,3 +494,42 @@ class _PointConvAgg(torch.autograd.Function):
 
 def pointconv_agg(grouped: torch.Tensor, wn: torch.Tensor) -> torch.Tensor:
     return _PointConvAgg.apply(grouped.contiguous(), wn.contiguous())
+
+
+# ------------------------------------------------------------------- fused losses (a18, a19)
+class _KDLoss(torch.autograd.Function):
+    """loss = sum_t w_t * multiScaleLoss(preds, target_t) + sum_h 0.5 * hw_h * |fs_h - ft_h|^2; the kernels write
+    the gradients in the same pass, backward only scales them by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, meta, *tensors):
+        ns, nh, fps_idxs, targets, alpha, weights, hint_ft, hint_w, point_major = meta
+        preds, hint_fs = list(tensors[:ns]), list(tensors[ns:ns + nh])
+        want = any(ctx.needs_input_grad[1:])
+        loss, g_pred, g_hint = K.kd_loss(preds, list(fps_idxs), list(targets), list(alpha), list(weights), point_major,
+                                         hint_fs, list(hint_ft), list(hint_w), want)
+        ctx.save_for_backward(*g_pred, *g_hint)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None,) + tuple(g * grad_out for g in ctx.saved_tensors)
+
+
+def kd_loss(pred_flows, fps_idxs, targets, weights, alpha, hints=()) -> torch.Tensor:
+    """pred_flows: [B,3,N_i] (the model's outputs; permuted views of point-major tensors are used in place);
+    targets: [B,N0,3] tensors (never differentiated: ground truth, or the teacher's flow computed under
+    no_grad); weights: one float per target, INCLUDING the 1/B of the batch mean; hints: (student_feat,
+    teacher_feat, weight) triples."""
+    preds = list(pred_flows)
+    point_major = all(p.dim() == 3 and p.stride(1) == 1 and p.permute(0, 2, 1).is_contiguous() for p in preds)
+    preds = [p.permute(0, 2, 1) for p in preds] if point_major else [p.contiguous() for p in preds]
+    fs = [h[0].contiguous() for h in hints]
+    ft = [h[1].detach().contiguous() for h in hints]
+    for a, b in zip(fs, ft):
+        if a.shape != b.shape:                     # what `fs - ft` raises in the reference (loss_functions.py:213-214)
+            raise RuntimeError(f"The size of tensor a {tuple(a.shape)} must match the size of tensor b {tuple(b.shape)}")
+    meta = (len(preds), len(fs), tuple(_as_i32(i) for i in fps_idxs), tuple(t.detach().contiguous() for t in targets),
+            tuple(float(a) for a in alpha), tuple(float(w) for w in weights), tuple(ft), tuple(float(h[2]) for h in hints),
+            point_major)
+    return _KDLoss.apply(meta, *preds, *fs)

@@ -24,9 +24,29 @@ scale = 1.0
 ALPHA = (0.02, 0.04, 0.08, 0.16)
 
 
+FUSED = True      # tests flip this to compare the fused kernel with the reference op chain
+
+
+def _fusable(pred_flows, gt_flow, fps_idxs, hints=()) -> bool:
+    ts = list(pred_flows) + [gt_flow] + [h for pair in hints for h in pair]
+    return (FUSED and scale == 1.0 and all(t.is_cuda and t.dtype == torch.float32 for t in ts)
+            and 1 <= len(pred_flows) <= 4 and len(fps_idxs) == len(pred_flows) - 1 and not gt_flow.requires_grad)
+
+
 def multiScaleLoss(pred_flows: Sequence[torch.Tensor], gt_flow: torch.Tensor, fps_idxs: Sequence[torch.Tensor],
                    alpha: Sequence[float] = ALPHA) -> torch.Tensor:
-    """pred_flows: [B,3,N_i] per scale (finest first); gt_flow [B,N,3]; fps_idxs int32 [B,N_{i+1}]."""
+    """pred_flows: [B,3,N_i] per scale (finest first); gt_flow [B,N,3]; fps_idxs int32 [B,N_{i+1}].
+    CUDA fp32 inputs with a constant target: ONE fused kernel (forward + gradient, functional.kd_loss);
+    otherwise (a target that needs a gradient) the reference op chain on kdpc gathers."""
+    if _fusable(pred_flows, gt_flow, fps_idxs):
+        B = gt_flow.shape[0]
+        return KF.kd_loss(pred_flows, fps_idxs, [gt_flow], [1.0 / B], alpha)
+    return multiScaleLoss_composed(pred_flows, gt_flow, fps_idxs, alpha)
+
+
+def multiScaleLoss_composed(pred_flows: Sequence[torch.Tensor], gt_flow: torch.Tensor, fps_idxs: Sequence[torch.Tensor],
+                            alpha: Sequence[float] = ALPHA) -> torch.Tensor:
+    """The reference's op chain (loss_functions.py:6-25) on the kdpc gather (differentiable w.r.t. everything)."""
     num_scale = len(pred_flows)
     offset = len(fps_idxs) - num_scale + 1
     gts: List[torch.Tensor] = [gt_flow]
@@ -44,14 +64,25 @@ def epe3d(pred_flow0: torch.Tensor, gt_flow: torch.Tensor) -> torch.Tensor:
     return torch.norm(pred_flow0.permute(0, 2, 1) - gt_flow, dim=2).mean()
 
 
+def _kd_fused(outputs, fps_idxs, gt_flow, t0, w_teacher, w_gt, hints, alpha):
+    B = gt_flow.shape[0]
+    return KF.kd_loss(outputs, fps_idxs, [t0, gt_flow], [w_teacher / B, w_gt / B], alpha, hints)
+
+
 def loss_fn_kd_2(outputs, fps_idxs, gt_flow, teacher_outputs, teacher_fps_idxs, gamma, alpha=ALPHA):
     t0 = teacher_outputs[0].permute(0, 2, 1)
+    if _fusable(outputs, gt_flow, fps_idxs) and not t0.requires_grad:
+        return _kd_fused(outputs, fps_idxs, gt_flow, t0, gamma, 1 - gamma, (), alpha)
     return gamma * multiScaleLoss(outputs, t0, fps_idxs, alpha) + (1 - gamma) * multiScaleLoss(outputs, gt_flow, fps_idxs, alpha)
 
 
 def biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, teacher_outputs, t_feat1s, t_feat2s,
                         t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=0, alpha=ALPHA):
     t0 = teacher_outputs[0].permute(0, 2, 1)
+    if (_fusable(outputs, gt_flow, fps_idxs1, [(feat1s[layer], t_feat1s[layer]), (feat2s[layer], t_feat2s[layer])])
+            and not t0.requires_grad):
+        hints = [(feat1s[layer], t_feat1s[layer], 0.5 * (1 - beta)), (feat2s[layer], t_feat2s[layer], 0.5 * (1 - beta))]
+        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha)
     loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
     loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
     src = ((feat1s[layer] - t_feat1s[layer]) ** 2) / 2
@@ -67,6 +98,10 @@ def cross_biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_
     ``hint_mode='first'`` compares against the teacher's feat1 only (shape-valid for the shipped
     student, same structure: MS-vs-teacher + MS-vs-GT + half squared hint error)."""
     t0 = teacher_outputs[0].permute(0, 2, 1)
+    pairs = [(feat1s[e], torch.cat([t_feat1s[e], t_feat2s[e]], dim=1) if hint_mode == "cat" else t_feat1s[e]) for e in layer]
+    if _fusable(outputs, gt_flow, fps_idxs1, pairs) and not t0.requires_grad:
+        hints = [(a, b, 1 - beta) for a, b in pairs]
+        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha)
     loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
     loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
     hint = torch.zeros(1, device=gt_flow.device, dtype=gt_flow.dtype)

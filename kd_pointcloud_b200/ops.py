@@ -563,6 +563,80 @@ _register("costvol_fused(Tensor xyz1, Tensor xyz2, Tensor p1, Tensor p2, Tensor 
           lambda x1, x2, p1, p2, idx, pw, pb, s0, wp, n, b, s1: p1.new_empty((p1.shape[0], p1.shape[1], n)))
 
 
+# ------------------------------------------------------------------------------------ a18, a19
+_LOSS_WS = {}
+
+
+def _loss_ws(device) -> torch.Tensor:
+    ws = _LOSS_WS.get(device)
+    if ws is None:
+        ws = torch.zeros((_lib.lib().kdpc_loss_workspace_bytes(),), dtype=torch.uint8, device=device)
+        _LOSS_WS[device] = ws
+    return ws
+
+
+def _kd_loss(preds, fps_idxs, targets, alpha, weights, point_major: bool, hint_fs, hint_ft, hint_w, want_grad: bool):
+    """loss[1] = sum_t weights[t] * multiScale(preds, targets[t]) + sum_h 0.5 * hint_w[h] * |hint_fs[h] - hint_ft[h]|^2,
+    plus (want_grad) the gradients w.r.t. preds and hint_fs.  One flow kernel + one kernel per hint pair, all
+    accumulating into the same scalar with deterministic reductions."""
+    import ctypes
+    ns = len(preds)
+    if not (1 <= ns <= 4) or len(fps_idxs) < ns - 1 or not (1 <= len(targets) <= 2) or len(alpha) < ns:
+        raise ValueError("kdpc: kd_loss supports 1..4 scales, 1..2 targets")
+    if len(weights) != len(targets) or len(hint_fs) != len(hint_ft) or len(hint_fs) != len(hint_w):
+        raise ValueError("kdpc: kd_loss list lengths do not match")
+    B = preds[0].shape[0]
+    n = []
+    for s_, pr in enumerate(preds):
+        _req(pr, torch.float32, 3, "pred_flow")
+        if pr.shape[0] != B or pr.shape[2 if point_major else 1] != 3:
+            raise ValueError("kdpc: pred_flow must be [B,3,N] (or [B,N,3] when point_major)")
+        n.append(pr.shape[1 if point_major else 2])
+    fps_idxs = list(fps_idxs)[len(fps_idxs) - (ns - 1):] if ns > 1 else []
+    for s_, ix in enumerate(fps_idxs):
+        _req(ix, torch.int32, 2, "fps_idx")
+        if tuple(ix.shape) != (B, n[s_ + 1]):
+            raise ValueError("kdpc: fps_idx[i] must be [B, N_{i+1}]")
+    for t in targets:
+        _req(t, torch.float32, 3, "target flow")
+        if tuple(t.shape) != (B, n[0], 3):
+            raise ValueError("kdpc: target flow must be [B,N0,3]")
+    dev = preds[0].device
+    with _guard(preds[0]):
+        loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        grads = [torch.empty_like(pr) for pr in preds] if want_grad else []
+        ws = _loss_ws(dev)
+        ptr_arr = lambda ts: (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts])
+        n_arr = (ctypes.c_int * ns)(*n)
+        alpha_arr = (ctypes.c_float * ns)(*[float(a) for a in alpha[:ns]])
+        w_arr = (ctypes.c_float * len(targets))(*[float(w) for w in weights])
+        _call("kdpc_flow_loss", B, ns, 1 if point_major else 0, ctypes.cast(n_arr, ctypes.c_void_p),
+              ctypes.cast(ptr_arr(preds), ctypes.c_void_p),
+              ctypes.cast(ptr_arr(grads), ctypes.c_void_p) if want_grad else None,
+              ctypes.cast(ptr_arr(fps_idxs), ctypes.c_void_p), ctypes.cast(alpha_arr, ctypes.c_void_p), len(targets),
+              ctypes.cast(ptr_arr(targets), ctypes.c_void_p), ctypes.cast(w_arr, ctypes.c_void_p), _p(ws), _p(loss),
+              _stream())
+        hgrads = []
+        for fs, ft, w in zip(hint_fs, hint_ft, hint_w):
+            _req(fs, torch.float32, None, "student feature")
+            _req(ft, torch.float32, None, "teacher feature")
+            if fs.shape != ft.shape:
+                raise RuntimeError(f"kdpc: hint features differ in shape: {tuple(fs.shape)} vs {tuple(ft.shape)}")
+            g = torch.empty_like(fs) if want_grad else None
+            if fs.numel():
+                _call("kdpc_hint_loss", fs.numel(), _p(fs), _p(ft), float(w), _p(g), _p(ws), _p(loss), _stream())
+            if want_grad:
+                hgrads.append(g)
+    return loss, grads, hgrads
+
+
+_register("kd_loss(Tensor[] preds, Tensor[] fps_idxs, Tensor[] targets, float[] alpha, float[] weights, bool point_major, "
+          "Tensor[] hint_fs, Tensor[] hint_ft, float[] hint_w, bool want_grad) -> (Tensor, Tensor[], Tensor[])", _kd_loss,
+          lambda preds, fps, tg, al, w, pm, hs, ht, hw, wg: (preds[0].new_empty((1,)),
+                                                              [torch.empty_like(p) for p in preds] if wg else [],
+                                                              [torch.empty_like(h) for h in hs] if wg else []))
+
+
 # --------------------------------------------------------------------------- backward plumbing
 def _build_csr(idx: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
     _req(idx, torch.int32, None, "idx")

@@ -1,0 +1,115 @@
+"""GPU tests for the fused loss kernels (a18, a19): forward value and gradients against the reference op
+chain (loss_functions.py formulas evaluated with torch ops), and the whole distillation step."""
+import pytest
+import torch
+
+from kd_pointcloud_b200 import functional as KF
+from kd_pointcloud_b200 import losses as L
+from kd_pointcloud_b200.synth import make_pairs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pyramid(B, sizes, seed):
+    g = torch.Generator().manual_seed(seed)
+    preds = [torch.randn(B, n, 3, generator=g).to(DEV).requires_grad_(True) for n in sizes]
+    fps = [torch.stack([torch.randperm(sizes[i], generator=g)[:sizes[i + 1]] for _ in range(B)]).int().to(DEV)
+           for i in range(len(sizes) - 1)]
+    gt = torch.randn(B, sizes[0], 3, generator=g).to(DEV)
+    return preds, fps, gt
+
+
+def _both(fn, leaves):
+    outs = []
+    for fused in (True, False):
+        L.FUSED = fused
+        try:
+            for t in leaves:
+                t.grad = None
+            loss = fn()
+            loss.backward()
+            outs.append((loss.detach().clone(), [t.grad.clone() for t in leaves]))
+        finally:
+            L.FUSED = True
+    return outs
+
+
+@pytest.mark.parametrize("B,sizes", [(8, (8192, 2048, 512, 256)), (3, (1000, 300, 77, 10)), (2, (64,))])
+def test_multiscale_loss_fused_matches_op_chain(B, sizes):
+    preds, fps, gt = _pyramid(B, sizes, 1)
+    cm = [p.permute(0, 2, 1) for p in preds]                      # what the model returns: [B,3,N] views
+    (lf, gf), (lc, gc) = _both(lambda: L.multiScaleLoss(cm, gt, fps), preds)
+    assert lf.shape == lc.shape == (1,)
+    assert abs(lf.item() - lc.item()) <= 1e-5 * abs(lc.item())
+    for a, b in zip(gf, gc):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+    # channel-major contiguous inputs take the other layout branch of the kernel
+    preds_cm = [p.detach().permute(0, 2, 1).contiguous().requires_grad_(True) for p in preds]
+    (lf2, gf2), (lc2, gc2) = _both(lambda: L.multiScaleLoss(preds_cm, gt, fps), preds_cm)
+    assert abs(lf2.item() - lc.item()) <= 1e-5 * abs(lc.item())
+    for a, b in zip(gf2, gc2):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+    # deterministic: bit-identical on repeat
+    L.FUSED = True
+    assert torch.equal(L.multiScaleLoss(cm, gt, fps), L.multiScaleLoss(cm, gt, fps))
+
+
+def test_zero_residual_has_zero_gradient():
+    preds, fps, gt = _pyramid(2, (128, 32), 3)
+    with torch.no_grad():
+        preds[0].copy_(gt)                                         # exact hit at the finest scale
+    loss = L.multiScaleLoss([p.permute(0, 2, 1) for p in preds], gt, fps)
+    loss.backward()
+    assert torch.isfinite(loss).all() and torch.count_nonzero(preds[0].grad) == 0      # torch.norm's sub-gradient at 0
+
+
+def test_distillation_losses_fused_match_op_chain():
+    B, sizes = 4, (2048, 512, 128, 64)
+    preds, fps, gt = _pyramid(B, sizes, 5)
+    g = torch.Generator().manual_seed(9)
+    t_flow0 = torch.randn(B, 3, sizes[0], generator=g).to(DEV)
+    fs = [torch.randn(B, 16 * (i + 1), sizes[min(i, 3)], generator=g).to(DEV).requires_grad_(True) for i in range(4)]
+    ft1 = [torch.randn_like(f) for f in fs]
+    ft2 = [torch.randn_like(f) for f in fs]
+    fs2 = [torch.randn_like(f).requires_grad_(True) for f in fs]
+    cm = [p.permute(0, 2, 1) for p in preds]
+    leaves = preds + fs + fs2
+
+    def close(x, y):
+        (lf, gf), (lc, gc) = x, y
+        assert abs(lf.item() - lc.item()) <= 2e-5 * abs(lc.item())
+        for a, b in zip(gf, gc):
+            assert torch.allclose(a, b, rtol=2e-5, atol=1e-7)
+
+    close(*_both(lambda: L.loss_fn_kd_2(cm, fps, gt, [t_flow0], None, 0.3) + 0 * sum(f.sum() for f in fs + fs2), leaves))
+    close(*_both(lambda: L.biDirection_loss_ht(cm, fs, fs2, fps, fps, gt, [t_flow0], ft1, ft2, None, None, 0.3, 0.8, layer=1)
+                 + 0 * sum(f.sum() for f in fs + fs2), leaves))
+    close(*_both(lambda: L.cross_biDirection_loss_ht(cm, fs, fs2, fps, fps, gt, [t_flow0], ft1, ft2, None, None, 0.3, 0.8,
+                                                     layer=(2, 3), hint_mode="first") + 0 * sum(f.sum() for f in fs + fs2), leaves))
+    # the reference formula verbatim raises for equal student/teacher widths: so do we, fused or not
+    for fused in (True, False):
+        L.FUSED = fused
+        try:
+            with pytest.raises(RuntimeError):
+                L.cross_biDirection_loss_ht(cm, fs, fs2, fps, fps, gt, [t_flow0], ft1, ft2, None, None, 0.3, 0.8, layer=(2, 3))
+        finally:
+            L.FUSED = True
+
+
+def test_kd_training_step_runs_and_learns():
+    """distilTrain.py:156-185 as one call: teacher forward (no grad), student forward + fused KD loss +
+    backward + Adam; the loss goes down on a fixed batch and every trainable parameter that the reference
+    trains receives a finite gradient."""
+    from kd_pointcloud_b200.flownet import student, teacher
+    from kd_pointcloud_b200.training import kd_step
+    torch.manual_seed(0)
+    t, s = teacher().to(DEV), student().to(DEV)
+    batch = make_pairs(2, 2048, seed=11, device=DEV)
+    opt = torch.optim.Adam(s.parameters(), lr=1e-3)
+    losses = [kd_step(t, s, batch, opt).item() for _ in range(4)]
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0]
+    with_grad = [p for p in s.parameters() if p.grad is not None]
+    assert len(with_grad) >= 200 and all(torch.isfinite(p.grad).all() for p in with_grad)
+    KF.clear_caches()
