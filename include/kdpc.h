@@ -43,6 +43,9 @@ const char *kdpc_error_string(int code);
  * receives the final min-distance field exactly as the reference leaves it. Bit-exact
  * incl. the reference's block-size dependent tie rule. */
 int kdpc_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, kdpc_stream_t stream);
+/* Clouds of 2048..16384 points run on a cluster of 8 CTAs per cloud (distributed-shared-memory arg-max);
+ * kdpc_fps_set_cluster(0) forces the one-CTA-per-cloud kernel (same results; for A/B measurements). */
+void kdpc_fps_set_cluster(int on);
 
 /* gather_points_kernel_launcher_fast, sampling_gpu.h:12-13.  f [B,C,N], idx [B,M] -> out [B,C,M] */
 int kdpc_gather(int b, int c, int n, int m, const float *f, const int *idx, float *out, kdpc_stream_t stream);

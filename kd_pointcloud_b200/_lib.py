@@ -127,17 +127,21 @@ def lib() -> ctypes.CDLL:
         L.kdpc_spatial_sort_bytes.argtypes = [c_int, c_int]
         L.kdpc_loss_workspace_bytes.restype = c_longlong
         L.kdpc_loss_workspace_bytes.argtypes = []
+        L.kdpc_fps_set_cluster.restype = None
+        L.kdpc_fps_set_cluster.argtypes = [c_int]
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = c_int
+        if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements
+            L.kdpc_fps_set_cluster(0)
         _lib = L
     return _lib
 
 
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
-            "kdpc_spatial_sort_bytes", "kdpc_loss_workspace_bytes"] + list(_SIGNATURES)
+            "kdpc_spatial_sort_bytes", "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -41,6 +41,23 @@ def test_fps_bit_exact(n, m, mode):
     assert torch.equal(got, O.furthest_point_sample(xyz, m))
 
 
+def test_fps_cluster_kernel_equals_single_cta_kernel():
+    """8192- and 2048-point clouds run on a cluster of 8 CTAs per cloud (DSMEM arg-max exchange): identical
+    indices AND identical final min-distance field to the one-CTA kernel, on tie-heavy clouds too."""
+    from kd_pointcloud_b200 import _lib
+    L = _lib.lib()
+    for n, m, mode in ((8192, 2048, "ft3d"), (8192, 2048, "grid"), (2048, 512, "dup"), (4096, 1000, "cm"), (16384, 300, "kitti")):
+        xyz = _cloud(5, n, 900 + n, mode).to(DEV)
+        a = K.fps(xyz, m)
+        L.kdpc_fps_set_cluster(0)
+        try:
+            b = K.fps(xyz, m)
+        finally:
+            L.kdpc_fps_set_cluster(1)
+        assert torch.equal(a, b), (n, m, mode)
+        assert torch.equal(a[:2].cpu(), O.furthest_point_sample(xyz[:2].cpu(), m))
+
+
 def test_fps_batch_of_16_clouds_and_determinism():
     xyz = _cloud(16, 2048, 7, "dup").to(DEV)
     a, b = K.fps(xyz, 512), K.fps(xyz, 512)
