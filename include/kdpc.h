@@ -155,15 +155,23 @@ int kdpc_interp3(int b, int n, int s, int c, const float *q_xyz, const float *c_
  * PointConv.linear (pointconv_util.py:223,250) for the fused kernel: channel order [features(d),
  * dx,dy,dz,0] x wn, K_src = (d+3)*wn, K_packed = (d+4)*wn.  out: kdpc_packed_weight_bytes(N, K_packed). N <= 256. */
 long long kdpc_packed_weight_bytes(int n, int k_packed);
+/* The fused tcgen05 layers stage their gathers asynchronously (bulk copies two pipeline iterations ahead);
+ * kdpc_tc_set_async(0) selects the synchronous register-staged producers (same results; A/B measurements). */
+void kdpc_tc_set_async(int on);
+int kdpc_tc_async_enabled(void);
 int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const float *w, void *out, kdpc_stream_t stream);
 
 /* y[M, ldo] = clamp(leaky(x[M, ldx(K)] W^T * scale + shift, slope), lo, hi) + residual    (N <= 256).
  * scale / shift / residual may be NULL; slope = 1 disables the activation; lo > hi disables the clamp.
  * Replaces nn.Linear / 1x1 Conv1d / Conv2d (+ eval BatchNorm + LeakyReLU) of pointconv_util.py:20-54,250-256,
- * 1797-1821, 2229-2255.  x, out and wpacked must be 16-byte aligned. */
+ * 1797-1821, 2229-2255.  x, out and wpacked must be 16-byte aligned.
+ * ws: kdpc_linear_tc_ws_bytes(m,n,k) bytes or NULL.  With a workspace, layers with few 128-row tiles and a long K
+ * (PointConv linears of the coarse levels: 1024 x 8240 -> 256) are split along K over the idle SMs and reduced
+ * in a fixed order (deterministic). */
+long long kdpc_linear_tc_ws_bytes(long long m, int n, int k);
 int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const void *wpacked,
                    const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
-                   const float *residual, float *out, int ldo, kdpc_stream_t stream);
+                   const float *residual, void *ws, float *out, int ldo, kdpc_stream_t stream);
 /* Same contract on CUDA cores, for layers too small for a 128-row MMA tile (K < 16 or N < 16). w fp32 [N,K]. */
 int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const float *w,
                      const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
@@ -174,20 +182,25 @@ int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const f
  * LeakyReLU(slope).  cand_xyz [B,N,3], query_xyz [B,S,3], feats [B,N,d] (d % 4 == 0), idx int32 [B,S,k]
  * (k = 9 or 16) -> out [B,S,n_out].  wn_params: HOST array of 248 floats (w1[8x3] b1[8] w2[8x8] b2[8]
  * w3[16x8] b3[16], nn.Conv2d layouts) passed to the kernel as launch parameters.  wpacked: the Linear
- * weight packed with kdpc_pack_weight(mode 1, d, 16).  Neither [B,S,k,3+d] nor [B,S,16(d+3)] touches HBM. */
+ * weight packed with kdpc_pack_weight(mode 1, d, 16).  Neither [B,S,k,3+d] nor [B,S,16(d+3)] touches HBM.
+ * ws: kdpc_pointconv_fused_ws_bytes(b,s,d,n_out) bytes or NULL (split-K workspace, as for kdpc_linear_tc). */
+long long kdpc_pointconv_fused_ws_bytes(int b, int s, int d, int n_out);
 int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
                          const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
                          const void *wpacked, const float *scale, const float *shift, float slope,
-                         float *out, kdpc_stream_t stream);
+                         void *ws, float *out, kdpc_stream_t stream);
 
 /* CrossLayerLight.cross (pointconv_util.py:1826-1850) with a single-layer mlp, fused: out[b,i,:] =
  * max_k leaky(W act(p2[idx[b,i,k]] + p1[b,i] + pos_w (xyz2[idx]-xyz1[i]) + pos_b) + bias, slope_post).
  * k must be 32, d % 8 == 0, d, d_out <= 256.  wpacked: kdpc_pack_weight(mode 0) of W [d_out, d].
- * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out]. */
+ * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out].
+ * ws: kdpc_costvol_fused_ws_bytes(b,s,n,d) bytes (16-byte aligned) for the per-point features with the positional
+ * encoding folded in; NULL selects the variant that evaluates the encoding per neighbour (no workspace). */
+long long kdpc_costvol_fused_ws_bytes(int b, int s, int n, int d);
 int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float *xyz1, const float *xyz2,
                        const float *p1, const float *p2, const int *idx, const float *pos_w,
                        const float *pos_b, float slope_pre, const void *wpacked, const float *bias,
-                       float slope_post, float *out, kdpc_stream_t stream);
+                       float slope_post, void *ws, float *out, kdpc_stream_t stream);
 
 /* ---- losses (loss_functions.py) ------------------------------------------------------ */
 

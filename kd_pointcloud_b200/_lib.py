@@ -90,10 +90,10 @@ _SIGNATURES = {
     "kdpc_max_over_k": [c_longlong, c_int, c_int, _P, _P, _P, _P],
     "kdpc_interp3": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_pack_weight": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
-    "kdpc_linear_tc": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
+    "kdpc_linear_tc": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, _P, c_int, _P],
     "kdpc_linear_simt": [c_longlong, c_int, c_int, _P, c_int, _P, _P, _P, c_float, c_float, c_float, _P, _P, c_int, _P],
-    "kdpc_pointconv_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
-    "kdpc_costvol_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_float, _P, _P],
+    "kdpc_pointconv_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P],
+    "kdpc_costvol_fused": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_float, _P, _P, _P],
     "kdpc_flow_loss": [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "kdpc_hint_loss": [c_longlong, _P, _P, c_float, _P, _P, _P, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
@@ -125,6 +125,12 @@ def lib() -> ctypes.CDLL:
         L.kdpc_knn_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.kdpc_spatial_sort_bytes.restype = c_longlong
         L.kdpc_spatial_sort_bytes.argtypes = [c_int, c_int]
+        L.kdpc_linear_tc_ws_bytes.restype = c_longlong
+        L.kdpc_linear_tc_ws_bytes.argtypes = [c_longlong, c_int, c_int]
+        L.kdpc_pointconv_fused_ws_bytes.restype = c_longlong
+        L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        L.kdpc_costvol_fused_ws_bytes.restype = c_longlong
+        L.kdpc_costvol_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
         L.kdpc_loss_workspace_bytes.restype = c_longlong
         L.kdpc_loss_workspace_bytes.argtypes = []
         L.kdpc_fps_set_cluster.restype = None
@@ -133,6 +139,11 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = c_int
+        L.kdpc_tc_set_async.restype = None
+        L.kdpc_tc_set_async.argtypes = [c_int]
+        L.kdpc_tc_async_enabled.restype = c_int
+        if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
+            L.kdpc_tc_set_async(0)
         if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements
             L.kdpc_fps_set_cluster(0)
         _lib = L
@@ -141,7 +152,9 @@ def lib() -> ctypes.CDLL:
 
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
-            "kdpc_spatial_sort_bytes", "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster"] + list(_SIGNATURES)
+            "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
+            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async",
+            "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -22,6 +22,8 @@ constexpr int CV_MAX_D = 256;
 
 struct CostVolProducer {
     static constexpr int kWarps = 8, kGroups = 2;
+    static constexpr bool kAsync = false;
+    static constexpr int kIssuers = 0, kLookahead = 0;
     struct Args {
         const float *xyz1;   // [B,S,3] queries
         const float *xyz2;   // [B,N,3] candidates
@@ -103,6 +105,138 @@ struct CostVolProducer {
     }
 };
 
+// Asynchronous variant.  The positional encoding is linear, pos_w (xyz2[j] - xyz1[i]) + pos_b =
+// (pos_w xyz2[j]) - (pos_w xyz1[i]) + pos_b, so a tiny elementwise pass (costvol_prep_kernel) folds it into the
+// point features once per POINT instead of once per (point, neighbour, channel):
+//     p2q[j] = points2[j] + pos_w xyz2[j]          p1q[i] = points1[i] + pos_b - pos_w xyz1[i]
+// and a row of the A operand is just act(p2q[idx] + p1q[i]).  Everything a row needs arrives through cp.async
+// (LDGSTS, 16-byte pieces; per-row bulk copies of 128 B turned out to be TMA-issue bound) two pipeline
+// iterations ahead of its conversion, so the converting threads only ever read shared memory; only the
+// neighbour index travels in a register (loaded one iteration before it is needed).  Completion:
+// cp.async.mbarrier.arrive on the raw stage's mbarrier, one arrival per producer thread.
+// 8 producer warps: thread (row, half) converts half of the chunk's channels.
+struct CostVolAsyncProducer {
+    static constexpr int kWarps = 8, kGroups = 1;
+    static constexpr bool kAsync = true;
+    static constexpr int kIssuers = 256, kLookahead = 2;
+    static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
+    static constexpr int kRawBytes = (TILE_M + TILE_M / CV_K) * ROW_PITCH;     // 128 neighbour rows + 4 point rows
+    struct Args {
+        const float *p1q;    // [B,S,D]  points1 + pos_b - pos_w xyz1
+        const float *p2q;    // [B,N,D]  points2 + pos_w xyz2
+        const int *idx;      // [B,S,32]
+        int s, n, d;
+        float slope;
+    };
+    static __device__ __forceinline__ void prologue(const Args &, int, int) {}
+    const Args &a;
+    const GemmShape &g;
+    int idx_pref;                                            // neighbour index of this thread's row in the NEXT issued tile
+
+    __device__ CostVolAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_), idx_pref(0) {}
+
+    // rows < 2^31 (checked on the host): all index arithmetic in 32 bits
+    __device__ __forceinline__ unsigned row_of(int tile, int r) const {
+        const unsigned row = (unsigned)tile * TILE_M + (unsigned)r;
+        return row < (unsigned)g.m ? row : (unsigned)g.m - 1u;   // padded rows repeat the last row; never stored
+    }
+    __device__ __forceinline__ void prime(int tile, int ptid) { idx_pref = __ldg(a.idx + row_of(tile, ptid & 127)); }
+
+    // channels [c0, c0 + 64) of a chunk are split between the two half-threads of a row: units of 8 channels,
+    // half 0 takes the first ceil(units/2)
+    __device__ __forceinline__ void split_units(int chunk, int half, int &u0, int &nu) const {
+        const int units = min(8, (a.d - chunk * CHUNK_K) >> 3);
+        const int first = (units + 1) >> 1;
+        u0 = half ? first : 0;
+        nu = half ? units - first : first;
+    }
+
+    __device__ __forceinline__ void issue(int tile, int chunk, int next_tile, unsigned char *raw, uint64_t *bar, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7, k = r & 31;
+        const unsigned row = row_of(tile, r);
+        const unsigned pt = row >> 5, b = pt / (unsigned)a.s;
+        const int j = idx_pref;
+        if (next_tile >= 0) idx_pref = __ldg(a.idx + row_of(next_tile, r));       // consumed by the next issue
+        const int c0 = chunk * CHUNK_K;
+        int u0, nu;
+        split_units(chunk, half, u0, nu);
+        {   // this half-thread's channels of the gathered row: two 16-byte pieces per unit
+            const float *src = a.p2q + ((size_t)b * a.n + j) * (size_t)a.d + c0 + u0 * 8;
+            const uint32_t dst = smem_u32(raw + r * ROW_PITCH + u0 * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < 2 * nu) cp_async_16(dst + e * 16, src + e * 4);
+        }
+        if (half == 1) {                                         // the point's own row, spread over its 32 neighbour rows
+            const int pieces = min(CHUNK_K, a.d - c0) >> 2;
+            if (k < pieces)
+                cp_async_16(smem_u32(raw + (TILE_M + (r >> 5)) * ROW_PITCH) + k * 16, a.p1q + (size_t)pt * a.d + c0 + k * 4);
+        }
+        cp_async_mbar_arrive(bar);                               // arrives once this thread's copies have landed
+    }
+
+    __device__ __forceinline__ void convert(int tile, int chunk, const unsigned char *raw, unsigned char *a_hi,
+                                            unsigned char *a_lo, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7;
+        const float4 *rr = reinterpret_cast<const float4 *>(raw + r * ROW_PITCH);
+        const float4 *pr = reinterpret_cast<const float4 *>(raw + (TILE_M + (r >> 5)) * ROW_PITCH);   // same for the warp
+        int u0, nu;
+        split_units(chunk, half, u0, nu);
+        const float slope = a.slope;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+            if (uu < nu) {
+                const int u = u0 + uu;
+                const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+                const float4 q0 = pr[2 * u], q1 = pr[2 * u + 1];
+                float v[8] = {g0.x + q0.x, g0.y + q0.y, g0.z + q0.z, g0.w + q0.w,
+                              g1.x + q1.x, g1.y + q1.y, g1.z + q1.z, g1.w + q1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], v[e] * slope);          // leaky / ReLU (0 <= slope < 1)
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                const uint32_t off = sw128_offset(r, u);
+                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+            }
+        }
+        // units beyond d (d < 64): the MMA never reads them (k_total stops the K loop at d rounded up to 16)
+        if (half == 1) {
+            const int units = min(8, (a.d - chunk * CHUNK_K) >> 3);
+            if (units & 1) {                                      // ... except the upper half of an odd last 16-wide K-step
+                const uint32_t off = sw128_offset(r, units);
+                *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+};
+
+// p2q = points2 + pos_w xyz2 (sign = +1, no bias);  p1q = points1 + pos_b - pos_w xyz1 (sign = -1, with bias)
+__global__ void __launch_bounds__(256)
+costvol_prep_kernel(long long rows1, long long rows2, int dvec, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                    const float *__restrict__ p1, const float *__restrict__ p2, const float *__restrict__ pos_w,
+                    const float *__restrict__ pos_b, float *__restrict__ p1q, float *__restrict__ p2q) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n1 = rows1 * dvec, n2 = rows2 * dvec;
+    if (e >= n1 + n2) return;
+    const bool first = e < n1;
+    const long long ee = first ? e : e - n1;
+    const long long row = ee / dvec;
+    const int dv = (int)(ee - row * dvec);
+    const float *x = (first ? xyz1 : xyz2) + row * 3;
+    const float sx = first ? -x[0] : x[0], sy = first ? -x[1] : x[1], sz = first ? -x[2] : x[2];
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(first ? p1 : p2) + ee);
+    const float4 bb = first ? __ldg(reinterpret_cast<const float4 *>(pos_b) + dv) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *w = pos_w + (size_t)dv * 12;
+    float4 o;
+    o.x = v.x + (bb.x + w[0] * sx + w[1] * sy + w[2] * sz);
+    o.y = v.y + (bb.y + w[3] * sx + w[4] * sy + w[5] * sz);
+    o.z = v.z + (bb.z + w[6] * sx + w[7] * sy + w[8] * sz);
+    o.w = v.w + (bb.w + w[9] * sx + w[10] * sy + w[11] * sz);
+    reinterpret_cast<float4 *>(first ? p1q : p2q)[ee] = o;
+}
+
 // order-preserving float <-> signed int (so that redux.sync.max.s32 is a float max)
 __device__ __forceinline__ int f2ord(float f) {
     const int i = __float_as_int(f);
@@ -118,8 +252,8 @@ struct MaxKEpilogue {
         int ldo;
         long long points;
     };
-    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, uint32_t t_acc, int quarter,
-                                         int lane) const {
+    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int /*split*/, uint32_t t_acc,
+                                         int quarter, int lane) const {
         const long long pt = tile * (TILE_M / CV_K) + quarter;
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
@@ -147,22 +281,47 @@ struct MaxKEpilogue {
 using namespace kdpc;
 using namespace kdpc::tc;
 
+KDPC_API long long kdpc_costvol_fused_ws_bytes(int b, int s, int n, int d) {
+    if (b <= 0 || s <= 0 || n <= 0 || d <= 0) return 0;
+    return ((long long)b * s + (long long)b * n) * d * 4;
+}
+
 KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float *xyz1, const float *xyz2,
                                 const float *p1, const float *p2, const int *idx, const float *pos_w,
                                 const float *pos_b, float slope_pre, const void *wpacked, const float *bias,
-                                float slope_post, float *out, kdpc_stream_t stream) {
+                                float slope_post, void *ws, float *out, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(xyz1 && xyz2 && p1 && p2 && idx && pos_w && pos_b && wpacked && out && b > 0 && s > 0 && n > 0 &&
                     d > 0 && d_out > 0);
-    if (k != CV_K || d > CV_MAX_D || (d & 7) != 0 || d_out > 256) return KDPC_EUNSUPPORTED;
-    const uintptr_t al = reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(wpacked);
+    if (k != CV_K || d > CV_MAX_D || (d & 7) != 0 || d_out > 256 || (long long)b * s * CV_K >= (1ll << 31)) return KDPC_EUNSUPPORTED;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(wpacked) |
+                         reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(pos_b);
     if (al % 16 != 0) return KDPC_EINVAL;
     const long long points = (long long)b * s;
+    MaxKEpilogue::Args ea{bias, slope_post, out, d_out, points};
+    if (ws != nullptr && slope_pre >= 0.f && slope_pre < 1.f && kdpc_tc_async_enabled()) {
+        // asynchronous producer whenever its raw staging fits next to >= 2 operand stages
+        using P = CostVolAsyncProducer;
+        GemmShape g = make_shape(points * CV_K, d_out, d, wpacked, P::kRawBytes, P::kLookahead + 1);
+        if (g.stages >= 2) {
+            float *p1q = reinterpret_cast<float *>(ws);
+            float *p2q = p1q + points * d;
+            const long long total = (points + (long long)b * n) * (d / 4);
+            costvol_prep_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
+                points, (long long)b * n, d / 4, xyz1, xyz2, p1, p2, pos_w, pos_b, p1q, p2q);
+            P::Args pa{p1q, p2q, idx, s, n, d, slope_pre};
+            const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
+            auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
+            KDPC_ENSURE_SMEM(kern, SMEM_BUDGET + 1024);
+            const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+            kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
+            KDPC_RETURN_LAST();
+        }
+    }
+    CostVolProducer::Args pa{xyz1, xyz2, p1, p2, idx, pos_w, pos_b, s, n, d, slope_pre};
     GemmShape g = make_shape(points * CV_K, d_out, d, wpacked);
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<CostVolProducer, MaxKEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
-    CostVolProducer::Args pa{xyz1, xyz2, p1, p2, idx, pos_w, pos_b, s, n, d, slope_pre};
-    MaxKEpilogue::Args ea{bias, slope_post, out, d_out, points};
     const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
     kern<<<grid, num_threads<CostVolProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
     KDPC_RETURN_LAST();

@@ -90,6 +90,10 @@ linear_simt_kernel(long long m, int n, int k, const float *__restrict__ x, int l
 using namespace kdpc;
 using namespace kdpc::tc;
 
+static int g_tc_async = 1;
+KDPC_API int kdpc_tc_async_enabled(void) { return g_tc_async; }
+KDPC_API void kdpc_tc_set_async(int on) { g_tc_async = on; }
+
 KDPC_API long long kdpc_packed_weight_bytes(int n, int k_packed) {
     const int n_pad = (n + 15) / 16 * 16;
     const int chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
@@ -114,22 +118,32 @@ KDPC_API int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const f
     KDPC_RETURN_LAST();
 }
 
+KDPC_API long long kdpc_linear_tc_ws_bytes(long long m, int n, int k) {
+    if (m <= 0 || n <= 0 || n > 256 || k <= 0) return 0;
+    GemmShape g = make_shape(m, n, k, nullptr);
+    plan_split_k(g);
+    return (long long)split_k_ws_bytes(g);
+}
+
 KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const void *wpacked,
                             const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
-                            const float *residual, float *out, int ldo, kdpc_stream_t stream) {
+                            const float *residual, void *ws, float *out, int ldo, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(x && wpacked && out && m > 0 && n > 0 && k > 0 && ldx >= k && ldo >= n);
     if (n > 256) return KDPC_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) % 16) != 0 || (reinterpret_cast<uintptr_t>(out) % 16) != 0 ||
-        (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0)
+        (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0 || (reinterpret_cast<uintptr_t>(ws) % 16) != 0)
         return KDPC_EINVAL;
     GemmShape g = make_shape(m, n, k, wpacked);
+    if (ws != nullptr) plan_split_k(g);                      // small-M / large-K layers: spread K over idle SMs
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<PlainProducer, StoreEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
     PlainProducer::Args pa{x, ldx, k};
-    StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo};
-    const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+    StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, reinterpret_cast<float *>(ws)};
+    const long long work = g.num_tiles * g.splits;
+    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
     kern<<<grid, num_threads<PlainProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
+    if (g.splits > 1) return launch_splitk_reduce(g, ea, to_stream(stream));
     KDPC_RETURN_LAST();
 }
 

@@ -23,6 +23,8 @@ namespace tc {
 template <int KN>
 struct PointConvProducer {
     static constexpr int kWarps = 8, kGroups = 1;
+    static constexpr bool kAsync = false;
+    static constexpr int kIssuers = 0, kLookahead = 0;
     struct Args {
         const float *cand_xyz;    // [B,N,3]
         const float *query_xyz;   // [B,S,3]
@@ -136,13 +138,17 @@ struct PointConvProducer {
 
 template <int KN>
 static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN>::Args &pa, const void *wpacked,
-                            const StoreEpilogue::Args &ea, cudaStream_t st) {
+                            StoreEpilogue::Args ea, void *ws, cudaStream_t st) {
     GemmShape g = make_shape(m, n_out, (pa.d + 4) * 16, wpacked);
+    if (ws != nullptr) plan_split_k(g);
+    ea.partial = reinterpret_cast<float *>(ws);
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<PointConvProducer<KN>, StoreEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
-    const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+    const long long work = g.num_tiles * g.splits;
+    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
     kern<<<grid, num_threads<PointConvProducer<KN>>(), smem, st>>>(g, pa, ea);
+    if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
     return (int)cudaGetLastError();
 }
 
@@ -152,11 +158,18 @@ static int launch_pointconv(long long m, int n_out, const typename PointConvProd
 using namespace kdpc;
 using namespace kdpc::tc;
 
+KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int d, int n_out) {
+    if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;
+    GemmShape g = make_shape((long long)b * s, n_out, (d + 4) * 16, nullptr);
+    plan_split_k(g);
+    return (long long)split_k_ws_bytes(g);
+}
+
 KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
                                   const float *query_xyz, const float *feats, const int *idx,
                                   const float *wn_params /* host: w1[24] b1[8] w2[64] b2[8] w3[128] b3[16] */,
                                   const void *wpacked, const float *scale, const float *shift, float slope,
-                                  float *out, kdpc_stream_t stream) {
+                                  void *ws, float *out, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(cand_xyz && query_xyz && feats && idx && wn_params && wpacked && out && b > 0 && n > 0 && s > 0 &&
                     d > 0 && n_out > 0);
     if (n_out > 256 || (d & 3) != 0 || k != 9) return KDPC_EUNSUPPORTED;
@@ -173,6 +186,6 @@ KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, 
     for (int i = 0; i < 8; ++i) pa.b2[i] = *p++;
     for (int i = 0; i < 128; ++i) pa.w3[i] = *p++;
     for (int i = 0; i < 16; ++i) pa.b3[i] = *p++;
-    StoreEpilogue::Args ea{scale, shift, slope, 1.f, 0.f, nullptr, out, n_out};
-    return launch_pointconv<9>((long long)b * s, n_out, pa, wpacked, ea, to_stream(stream));
+    StoreEpilogue::Args ea{scale, shift, slope, 1.f, 0.f, nullptr, out, n_out, nullptr};
+    return launch_pointconv<9>((long long)b * s, n_out, pa, wpacked, ea, ws, to_stream(stream));
 }

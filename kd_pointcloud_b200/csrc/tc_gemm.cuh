@@ -15,6 +15,9 @@
 #pragma once
 #include "tc_common.cuh"
 
+// A/B switch (kdpc_tc_set_async): 0 = synchronous register-staged producers everywhere
+extern "C" int kdpc_tc_async_enabled(void);
+
 namespace kdpc {
 namespace tc {
 
@@ -31,22 +34,32 @@ struct GemmShape {
     int num_chunks;       // K chunks of 64 (packed-weight K, zero padded)
     int k_total;          // packed K (multiple of 16): K-steps beyond it are skipped
     int stages;
+    int splits;           // split-K: each tile's K chunks are spread over `splits` work items (partial sums to a workspace)
+    int chunks_per_split;
+    int raw_bytes;        // bytes of one raw staging buffer of an asynchronous producer (0: none)
+    int raw_stages;       // lookahead + 1
     long long num_tiles;
     const unsigned char *wpacked;   // [chunk][hi|lo][n_pad][128 B]
 };
 
+constexpr int MAX_RAW_STAGES = 4;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
 static inline int b_stage_bytes(int n_pad) { return 2 * n_pad * 128; }
 
-static inline size_t smem_bytes(int n_pad, int stages) {
-    return (size_t)stages * (A_STAGE_BYTES + b_stage_bytes(n_pad)) + 1024;     // + alignment slack
+static inline size_t smem_bytes(int n_pad, int stages, int raw_total = 0) {
+    return (size_t)stages * (A_STAGE_BYTES + b_stage_bytes(n_pad)) + (size_t)raw_total + 1024;     // + alignment slack
 }
 
-static inline int pick_stages(int n_pad) {
-    int s = (int)((200 * 1024 - 1024) / (A_STAGE_BYTES + b_stage_bytes(n_pad)));
+static inline int pick_stages(int n_pad, int raw_total = 0) {
+    int s = (int)((SMEM_BUDGET - 1024 - raw_total) / (A_STAGE_BYTES + b_stage_bytes(n_pad)));
     return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
-static inline GemmShape make_shape(long long m, int n, int k_packed, const void *wpacked) {
+// raw_bytes / raw_stages: staging of an asynchronous producer (Producer::kRawBytes, kLookahead + 1); the shape is
+// unusable (stages < 2) when the operand stages no longer fit next to it: callers fall back to a synchronous producer.
+static inline GemmShape make_shape(long long m, int n, int k_packed, const void *wpacked, int raw_bytes = 0,
+                                   int raw_stages = 0) {
     GemmShape g;
     g.m = m;
     g.n = n;
@@ -57,28 +70,52 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.tmem_cols = c;
     g.k_total = (k_packed + 15) / 16 * 16;
     g.num_chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
-    g.stages = pick_stages(g.n_pad);
+    g.splits = 1;
+    g.chunks_per_split = g.num_chunks;
+    g.raw_bytes = raw_bytes;
+    g.raw_stages = raw_stages;
+    g.stages = pick_stages(g.n_pad, raw_bytes * raw_stages);
     g.num_tiles = (m + TILE_M - 1) / TILE_M;
     g.wpacked = reinterpret_cast<const unsigned char *>(wpacked);
     return g;
 }
 
+// Split-K for small-M / large-K layers (a handful of 128-row tiles would otherwise leave most SMs idle while each
+// CTA walks >100 K-chunks): partial accumulators go to a workspace [splits][M][n_pad] and splitk_reduce_kernel adds
+// them in split order (deterministic) and applies the epilogue.
+static inline void plan_split_k(GemmShape &g) {
+    g.splits = 1;
+    g.chunks_per_split = g.num_chunks;
+    if (g.num_tiles * 2 > 148 || g.num_chunks < 8) return;
+    int want = (int)(148 / g.num_tiles);
+    if (want > g.num_chunks / 4) want = g.num_chunks / 4;
+    if (want > 16) want = 16;
+    if (want < 2) return;
+    g.chunks_per_split = (g.num_chunks + want - 1) / want;
+    g.splits = (g.num_chunks + g.chunks_per_split - 1) / g.chunks_per_split;
+}
+static inline size_t split_k_ws_bytes(const GemmShape &g) {
+    return g.splits > 1 ? (size_t)g.splits * (size_t)g.m * g.n_pad * sizeof(float) : 0;
+}
+
 // Producer concept:
 //   struct P { struct Args {...};
 //              static constexpr int kWarps, kGroups;   // producer warps, independent groups (kWarps/kGroups warps fill one stage)
+//              static constexpr bool kAsync;           // true: prime/issue/convert with kLookahead, kIssuers, raw staging (see the loop)
 //              static __device__ void prologue(const Args&, int tid, int nthreads);      // all threads, before the role split
 //              __device__ P(const Args&, const GemmShape&);
 //              __device__ void begin_tile(long long tile, int r);                       // r = producer thread 0..127 = tile row
 //              __device__ void fill(int chunk, unsigned char *a_hi, unsigned char *a_lo, int r); };
 // Epilogue concept:
 //   struct E { struct Args {...};
-//              __device__ void tile(const Args&, const GemmShape&, long long tile, uint32_t tmem_acc, int quarter, int lane); };
+//              __device__ void tile(const Args&, const GemmShape&, long long tile, int split, uint32_t tmem_acc, int quarter, int lane); };
 template <class Producer, class Epilogue>
 __global__ void __launch_bounds__((Producer::kWarps + 5) * 32, 1)
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+    __shared__ __align__(8) uint64_t raw_full[MAX_RAW_STAGES];
     __shared__ uint32_t tmem_base_smem;
 
     constexpr int PW = Producer::kWarps;                                     // 4 or 8: epilogue warps PW+1..PW+4 have (warp & 3) = 1,2,3,0
@@ -88,6 +125,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
     const int bbytes = 2 * g.n_pad * 128;
     unsigned char *a_base = smem;
     unsigned char *b_base = smem + (size_t)g.stages * A_STAGE_BYTES;
+    unsigned char *raw_base = b_base + (size_t)g.stages * bbytes;            // asynchronous producers only
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
@@ -95,6 +133,8 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             mbar_init(&full_b[s], 1);        // expect_tx arrive of the W loader
             mbar_init(&empty[s], 1);         // tcgen05.commit
         }
+        if constexpr (Producer::kAsync)
+            for (int r = 0; r < MAX_RAW_STAGES; ++r) mbar_init(&raw_full[r], Producer::kIssuers);   // arrive.expect_tx per issuing thread
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);     // tcgen05.commit
             mbar_init(&tmem_empty[a], 4);    // one arrive per epilogue warp
@@ -116,10 +156,61 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         const int grp = warp / GW;
         const int ptid = tid - grp * GW * 32;
         Producer prod(pa, g);
+        if constexpr (Producer::kAsync) {
+            // Asynchronous producer: the global -> shared gathers of iteration it + LA are issued (bulk copies that
+            // complete on raw_full[]) while iteration it is converted fp32 -> bf16 hi/lo into the operand stage, so
+            // the gather latency never sits on the critical path and no register holds data in flight.
+            // (all bookkeeping is incremental 32-bit arithmetic: 64-bit divisions cost more than the conversion itself)
+            constexpr int LA = Producer::kLookahead, RAW = LA + 1;
+            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles, nchunks = g.num_chunks;
+            int total = ((ntiles - (int)blockIdx.x + tile_step - 1) / tile_step) * nchunks;       // iterations of this CTA
+            // cursors: `ah` = the iteration being issued (i + LA), `nx` = the one after it (index prefetch), `cu` = converted
+            int ah_tile = (int)blockIdx.x, ah_chunk = 0, nx_tile = ah_tile, nx_chunk = 0, cu_tile = ah_tile, cu_chunk = 0;
+            auto step = [&](int &t, int &c) { if (++c == nchunks) { c = 0; t += tile_step; } };
+            step(nx_tile, nx_chunk);
+            int ah_slot = 0, issued = 0;
+            prod.prime(ah_tile, ptid);
+            auto issue_next = [&]() {
+                prod.issue(ah_tile, ah_chunk, nx_tile < ntiles ? nx_tile : -1, raw_base + (size_t)ah_slot * g.raw_bytes,
+                           &raw_full[ah_slot], ptid);
+                step(ah_tile, ah_chunk);
+                step(nx_tile, nx_chunk);
+                ah_slot = ah_slot + 1 == RAW ? 0 : ah_slot + 1;
+                ++issued;
+            };
+#pragma unroll
+            for (int la = 0; la < LA; ++la)
+                if (issued < total) issue_next();
+            int s = 0, cu_slot = 0;
+            uint32_t ph = 0, raw_ph = 0;
+            for (int i = 0; i < total; ++i) {
+                fence_async_smem();                               // my generic reads of the slot about to be refilled
+                asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");   // every producer finished converting i-1
+                if (issued < total) issue_next();
+                mbar_wait(&empty[s], ph ^ 1);
+                if (ptid == 0) {
+                    mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)cu_chunk * bbytes, (uint32_t)bbytes, &full_b[s]);
+                }
+                mbar_wait(&raw_full[cu_slot], raw_ph);
+                unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
+                prod.convert(cu_tile, cu_chunk, raw_base + (size_t)cu_slot * g.raw_bytes, a_hi, a_hi + A_PART_BYTES, ptid);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[s]);
+                step(cu_tile, cu_chunk);
+                if (++s == g.stages) { s = 0; ph ^= 1; }
+                if (++cu_slot == RAW) { cu_slot = 0; raw_ph ^= 1; }
+            }
+        } else {
         uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const long long work = g.num_tiles * g.splits;
+        for (long long w = blockIdx.x; w < work; w += gridDim.x) {
+            const long long tile = w / g.splits;
+            const int c_begin = (int)(w - tile * g.splits) * g.chunks_per_split;
+            const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             bool began = false;
-            for (int c = 0; c < g.num_chunks; ++c, ++it) {
+            for (int c = c_begin; c < c_end; ++c, ++it) {
                 if (PG > 1 && (int)(it % PG) != grp) continue;
                 if (!began) { prod.begin_tile(tile, ptid); began = true; }
                 const int s = it % g.stages;
@@ -136,16 +227,20 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 if (lane == 0) mbar_arrive(&full_a[s]);
             }
         }
+        }
     } else if (warp == PW) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
         uint32_t it = 0, tcount = 0;
-        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+        const long long work = g.num_tiles * g.splits;
+        for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
+            const int c_begin = (int)(w % g.splits) * g.chunks_per_split;
+            const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             const uint32_t acc = tcount & 1;
             mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             fence_after_sync();
             const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
-            for (int c = 0; c < g.num_chunks; ++c, ++it) {
+            for (int c = c_begin; c < c_end; ++c, ++it) {
                 const int s = it % g.stages;
                 const uint32_t ph = (it / g.stages) & 1;
                 mbar_wait(&full_a[s], ph);
@@ -161,12 +256,12 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                         const uint32_t off = (uint32_t)kk * (UMMA_K * 2);
                         const uint64_t dah = make_smem_desc_sw128(a_hi + off), dal = make_smem_desc_sw128(a_lo + off);
                         const uint64_t dbh = make_smem_desc_sw128(b_hi + off), dbl = make_smem_desc_sw128(b_lo + off);
-                        umma_bf16(d_addr, dah, dbh, idesc, (c | kk) != 0);
+                        umma_bf16(d_addr, dah, dbh, idesc, (c != c_begin) || (kk != 0));
                         umma_bf16(d_addr, dah, dbl, idesc, 1);
                         umma_bf16(d_addr, dal, dbh, idesc, 1);
                     }
                     umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
-                    if (c == g.num_chunks - 1) umma_commit(&tmem_full[acc]);
+                    if (c == c_end - 1) umma_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
             }
@@ -176,12 +271,14 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
         Epilogue epi;
         uint32_t tcount = 0;
-        for (long long tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tcount) {
+        const long long work = g.num_tiles * g.splits;
+        for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
+            const long long tile = w / g.splits;
             const uint32_t acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
-            epi.tile(ea, g, tile, t_acc, quarter, lane);
+            epi.tile(ea, g, tile, (int)(w - tile * g.splits), t_acc, quarter, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -209,14 +306,24 @@ struct StoreEpilogue {
         const float *residual;   // optional [M, ldo] added last (flow = flow_local + up_flow)
         float *out;
         int ldo;
+        float *partial;          // split-K workspace [splits][M][n_pad] (g.splits > 1): raw sums, epilogue applied by the reducer
     };
-    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, uint32_t t_acc, int quarter,
-                                         int lane) const {
+    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int split, uint32_t t_acc,
+                                         int quarter, int lane) const {
         const long long row = tile * TILE_M + quarter * 32 + lane;
         const bool vec = (e.ldo & 3) == 0;
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
             tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // warp-collective: no divergence around it
+            if (g.splits > 1) {
+                if (row < g.m) {
+                    float *o = e.partial + ((size_t)split * g.m + row) * g.n_pad + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (c0 + j < g.n_pad) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                continue;
+            }
             if (row < g.m) {
                 float *o = e.out + row * e.ldo + c0;
                 const float *res = e.residual ? e.residual + row * e.ldo + c0 : nullptr;
@@ -245,10 +352,47 @@ struct StoreEpilogue {
     }
 };
 
+// out[row, col] = epilogue(sum_s partial[s][row][col]), splits added in index order
+static __global__ void __launch_bounds__(256)
+splitk_reduce_kernel(long long m, int n, int n_pad, int splits, const StoreEpilogue::Args e) {
+    const int ng = (n + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * ng) return;
+    const long long row = t / ng;
+    const int c0 = (int)(t - row * ng) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4 *>(e.partial + ((size_t)s * m + row) * n_pad + c0);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int col = c0 + j;
+        if (col < n) {
+            float y = a[j];
+            if (e.scale) y *= __ldg(e.scale + col);
+            if (e.shift) y += __ldg(e.shift + col);
+            y = y > 0.f ? y : y * e.slope;
+            if (e.lo <= e.hi) y = fminf(fmaxf(y, e.lo), e.hi);
+            if (e.residual) y += __ldg(e.residual + row * e.ldo + col);
+            e.out[row * e.ldo + col] = y;
+        }
+    }
+}
+
+static inline int launch_splitk_reduce(const GemmShape &g, const StoreEpilogue::Args &e, cudaStream_t st) {
+    const long long total = g.m * ((g.n + 3) / 4);
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.m, g.n, g.n_pad, g.splits, e);
+    return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // Producer: plain fp32 rows x[M, ldx] (K contiguous).
 struct PlainProducer {
     static constexpr int kWarps = 8, kGroups = 2;        // two groups of 4 warps alternate K-chunks
+    static constexpr bool kAsync = false;
+    static constexpr int kIssuers = 0, kLookahead = 0;
     struct Args {
         const float *x;
         int ldx;

@@ -38,9 +38,19 @@ def _req(t: torch.Tensor, dtype, ndim=None, name="tensor"):
     assert t.is_contiguous(), f"kdpc: {name} must be contiguous"
 
 
+TRACE = None          # set to a list to record (name, int args, start event, end event) per C-ABI call (tools/trace_model.py)
+
+
 def _call(name: str, *args):
     global LAUNCHES
     LAUNCHES += 1
+    if TRACE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(getattr(_lib.lib(), name)(*args), name)
+        b.record()
+        TRACE.append((name, tuple(x for x in args if isinstance(x, int) and not isinstance(x, bool) and abs(x) < (1 << 24)), a, b))
+        return
     check(getattr(_lib.lib(), name)(*args), name)
 
 
@@ -484,9 +494,11 @@ def _linear_tc(x, wpacked, n: int, scale, shift, slope: float, lo: float, hi: fl
     m, k = _linear_args(x, n, scale, shift, residual)
     with _guard(x):
         out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
+        nws = _lib.lib().kdpc_linear_tc_ws_bytes(m, n, k)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=x.device) if nws else None
         if out.numel():
             _call("kdpc_linear_tc", m, n, k, _p(x), k, _p(wpacked), _p(scale), _p(shift), float(slope), float(lo),
-                  float(hi), _p(residual), _p(out), n, _stream())
+                  float(hi), _p(residual), _p(ws), _p(out), n, _stream())
     return out
 
 
@@ -530,9 +542,12 @@ def _pointconv_fused(cand_xyz, query_xyz, feats, idx, wn_params, wpacked, n_out:
     host = (ctypes.c_float * 248)(*wn_params)
     with _guard(feats):
         out = torch.empty((B, S, n_out), dtype=torch.float32, device=feats.device)
+        nws = _lib.lib().kdpc_pointconv_fused_ws_bytes(B, S, D, n_out)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=feats.device) if nws else None
         if out.numel():
             _call("kdpc_pointconv_fused", B, N, S, K, D, n_out, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx),
-                  ctypes.cast(host, ctypes.c_void_p), _p(wpacked), _p(scale), _p(shift), float(slope), _p(out), _stream())
+                  ctypes.cast(host, ctypes.c_void_p), _p(wpacked), _p(scale), _p(shift), float(slope), _p(ws), _p(out),
+                  _stream())
     return out
 
 
@@ -549,9 +564,10 @@ def _costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, slope_pre: float, wpac
     D = p1.shape[2]
     with _guard(p1):
         out = torch.empty((B, S, n_out), dtype=torch.float32, device=p1.device)
+        ws = torch.empty((_lib.lib().kdpc_costvol_fused_ws_bytes(B, S, N, D),), dtype=torch.uint8, device=p1.device)
         if out.numel():
             _call("kdpc_costvol_fused", B, S, N, K, D, n_out, _p(xyz1), _p(xyz2), _p(p1), _p(p2), _p(idx), _p(pos_w),
-                  _p(pos_b), float(slope_pre), _p(wpacked), _p(bias), float(slope_post), _p(out), _stream())
+                  _p(pos_b), float(slope_pre), _p(wpacked), _p(bias), float(slope_post), _p(ws), _p(out), _stream())
     return out
 
 
