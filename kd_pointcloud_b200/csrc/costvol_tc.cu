@@ -302,6 +302,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
         // asynchronous producer whenever its raw staging fits next to >= 2 operand stages
         using P = CostVolAsyncProducer;
         GemmShape g = make_shape(points * CV_K, d_out, d, wpacked, P::kRawBytes, P::kLookahead + 1);
+        if (g.stages < 2) g = make_shape(points * CV_K, d_out, d, wpacked, P::kRawBytes, P::kLookahead);   // lookahead 1
         if (g.stages >= 2) {
             float *p1q = reinterpret_cast<float *>(ws);
             float *p2q = p1q + points * d;

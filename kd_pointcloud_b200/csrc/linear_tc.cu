@@ -135,6 +135,22 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
         return KDPC_EINVAL;
     GemmShape g = make_shape(m, n, k, wpacked);
     if (ws != nullptr) plan_split_k(g);                      // small-M / large-K layers: spread K over idle SMs
+    if (g.splits == 1 && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled()) {
+        // streaming layers: asynchronous row fetch, 2 raw buffers ahead if they fit next to 2 operand stages, else 1
+        using P = PlainAsyncProducer;
+        for (int raw = P::kLookahead + 1; raw >= 2; --raw) {
+            GemmShape ga = make_shape(m, n, k, wpacked, P::kRawBytes, raw);
+            if (ga.stages < 2) continue;
+            const size_t smem_a = smem_bytes(ga.n_pad, ga.stages, ga.raw_bytes * ga.raw_stages);
+            auto kern_a = tc_gemm_kernel<P, StoreEpilogue>;
+            KDPC_ENSURE_SMEM(kern_a, SMEM_BUDGET + 1024);
+            P::Args pa{x, ldx, k};
+            StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
+            const unsigned grid = (unsigned)(ga.num_tiles < kNumSMs ? ga.num_tiles : kNumSMs);
+            kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
+            KDPC_RETURN_LAST();
+        }
+    }
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<PlainProducer, StoreEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);

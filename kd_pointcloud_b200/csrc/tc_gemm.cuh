@@ -161,7 +161,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             // complete on raw_full[]) while iteration it is converted fp32 -> bf16 hi/lo into the operand stage, so
             // the gather latency never sits on the critical path and no register holds data in flight.
             // (all bookkeeping is incremental 32-bit arithmetic: 64-bit divisions cost more than the conversion itself)
-            constexpr int LA = Producer::kLookahead, RAW = LA + 1;
+            const int RAW = g.raw_stages, LA = RAW - 1;                     // 2 or 3 raw buffers: lookahead 1 or 2
             const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles, nchunks = g.num_chunks;
             int total = ((ntiles - (int)blockIdx.x + tile_step - 1) / tile_step) * nchunks;       // iterations of this CTA
             // cursors: `ah` = the iteration being issued (i + LA), `nx` = the one after it (index prefetch), `cu` = converted
@@ -178,7 +178,6 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 ah_slot = ah_slot + 1 == RAW ? 0 : ah_slot + 1;
                 ++issued;
             };
-#pragma unroll
             for (int la = 0; la < LA; ++la)
                 if (issued < total) issue_next();
             int s = 0, cu_slot = 0;
@@ -308,44 +307,79 @@ struct StoreEpilogue {
         int ldo;
         float *partial;          // split-K workspace [splits][M][n_pad] (g.splits > 1): raw sums, epilogue applied by the reducer
     };
+    // tcgen05.ld hands each lane ONE ROW of the 32 x 32 block (v[j] = column j).  Storing that directly makes every
+    // store instruction touch 32 different rows, 16 bytes each: measured 4x slower than the whole rest of the kernel
+    // (partial-sector writes, 32 transactions per instruction).  So the block is transposed through a small
+    // per-warp shared-memory tile and stored with each instruction covering 4 rows x 128 contiguous bytes; the
+    // affine / activation / clamp / residual are applied after the transpose, where a lane owns 4 fixed columns.
+    static constexpr int TP = 36;                             // floats per staged row (32 + 4): conflict-free 16-byte accesses
     __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int split, uint32_t t_acc,
                                          int quarter, int lane) const {
-        const long long row = tile * TILE_M + quarter * 32 + lane;
-        const bool vec = (e.ldo & 3) == 0;
+        __shared__ __align__(16) float stage[4][32 * TP];
+        float *st = stage[quarter];
+        const long long row0 = tile * TILE_M + quarter * 32;
+        const bool partial = g.splits > 1;
+        float *obase = partial ? e.partial + (size_t)split * g.m * g.n_pad : e.out;
+        const int ld = partial ? g.n_pad : e.ldo;
+        const int ncols = partial ? g.n_pad : g.n;
+        const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0 &&
+                         (e.residual == nullptr || partial || (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // this lane's row within a group of 4, and its 4 columns
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
             tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // warp-collective: no divergence around it
-            if (g.splits > 1) {
-                if (row < g.m) {
-                    float *o = e.partial + ((size_t)split * g.m + row) * g.n_pad + c0;
+            if (c0 >= ncols) continue;
+            __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (c0 + j < g.n_pad) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                continue;
-            }
-            if (row < g.m) {
-                float *o = e.out + row * e.ldo + c0;
-                const float *res = e.residual ? e.residual + row * e.ldo + c0 : nullptr;
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(st + lane * TP + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            const int col = c0 + c4;
+            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!partial) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = c0 + j;
-                    if (col < g.n) {
-                        float y = v[j];
-                        if (e.scale) y *= __ldg(e.scale + col);
-                        if (e.shift) y += __ldg(e.shift + col);
-                        y = y > 0.f ? y : y * e.slope;
-                        if (e.lo <= e.hi) y = fminf(fmaxf(y, e.lo), e.hi);
-                        if (res) y += __ldg(res + j);
-                        v[j] = y;
+                for (int j = 0; j < 4; ++j) {
+                    if (col + j < g.n) {
+                        if (e.scale) sc[j] = __ldg(e.scale + col + j);
+                        if (e.shift) sh[j] = __ldg(e.shift + col + j);
                     }
                 }
-                if (vec && c0 + 32 <= g.n) {
+            }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && c0 + j < g.n; ++j) o[j] = v[j];
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + rsub;
+                const long long row = row0 + r;
+                const float4 t = *reinterpret_cast<const float4 *>(st + r * TP + c4);
+                float y[4] = {t.x, t.y, t.z, t.w};
+                if (row < g.m && col < ncols) {
+                    float *o = obase + row * ld + col;
+                    if (!partial) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float z = y[j] * sc[j] + sh[j];
+                            z = z > 0.f ? z : z * e.slope;
+                            if (e.lo <= e.hi) z = fminf(fmaxf(z, e.lo), e.hi);
+                            y[j] = z;
+                        }
+                        if (e.residual) {
+                            const float *rp = e.residual + row * ld + col;
+                            if (vec && col + 4 <= ncols) {
+                                const float4 rr = __ldg(reinterpret_cast<const float4 *>(rp));
+                                y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < ncols) y[j] += __ldg(rp + j);
+                            }
+                        }
+                    }
+                    if (vec && col + 4 <= ncols) {
+                        *reinterpret_cast<float4 *>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < ncols) o[j] = y[j];
+                    }
                 }
             }
         }
@@ -438,6 +472,60 @@ struct PlainProducer {
             const uint32_t off = sw128_offset(r, u);
             *reinterpret_cast<uint4 *>(a_hi + off) = hi;
             *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+        }
+    }
+};
+
+
+// ------------------------------------------------------------------------------------------
+// Asynchronous producer for plain fp32 rows (K % 8 == 0, ldx % 4 == 0): the 128 x 64 chunk is fetched with
+// 16-byte cp.async one or two pipeline iterations ahead (no registers hold data in flight, so the HBM latency
+// is off the critical path), then converted fp32 -> bf16 hi/lo from shared memory.  Thread (row, half) owns 32
+// of the 64 columns.
+struct PlainAsyncProducer {
+    static constexpr int kWarps = 8, kGroups = 1;
+    static constexpr bool kAsync = true;
+    static constexpr int kIssuers = 256, kLookahead = 2;
+    static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
+    static constexpr int kRawBytes = TILE_M * ROW_PITCH;
+    using Args = PlainProducer::Args;
+    static __device__ __forceinline__ void prologue(const Args &, int, int) {}
+    const Args &a;
+    const GemmShape &g;
+    __device__ PlainAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
+    __device__ __forceinline__ void prime(int, int) {}
+    __device__ __forceinline__ void issue(int tile, int chunk, int /*next_tile*/, unsigned char *raw, uint64_t *bar, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7;
+        long long row = (long long)tile * TILE_M + r;
+        if (row >= g.m) row = g.m - 1;                       // padded rows repeat the last row; never stored
+        const int k0 = chunk * CHUNK_K + half * 32;
+        const int pieces = max(0, min(32, a.k - k0)) >> 2;
+        const float *src = a.x + row * a.ldx + k0;
+        const uint32_t dst = smem_u32(raw + r * ROW_PITCH + half * 128);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (e < pieces) cp_async_16(dst + e * 16, src + e * 4);
+        cp_async_mbar_arrive(bar);
+    }
+    __device__ __forceinline__ void convert(int /*tile*/, int chunk, const unsigned char *raw, unsigned char *a_hi,
+                                            unsigned char *a_lo, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7;
+        const float4 *rr = reinterpret_cast<const float4 *>(raw + r * ROW_PITCH);
+        const int units = min(8, (a.k - chunk * CHUNK_K) >> 3);          // k % 8 == 0
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+            const int u = half * 4 + uu;
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if (u < units) {
+                const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+                const float v[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                split8(v, hi, lo);
+            }
+            if (u <= units) {                                // unit == units: the zero half of an odd last 16-wide K-step
+                const uint32_t off = sw128_offset(r, u);
+                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+            }
         }
     }
 };

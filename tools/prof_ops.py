@@ -44,6 +44,9 @@ for _ in range(2):
         w = torch.randn(128, 2096, device=dev)
         wp = K.pack_weight(w, 0, 0, 0)
         K.linear_tc(x, wp, 128, None, None, 0.1, 1.0, 0.0, None)
+        x3 = torch.randn(128, 256, device=dev)
+        wp3 = K.pack_weight(torch.randn(256, 256, device=dev), 0, 0, 0)
+        K.linear_tc(x3, wp3, 256, None, None, 0.1, 1.0, 0.0, None)
         x2 = torch.randn(8 * 8192 * 4, 64, device=dev)
         wp2 = K.pack_weight(torch.randn(64, 64, device=dev), 0, 0, 0)
         K.linear_tc(x2, wp2, 64, None, None, 0.1, 1.0, 0.0, None)
