@@ -142,6 +142,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_tc_set_async.restype = None
         L.kdpc_tc_set_async.argtypes = [c_int]
         L.kdpc_tc_async_enabled.restype = c_int
+        if os.environ.get("KDPC_PC_STAGES"):
+            L.kdpc_pointconv_set_stages(int(os.environ["KDPC_PC_STAGES"]))
         if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
             L.kdpc_tc_set_async(0)
         if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements

@@ -136,12 +136,17 @@ struct PointConvProducer {
     }
 };
 
+static int kdpc_pointconv_stages = 2;
+
 template <int KN>
 static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN>::Args &pa, const void *wpacked,
                             StoreEpilogue::Args ea, void *ws, cudaStream_t st) {
     GemmShape g = make_shape(m, n_out, (pa.d + 4) * 16, wpacked);
     if (ws != nullptr) plan_split_k(g);
     ea.partial = reinterpret_cast<float *>(ws);
+    // the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand stages are
+    // enough to keep the MMA fed and leave ~100 KB of the unified L1/shared array to the cache
+    if (g.stages > kdpc_pointconv_stages) g.stages = kdpc_pointconv_stages;
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<PointConvProducer<KN>, StoreEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
@@ -157,6 +162,8 @@ static int launch_pointconv(long long m, int n_out, const typename PointConvProd
 
 using namespace kdpc;
 using namespace kdpc::tc;
+
+KDPC_API void kdpc_pointconv_set_stages(int n) { kdpc::tc::kdpc_pointconv_stages = n < 2 ? 2 : n; }
 
 KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int d, int n_out) {
     if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;
