@@ -128,7 +128,7 @@ def lib() -> ctypes.CDLL:
         L.kdpc_linear_tc_ws_bytes.restype = c_longlong
         L.kdpc_linear_tc_ws_bytes.argtypes = [c_longlong, c_int, c_int]
         L.kdpc_pointconv_fused_ws_bytes.restype = c_longlong
-        L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         L.kdpc_costvol_fused_ws_bytes.restype = c_longlong
         L.kdpc_costvol_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
         L.kdpc_loss_workspace_bytes.restype = c_longlong
@@ -142,6 +142,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_tc_set_async.restype = None
         L.kdpc_tc_set_async.argtypes = [c_int]
         L.kdpc_tc_async_enabled.restype = c_int
+        L.kdpc_pointconv_set_stages.restype = None
+        L.kdpc_pointconv_set_stages.argtypes = [c_int]
         if os.environ.get("KDPC_PC_STAGES"):
             L.kdpc_pointconv_set_stages(int(os.environ["KDPC_PC_STAGES"]))
         if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
@@ -155,7 +157,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async",
+            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 

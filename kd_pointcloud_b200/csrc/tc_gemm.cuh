@@ -31,7 +31,8 @@ struct GemmShape {
     int n_pad;            // UMMA N: multiple of 16, 16..256
     int acc_stride;       // TMEM columns per accumulator buffer: round_up(n_pad, 32)
     int tmem_cols;        // power of two >= 2 * acc_stride
-    int num_chunks;       // K chunks of 64 (packed-weight K, zero padded)
+    int num_chunks;       // pipeline iterations per tile: K chunks of 64 (x neighbour passes of the PointConv producer)
+    int wchunks;          // chunks of the packed weight: iteration c uses weight chunk c % wchunks
     int k_total;          // packed K (multiple of 16): K-steps beyond it are skipped
     int stages;
     int splits;           // split-K: each tile's K chunks are spread over `splits` work items (partial sums to a workspace)
@@ -70,6 +71,7 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.tmem_cols = c;
     g.k_total = (k_packed + 15) / 16 * 16;
     g.num_chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
+    g.wchunks = g.num_chunks;
     g.splits = 1;
     g.chunks_per_split = g.num_chunks;
     g.raw_bytes = raw_bytes;
@@ -217,7 +219,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 mbar_wait(&empty[s], ph ^ 1);
                 if (ptid == 0) {                                  // weight chunk for this stage (bulk TMA, async)
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)c * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(c % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
                 }
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
                 prod.fill(c, a_hi, a_hi + A_PART_BYTES, ptid);
@@ -250,7 +252,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                     const uint32_t a_lo = a_hi + A_PART_BYTES;
                     const uint32_t b_hi = smem_u32(b_base + (size_t)s * bbytes);
                     const uint32_t b_lo = b_hi + (uint32_t)g.n_pad * 128u;
-                    const int ksteps = min(CHUNK_K / UMMA_K, (g.k_total - c * CHUNK_K) / UMMA_K);
+                    const int ksteps = min(CHUNK_K / UMMA_K, (g.k_total - (c % g.wchunks) * CHUNK_K) / UMMA_K);
                     for (int kk = 0; kk < ksteps; ++kk) {
                         const uint32_t off = (uint32_t)kk * (UMMA_K * 2);
                         const uint64_t dah = make_smem_desc_sw128(a_hi + off), dal = make_smem_desc_sw128(a_lo + off);

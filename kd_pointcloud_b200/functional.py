@@ -447,7 +447,7 @@ def fused_pointconv_available(weightnet, linear, bn, nsample: int, feats: torch.
     return fused_linear_available(feats, linear.weight, linear.bias, bn)
 
 
-FUSED_POINTCONV_K = (9,)
+FUSED_POINTCONV_K = (9, 16)
 
 
 def fused_pointconv(cand_xyz, query_xyz, feats, idx, weightnet, linear, bn, slope: float) -> torch.Tensor:

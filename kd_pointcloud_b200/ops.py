@@ -542,7 +542,7 @@ def _pointconv_fused(cand_xyz, query_xyz, feats, idx, wn_params, wpacked, n_out:
     host = (ctypes.c_float * 248)(*wn_params)
     with _guard(feats):
         out = torch.empty((B, S, n_out), dtype=torch.float32, device=feats.device)
-        nws = _lib.lib().kdpc_pointconv_fused_ws_bytes(B, S, D, n_out)
+        nws = _lib.lib().kdpc_pointconv_fused_ws_bytes(B, S, K, D, n_out)
         ws = torch.empty((nws,), dtype=torch.uint8, device=feats.device) if nws else None
         if out.numel():
             _call("kdpc_pointconv_fused", B, N, S, K, D, n_out, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx),

@@ -116,15 +116,16 @@ def _pointconv_ref64(cand, query, feats, idx, wn_convs, lin_w, scale, shift, slo
     return torch.where(y > 0, y, y * slope)
 
 
-@pytest.mark.parametrize("B,N,S,D,Cout", [(2, 1024, 1024, 32, 64), (1, 700, 300, 128, 128), (3, 512, 512, 320, 128),
-                                          (1, 8192, 8192, 128, 128)])
-def test_pointconv_fused_matches_fp64(B, N, S, D, Cout):
+@pytest.mark.parametrize("B,N,S,D,Cout,KN", [(2, 1024, 1024, 32, 64, 9), (1, 700, 300, 128, 128, 9), (3, 512, 512, 320, 128, 9),
+                                             (1, 8192, 8192, 128, 128, 9), (2, 8192, 2048, 64, 64, 16), (4, 256, 64, 512, 256, 16),
+                                             (2, 512, 256, 256, 256, 16)])
+def test_pointconv_fused_matches_fp64(B, N, S, D, Cout, KN):
     from kd_pointcloud_b200 import pointconv_util as P
     torch.manual_seed(B * 1000 + D)
     cand = (torch.rand(B, N, 3, device=DEV) * 4 - 2)
     query = cand[:, :S].contiguous() if S <= N else torch.rand(B, S, 3, device=DEV)
     feats = torch.randn(B, N, D, device=DEV)
-    idx = K.knn(query, cand, 9)
+    idx = K.knn(query, cand, KN)
     wn = P.WeightNet(3, 16).to(DEV)
     lin = torch.nn.Linear(16 * (D + 3), Cout).to(DEV)
     scale, shift = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
