@@ -51,8 +51,8 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1600.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1600.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -158,10 +158,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- our arm
-def kernel_rooflines(torch, dev, B, hbm_peak):
-    """Live CUDA-event timing of the HBM-bound kernels at their largest model shapes, and of the
-    kNN at l0.  Algorithmic bytes per SURVEY 8(d) / DESIGN.md."""
+def kernel_rooflines(torch, dev, B, hbm_peak, tc_peak):
+    """Live CUDA-event timing (L2 flushed before every launch) of the hot kernels at their largest model shapes.
+    Algorithmic bytes / flops per SURVEY 8(d) / DESIGN.md section 4."""
     from kd_pointcloud_b200 import functional as KF
+    from kd_pointcloud_b200 import pointconv_util as P
     from kd_pointcloud_b200.synth import make_pairs
     K = torch.ops.kdpc
     d = make_pairs(B, NPOINTS, seed=99, device=dev)
@@ -183,24 +184,51 @@ def kernel_rooflines(torch, dev, B, hbm_peak):
         return ts[len(ts) // 2] * 1e-3
 
     out = {}
-    N, Kn, D = NPOINTS, 9, 128                             # flow0 PointConv grouping: [8,8192,9,131]
+    N = NPOINTS
+    # ---- fused PointConv, flow0 shape: [B,8192] points, K=9 neighbours, D=128 -> 128 (pointconv_util.py:231-258)
+    D, Cout, Kn = 128, 128, 9
     idx9 = K.knn(xyz, xyz, Kn)
     feats = torch.randn(B, N, D, device=dev)
-    t = timeit(lambda: K.group_concat(xyz, xyz, feats, idx9))
-    alg = B * (4 * N * Kn + 12 * (N + N) + 4 * N * D + 4 * N * Kn * (D + 3))
-    out["group_concat"] = {"shape": f"B={B} S=N={N} K={Kn} D={D}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
-    idx32 = None
+    wn = P.WeightNet(3, 16).to(dev)
+    lin = torch.nn.Linear(16 * (D + 3), Cout).to(dev)
+    wp = K.pack_weight(lin.weight.detach(), 1, D, 16)
+    params = KF._weightnet_host_params(wn.mlp_convs)
+    bias = lin.bias.detach()
+    t = timeit(lambda: K.pointconv_fused(xyz, xyz, feats, idx9, params, wp, Cout, None, bias, 0.1))
+    S = B * N
+    flops = 2.0 * S * (D + 3) * Kn * 16 + 2.0 * S * 16 * (D + 3) * Cout + 2.0 * S * Kn * 216
+    byts = B * (4 * N * Kn + 24 * N + 4 * N * D + 4 * N * Cout)
+    out["pointconv_fused"] = {"shape": f"B={B} S=N={N} K={Kn} D={D}->{Cout}", "flops": flops, "bytes": byts, "sec": t,
+                              "tflops": flops / t / 1e12, "frac_tensor": flops / t / 1e12 / tc_peak,
+                              "gbs": byts / t / 1e9, "note": "fp32 result from 3 bf16 MMAs per product: tensor-pipe work is 3x the algorithmic flops of the Linear"}
+    # ---- exact kNN (Morton sort of both clouds + best-first search), l0 cross-frame shape
     for kk in (32, 16, 9, 3):
         t = timeit(lambda: K.knn(xyz2, xyz, kk), iters=5)
         algk = B * (12 * (N + N) + 4 * N * kk)
         out[f"knn_k{kk}"] = {"shape": f"B={B} S=N={N} K={kk}", "bytes": algk, "sec": t, "gbs": algk / t / 1e9,
                              "gpairs_per_s": B * N * N / t / 1e9}
+    # ---- fused cost volume, cross0 shape (pointconv_util.py:1826-1850)
     idx32 = K.knn(xyz2, xyz, 32)
-    p1, p2 = torch.randn(B, N, 32, device=dev), torch.randn(B, N, 32, device=dev)
-    pw, pb = torch.randn(32, 3, device=dev), torch.randn(32, device=dev)
-    t = timeit(lambda: K.costvol_pre(xyz2, xyz, p1, p2, idx32, pw, pb, 0.1))
-    algc = B * (4 * N * 32 + 24 * N + 2 * 4 * N * 32 + 4 * N * 32 * 32)
-    out["costvol_pre"] = {"shape": f"B={B} N={N} K=32 D=32", "bytes": algc, "sec": t, "gbs": algc / t / 1e9}
+    Dc = 32
+    p1, p2 = torch.randn(B, N, Dc, device=dev), torch.randn(B, N, Dc, device=dev)
+    pw, pb = torch.randn(Dc, 3, device=dev), torch.randn(Dc, device=dev)
+    wpc = K.pack_weight(torch.randn(Dc, Dc, device=dev), 0, 0, 0)
+    t = timeit(lambda: K.costvol_fused(xyz2, xyz, p1, p2, idx32, pw, pb, 0.1, wpc, Dc, pb, 0.1))
+    algc = B * (4 * N * 32 + 24 * N + 2 * 4 * N * Dc + 4 * N * Dc)
+    out["costvol_fused"] = {"shape": f"B={B} N={N} K=32 D={Dc}", "bytes": algc, "sec": t, "gbs": algc / t / 1e9,
+                            "flops": 2.0 * B * N * 32 * Dc * (Dc + 3)}
+    # ---- streaming 1x1 convolution on tcgen05 (flow0 mlp: 65536 x 128 -> 128)
+    x = torch.randn(B * N, 128, device=dev)
+    wpl = K.pack_weight(torch.randn(128, 128, device=dev), 0, 0, 0)
+    sh = torch.randn(128, device=dev)
+    t = timeit(lambda: K.linear_tc(x, wpl, 128, None, sh, 0.1, 1.0, 0.0, None))
+    algl = B * N * (128 + 128) * 4
+    out["linear_tc"] = {"shape": f"M={B * N} K=128 N=128", "bytes": algl, "sec": t, "gbs": algl / t / 1e9}
+    # ---- grouping (training path; inference fuses it into PointConv)
+    t = timeit(lambda: K.group_concat(xyz, xyz, feats, idx9))
+    alg = B * (4 * N * Kn + 12 * (N + N) + 4 * N * D + 4 * N * Kn * (D + 3))
+    out["group_concat"] = {"shape": f"B={B} S=N={N} K={Kn} D={D}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    # ---- FPS: latency-bound (sequential arg-max)
     t = timeit(lambda: K.fps(xyz, 2048), iters=3)
     out["fps_8192_2048"] = {"shape": f"B={B} 8192->2048", "sec": t, "us_per_iter": t / 2047 * 1e6,
                             "bytes": B * (12 * N + 4 * 2048), "gbs": B * (12 * N + 4 * 2048) / t / 1e9}
@@ -313,12 +341,12 @@ def run_kdpc(args):
     h2d = sum(host[0][k].numel() * 4 for k in KEYS)
     line = None
     if rank == 0:
-        hbm_peak, peak_src = peaks()
+        hbm_peak, tc_peak, peak_src = peaks()
         ms_step = dev_ms / args.steps
         value = B * world / (ms_step * 1e-3)
         e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
-        kr = kernel_rooflines(torch, dev, B, hbm_peak)
-        gc = kr["group_concat"]
+        kr = kernel_rooflines(torch, dev, B, hbm_peak, tc_peak)
+        pc = kr["pointconv_fused"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -331,10 +359,13 @@ def run_kdpc(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "group_concat_kernel (kNN-indexed gather + rel-xyz + concat, flow0 shape)",
-                         "bound": "hbm", "achieved": gc["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                         "frac": gc["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": gc["bytes"]},
+            # dominant kernel of the step (profiles/: 8 launches, largest single share): the fused PointConv
+            "roofline": {"kernel": "tc_gemm_kernel<PointConvProducer<9,1>, StoreEpilogue> (fused PointConv, flow0 shape)",
+                         "bound": "tensor", "achieved": pc["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
+                         "frac": pc["tflops"] / tc_peak, "traffic": 41.75e6, "peak_source": peak_src + ", burst bf16",
+                         "algorithmic_flops_per_launch": pc["flops"], "algorithmic_bytes_per_launch": pc["bytes"],
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_tc_kernels.txt)",
+                         "note": pc["note"]},
             "kernels": {k: {kk: (round(vv, 6) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kr.items()},
         }
         if not args.no_cpu_baseline and world == 1:
