@@ -191,7 +191,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 mbar_wait(&empty[s], ph ^ 1);
                 if (ptid == 0) {
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)cu_chunk * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
                 }
                 mbar_wait(&raw_full[cu_slot], raw_ph);
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
