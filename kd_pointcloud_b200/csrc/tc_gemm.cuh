@@ -112,7 +112,7 @@ static inline size_t split_k_ws_bytes(const GemmShape &g) {
 //   struct E { struct Args {...};
 //              __device__ void tile(const Args&, const GemmShape&, long long tile, int split, uint32_t tmem_acc, int quarter, int lane); };
 template <class Producer, class Epilogue>
-__global__ void __launch_bounds__((Producer::kWarps + 5) * 32, 1)
+__global__ void __launch_bounds__((Producer::kWarps + 5) * 32, 1)      // 13 warps are allocated as 16: 128 registers per thread
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];

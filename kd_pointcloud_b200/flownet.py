@@ -25,6 +25,50 @@ from .pointconv_util import (Conv1d, CrossLayerLight, PointConvD, PointWarping, 
                              UpsampleFlow)
 
 scale = 1.0
+OVERLAP_SAMPLING = False     # opt-in: measured 11 % SLOWER on B200 - the cluster FPS wants all its SMs at once and the
+                             # persistent tcgen05 kernels of the main stream hold every SM (results are identical)
+_SIDE_STREAMS = {}
+
+
+class _SamplePyramid:
+    """FPS + gather for all four levels, issued on a side CUDA stream (fork/join that a CUDA graph capture records
+    as parallel branches).  ``level(i)`` makes the current stream wait for level i and hands out (fps_idx, new_xyz)."""
+
+    def __init__(self, pc_l0: torch.Tensor, npoints):
+        self.overlapped = bool(OVERLAP_SAMPLING and pc_l0.is_cuda)
+        self.items, self.events = [], []
+        if not self.overlapped:
+            xyz = pc_l0
+            for n in npoints:
+                idx = KF.furthest_point_sample(xyz, n)
+                xyz = KF.gather_rows(xyz, idx)
+                self.items.append((idx, xyz))
+            return
+        dev = pc_l0.device
+        main = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            xyz = pc_l0
+            for n in npoints:
+                idx = KF.furthest_point_sample(xyz, n)
+                xyz = KF.gather_rows(xyz, idx)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self.items.append((idx, xyz))
+                self.events.append(ev)
+        pc_l0.record_stream(side)
+        self._main = main
+
+    def level(self, i: int):
+        idx, xyz = self.items[i]
+        if self.overlapped:
+            torch.cuda.current_stream(idx.device).wait_event(self.events[i])
+            idx.record_stream(torch.cuda.current_stream(idx.device))
+            xyz.record_stream(torch.cuda.current_stream(idx.device))
+        return idx, xyz
 
 
 class PointConvBidirection(nn.Module):
@@ -66,6 +110,9 @@ class PointConvBidirection(nn.Module):
         self.warping = PointWarping()
         self.upsample = UpsampleFlow()
 
+    def _sample_pyramid(self, pc_l0):
+        return _SamplePyramid(pc_l0, [self.level1.npoint, self.level2.npoint, self.level3.npoint, self.level4.npoint])
+
     def forward(self, xyz1, xyz2, color1, color2):
         # xyz*, color*: [B,N,3]   (models_bid_pointconv.py:74-92)
         B = xyz1.shape[0]
@@ -75,22 +122,27 @@ class PointConvBidirection(nn.Module):
 
         # ---- encoder: clouds 1 and 2 as one batch of 2B (weights are shared, no BN) --------------
         pc_l0 = both(xyz1, xyz2).contiguous()
+        # The sampling pyramid depends on coordinates only and is a chain of latency-bound kernels on <= 64 SMs:
+        # it runs on a side stream while this stream does the level-0 convolutions and the level-0 self-kNN.
+        pyramid = self._sample_pyramid(pc_l0)
         f_l0 = self.level0_1.forward_pm(self.level0.forward_pm(both(color1, color2)))
         f_l0_1 = self.level0_2.forward_pm(f_l0)
+        if pyramid.overlapped:
+            knn_idx(self.flow0.pointconv_list[0].nsample, pc_l0[:B], pc_l0[:B])      # flow0's neighbourhoods (cached)
 
-        pc_l1, f_l1, fps_l1 = self.level1.forward_pm(pc_l0, f_l0_1)
+        pc_l1, f_l1, fps_l1 = self.level1.forward_pm(pc_l0, f_l0_1, pyramid.level(0))
         f_l1 = self.level1_0.forward_pm(f_l1)
         f_l1_2 = self.level1_1.forward_pm(f_l1)
 
-        pc_l2, f_l2, fps_l2 = self.level2.forward_pm(pc_l1, f_l1_2)
+        pc_l2, f_l2, fps_l2 = self.level2.forward_pm(pc_l1, f_l1_2, pyramid.level(1))
         f_l2 = self.level2_0.forward_pm(f_l2)
         f_l2_3 = self.level2_1.forward_pm(f_l2)
 
-        pc_l3, f_l3, fps_l3 = self.level3.forward_pm(pc_l2, f_l2_3)
+        pc_l3, f_l3, fps_l3 = self.level3.forward_pm(pc_l2, f_l2_3, pyramid.level(2))
         f_l3 = self.level3_0.forward_pm(f_l3)
         f_l3_4 = self.level3_1.forward_pm(f_l3)
 
-        pc_l4, f_l4, _ = self.level4.forward_pm(pc_l3, f_l3_4)
+        pc_l4, f_l4, _ = self.level4.forward_pm(pc_l3, f_l3_4, pyramid.level(3))
         f_l4_3 = self.deconv4_3.forward_pm(up(pc_l3, pc_l4, f_l4))
 
         # 3-NN index sets dense<-sparse, computed once for both clouds and reused below

@@ -248,9 +248,14 @@ class PointConvD(_PointConvBase):
         self.npoint = npoint
         self._init_common(nsample, in_channel, out_channel, weightnet, bn, use_leaky)
 
-    def forward_pm(self, xyz_pm, points_pm):
-        fps_idx = KF.furthest_point_sample(xyz_pm, self.npoint)
-        new_xyz = KF.gather_rows(xyz_pm, fps_idx)                         # [B,S,3]
+    def forward_pm(self, xyz_pm, points_pm, sampled=None):
+        """``sampled`` = (fps_idx, new_xyz) when the caller already ran the sampling (flownet.py computes the whole
+        FPS pyramid up front on a side stream: it depends on coordinates only)."""
+        if sampled is None:
+            fps_idx = KF.furthest_point_sample(xyz_pm, self.npoint)
+            new_xyz = KF.gather_rows(xyz_pm, fps_idx)                     # [B,S,3]
+        else:
+            fps_idx, new_xyz = sampled
         idx = knn_idx(self.nsample, xyz_pm, new_xyz)
         return new_xyz, self._contract(xyz_pm, new_xyz, points_pm, idx), fps_idx
 
