@@ -29,24 +29,27 @@ constexpr int SORT_THREADS = 1024;
 constexpr float BF_MARGIN = 4e-6f;
 
 // ---- 1. spatial sort -------------------------------------------------------------------------
-// ws layout per cloud b (all 16-byte aligned): sorted4 [n] float4 | boxes [ntiles] 2 x float4 | sidx [n] int
+// ws layout per cloud b (all 16-byte aligned): sorted4 [n] float4 | boxes [ntiles] 2 x float4 | sidx [n] int | inv [n] int
 struct SortedCloud {
     float4 *p4;
     float4 *boxes;
-    int *sidx;
+    int *sidx;      // sorted position -> original index
+    int *inv;       // original index -> sorted position
 };
+__host__ __device__ static inline size_t sorted_idx_bytes(int n) { return (((size_t)n * 4 + 15) / 16) * 16; }
 static inline size_t sorted_cloud_bytes(int n) {
     const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;
-    return (size_t)n * 16 + nt * 32 + (((size_t)n * 4 + 15) / 16) * 16;
+    return (size_t)n * 16 + nt * 32 + 2 * sorted_idx_bytes(n);
 }
 __host__ __device__ static inline SortedCloud sorted_cloud_at(void *ws, int b, int n) {
     const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;
-    const size_t per = (size_t)n * 16 + nt * 32 + (((size_t)n * 4 + 15) / 16) * 16;
+    const size_t per = (size_t)n * 16 + nt * 32 + 2 * sorted_idx_bytes(n);
     unsigned char *base = reinterpret_cast<unsigned char *>(ws) + per * (size_t)b;
     SortedCloud c;
     c.p4 = reinterpret_cast<float4 *>(base);
     c.boxes = reinterpret_cast<float4 *>(base + (size_t)n * 16);
     c.sidx = reinterpret_cast<int *>(base + (size_t)n * 16 + nt * 32);
+    c.inv = reinterpret_cast<int *>(base + (size_t)n * 16 + nt * 32 + sorted_idx_bytes(n));
     return c;
 }
 
@@ -171,6 +174,7 @@ spatial_sort_kernel(int n, int n2 /* pow2 >= n, = E * blockDim.x */, const float
         const float x = p[src * 3 + 0], y = p[src * 3 + 1], z = p[src * 3 + 2];
         out.p4[i] = make_float4(x, y, z, sq_norm3(x, y, z));
         out.sidx[i] = src;
+        out.inv[src] = i;
     }
     // tile boxes: one warp per tile
     const int ntiles = (n + BF_TILE - 1) / BF_TILE;
@@ -208,7 +212,7 @@ spatial_sort_kernel(int n, int n2 /* pow2 >= n, = E * blockDim.x */, const float
 // (d, i) < (e, j) in the (distance, index) order
 __device__ __forceinline__ bool lex_less(float d, int i, float e, int j) { return d < e || (d == e && i < j); }
 
-constexpr int BF_QPW = 4;                // max consecutive (Morton-adjacent) queries per warp
+constexpr int BF_QPW = 8;                // max consecutive (Morton-adjacent) queries per warp
 constexpr int BF_CTA_WARPS = 8;
 constexpr unsigned BF_NONE = 0xffffffffu;
 constexpr int BF_SMALL_K = 12;           // up to here survivors are inserted one by one, beyond in merged batches
@@ -237,6 +241,8 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
     const int qbeg = (blockIdx.x * BF_CTA_WARPS + warp) * qpw;
     const int qend = min(s, qbeg + qpw);
 
+    float dj = INFINITY;                                    // the list survives the loop iteration: it seeds the next query
+    int ij = 0x7fffffff;
 #pragma unroll 1
     for (int qpos = qbeg; qpos < qend; ++qpos) {
         const float4 q = __ldg(Q.p4 + qpos);
@@ -279,10 +285,32 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
             }
         };
 
-        float dj = INFINITY;                                // lane j: j-th best so far
-        int ij = 0x7fffffff;
-        float tau = INFINITY;                               // K-th best as of the last merge (warp-uniform, never too small)
+        // Seed: the previous query of this warp is Morton-adjacent, so its 32 best candidates are (almost) this
+        // query's too.  The K-th smallest of THIS query's distances to those 32 distinct candidates is a valid upper
+        // bound of its K-th neighbour distance, known before a single tile is visited: the tile scan then lets
+        // through little more than the true neighbours (instead of everything until the list has warmed up).
+        float tau = INFINITY;                               // K-th best so far / its upper bound (warp-uniform, never too small)
         bool first = true;
+        if (qpos > qbeg) {
+            float sd = INFINITY;
+            if (ij != 0x7fffffff) {
+                const float4 c = __ldg(C.p4 + __ldg(C.inv + ij));
+                sd = MODE == 0 ? expansion_dist(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w)
+                               : direct_dist(q.x - c.x, q.y - c.y, q.z - c.z);
+            }
+#pragma unroll
+            for (int kk = 2; kk <= 32; kk <<= 1) {          // ascending bitonic sort of the 32 values
+#pragma unroll
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    const float pd = __shfl_xor_sync(0xffffffffu, sd, j);
+                    sd = (((lane & j) == 0) == ((lane & kk) == 0)) ? fminf(sd, pd) : fmaxf(sd, pd);
+                }
+            }
+            tau = __shfl_sync(0xffffffffu, sd, k - 1);
+            first = false;
+        }
+        dj = INFINITY;                                      // lane j: j-th best so far
+        ij = 0x7fffffff;
         int nb = 0;                                         // survivors waiting in the warp's buffer
 
         // ascending bitonic sort of one (d, i) per lane
@@ -324,7 +352,7 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
             for (int base = 0; base < nb; base += 32) merge_batch(base);
             __syncwarp();
             nb = 0;
-            tau = __shfl_sync(0xffffffffu, dj, k - 1);
+            tau = fminf(tau, __shfl_sync(0xffffffffu, dj, k - 1));
         };
 
         unsigned cur = pop_min();
@@ -370,7 +398,7 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
                             }
                         }
                     }
-                    tau = __shfl_sync(0xffffffffu, dj, k - 1);
+                    tau = fminf(tau, __shfl_sync(0xffffffffu, dj, k - 1));
                 } else {
                     // larger K: survivors of the (possibly stale) K-th distance are only APPENDED to the warp's buffer ...
                     const bool pass = d <= tau;
