@@ -209,13 +209,25 @@ spatial_sort_kernel(int n, int n2 /* pow2 >= n, = E * blockDim.x */, const float
 }
 
 // ---- 2. best-first search, one WARP per query ----------------------------------------------------
-// (d, i) < (e, j) in the (distance, index) order
-__device__ __forceinline__ bool lex_less(float d, int i, float e, int j) { return d < e || (d == e && i < j); }
+// A list entry is ONE 64-bit key: (order-preserving bits of the fp32 distance) << 32 | candidate index, so that the
+// (distance, index) order is a plain unsigned compare (2 instructions, branch-free) and a shuffle moves both.
+__device__ __forceinline__ unsigned long long make_key(float d, int i) {
+    const unsigned u = __float_as_uint(d);
+    const unsigned o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // monotone: -x < +0 < +x < +inf
+    return ((unsigned long long)o << 32) | (unsigned)i;
+}
+__device__ __forceinline__ float key_dist(unsigned long long k) {
+    const unsigned o = (unsigned)(k >> 32);
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
+constexpr unsigned long long BF_EMPTY = 0xff8000007fffffffull;          // (+inf, INT_MAX)
 
 constexpr int BF_QPW = 8;                // max consecutive (Morton-adjacent) queries per warp
 constexpr int BF_CTA_WARPS = 8;
 constexpr unsigned BF_NONE = 0xffffffffu;
 constexpr int BF_SMALL_K = 12;           // up to here survivors are inserted one by one, beyond in merged batches
+constexpr int BF_FEW = 5;                // flush of up to this many survivors: one by one
 constexpr int BF_FLUSH = 24;             // merge the buffered survivors when this many are waiting (checked per tile)
 constexpr int BF_BUF = BF_FLUSH + 64;    // a tile adds at most 64
 
@@ -231,8 +243,7 @@ template <int MODE, int KEYS>
 __global__ void __launch_bounds__(BF_CTA_WARPS * 32)
 knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const void *__restrict__ cws,
               int *__restrict__ idx32, long long *__restrict__ idx64, float *__restrict__ dist_out) {
-    __shared__ float buf_d[BF_CTA_WARPS][BF_BUF];
-    __shared__ int buf_i[BF_CTA_WARPS][BF_BUF];
+    __shared__ unsigned long long buf[BF_CTA_WARPS][BF_BUF];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const SortedCloud Q = sorted_cloud_at(const_cast<void *>(qws), b, s);
@@ -241,8 +252,7 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
     const int qbeg = (blockIdx.x * BF_CTA_WARPS + warp) * qpw;
     const int qend = min(s, qbeg + qpw);
 
-    float dj = INFINITY;                                    // the list survives the loop iteration: it seeds the next query
-    int ij = 0x7fffffff;
+    unsigned long long key = BF_EMPTY;                      // the list survives the loop iteration: it seeds the next query
 #pragma unroll 1
     for (int qpos = qbeg; qpos < qend; ++qpos) {
         const float4 q = __ldg(Q.p4 + qpos);
@@ -293,8 +303,9 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
         bool first = true;
         if (qpos > qbeg) {
             float sd = INFINITY;
-            if (ij != 0x7fffffff) {
-                const float4 c = __ldg(C.p4 + __ldg(C.inv + ij));
+            const int pi = key_idx(key);
+            if (pi != 0x7fffffff) {
+                const float4 c = __ldg(C.p4 + __ldg(C.inv + pi));
                 sd = MODE == 0 ? expansion_dist(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w)
                                : direct_dist(q.x - c.x, q.y - c.y, q.z - c.z);
             }
@@ -309,50 +320,55 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
             tau = __shfl_sync(0xffffffffu, sd, k - 1);
             first = false;
         }
-        dj = INFINITY;                                      // lane j: j-th best so far
-        ij = 0x7fffffff;
+        key = BF_EMPTY;                                     // lane j: j-th best so far
         int nb = 0;                                         // survivors waiting in the warp's buffer
 
-        // ascending bitonic sort of one (d, i) per lane
-        auto sort32 = [&](float &d, int &i) {
+        // ascending bitonic sort of one key per lane
+        auto sort32 = [&](unsigned long long &x) {
 #pragma unroll
             for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
                 for (int j = kk >> 1; j > 0; j >>= 1) {
-                    const float pd = __shfl_xor_sync(0xffffffffu, d, j);
-                    const int pi = __shfl_xor_sync(0xffffffffu, i, j);
+                    const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
                     const bool keep_min = ((lane & j) == 0) == ((lane & kk) == 0);
-                    const bool take = keep_min ? lex_less(pd, pi, d, i) : lex_less(d, i, pd, pi);
-                    d = take ? pd : d;
-                    i = take ? pi : i;
+                    x = (keep_min == (y < x)) ? y : x;
                 }
             }
         };
         // merge up to 32 buffered survivors (one per lane) into the list: sort them, pair the list with the REVERSED
         // batch (lane-wise minimum = the 32 smallest of the 64, as a bitonic sequence), 5 half-cleaner steps
         auto merge_batch = [&](int base) {
-            float nd = INFINITY;
-            int ni = 0x7fffffff;
-            if (base + lane < nb) { nd = buf_d[warp][base + lane]; ni = buf_i[warp][base + lane]; }
-            sort32(nd, ni);
-            const float rd = __shfl_sync(0xffffffffu, nd, 31 - lane);
-            const int ri = __shfl_sync(0xffffffffu, ni, 31 - lane);
-            if (lex_less(rd, ri, dj, ij)) { dj = rd; ij = ri; }
+            unsigned long long nk = base + lane < nb ? buf[warp][base + lane] : BF_EMPTY;
+            sort32(nk);
+            const unsigned long long rk = __shfl_sync(0xffffffffu, nk, 31 - lane);
+            key = rk < key ? rk : key;
 #pragma unroll
             for (int j = 16; j > 0; j >>= 1) {
-                const float pd = __shfl_xor_sync(0xffffffffu, dj, j);
-                const int pi = __shfl_xor_sync(0xffffffffu, ij, j);
-                const bool take = (lane & j) == 0 ? lex_less(pd, pi, dj, ij) : lex_less(dj, ij, pd, pi);
-                dj = take ? pd : dj;
-                ij = take ? pi : ij;
+                const unsigned long long y = __shfl_xor_sync(0xffffffffu, key, j);
+                key = (((lane & j) == 0) == (y < key)) ? y : key;
             }
         };
+        // one survivor: lanes whose entry comes after it shift up by one; it enters iff lane k-1 is one of them
+        auto insert_one = [&](unsigned long long x) {
+            const bool before = x < key;
+            const unsigned bm = __ballot_sync(0xffffffffu, before);
+            if (bm & (1u << (k - 1))) {                     // warp-uniform
+                const int pos = __ffs(bm) - 1;
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, key, 1);
+                if (before) key = lane == pos ? x : up;
+            }
+        };
+        auto kth = [&]() { return key_dist(__shfl_sync(0xffffffffu, key, k - 1)); };
         auto flush = [&]() {
             __syncwarp();
-            for (int base = 0; base < nb; base += 32) merge_batch(base);
+            if (nb <= BF_FEW) {                             // a handful: one-by-one is cheaper than the sorting network
+                for (int e = 0; e < nb; ++e) insert_one(buf[warp][e]);
+            } else {
+                for (int base = 0; base < nb; base += 32) merge_batch(base);
+            }
             __syncwarp();
             nb = 0;
-            tau = fminf(tau, __shfl_sync(0xffffffffu, dj, k - 1));
+            tau = fminf(tau, kth());
         };
 
         unsigned cur = pop_min();
@@ -369,56 +385,39 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
                 const float4 c = h ? c1 : c0;
                 float d = MODE == 0 ? expansion_dist(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w)
                                     : direct_dist(q.x - c.x, q.y - c.y, q.z - c.z);
-                int i = h ? ci1 : ci0;
+                const int i = h ? ci1 : ci0;
                 if (i == 0x7fffffff) d = INFINITY;          // slot beyond the cloud
                 if (first) {                                // the first 32 candidates, sorted, ARE the initial list
                     first = false;
-                    sort32(d, i);
-                    dj = d;
-                    ij = i;
-                    tau = __shfl_sync(0xffffffffu, dj, k - 1);
+                    key = make_key(d, i);
+                    sort32(key);
+                    tau = kth();
                 } else if (k <= BF_SMALL_K) {
-                    // small K: few survivors, insert them one by one (ballot + shuffle-up, ~25 instructions each)
+                    // small K: few survivors, insert them one by one (ballot + shuffle-up)
                     unsigned mask = __ballot_sync(0xffffffffu, d <= tau);
+                    const unsigned long long mine = make_key(d, i);
                     while (mask) {
                         const int l = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const float ds = __shfl_sync(0xffffffffu, d, l);
-                        const int is = __shfl_sync(0xffffffffu, i, l);
-                        // lanes whose entry comes after the candidate; it enters the list iff lane k-1 is one of them
-                        const bool before = lex_less(ds, is, dj, ij);
-                        const unsigned bm = __ballot_sync(0xffffffffu, before);
-                        if (bm & (1u << (k - 1))) {         // warp-uniform
-                            const int pos = __ffs(bm) - 1;
-                            const float ud = __shfl_up_sync(0xffffffffu, dj, 1);
-                            const int ui = __shfl_up_sync(0xffffffffu, ij, 1);
-                            if (before) {
-                                dj = lane == pos ? ds : ud;
-                                ij = lane == pos ? is : ui;
-                            }
-                        }
+                        insert_one(__shfl_sync(0xffffffffu, mine, l));
                     }
-                    tau = fminf(tau, __shfl_sync(0xffffffffu, dj, k - 1));
+                    tau = fminf(tau, kth());
                 } else {
                     // larger K: survivors of the (possibly stale) K-th distance are only APPENDED to the warp's buffer ...
                     const bool pass = d <= tau;
                     const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    if (pass) {
-                        const int pos = nb + __popc(mask & ((1u << lane) - 1u));
-                        buf_d[warp][pos] = d;
-                        buf_i[warp][pos] = i;
-                    }
+                    if (pass) buf[warp][nb + __popc(mask & ((1u << lane) - 1u))] = make_key(d, i);
                     nb += __popc(mask);
                 }
             }
-            if (nb >= BF_FLUSH) flush();                    // ... and merged 24+ at a time (sorting network, ~7 instr each)
+            if (nb >= BF_FLUSH) flush();                    // ... and merged 24+ at a time by a sorting network
         }
         if (nb > 0) flush();
         if (lane < k) {
             const size_t o = ((size_t)b * s + qorig) * k + lane;
-            if (idx32) idx32[o] = ij;
-            if (idx64) idx64[o] = ij;
-            if (dist_out) dist_out[o] = dj;
+            if (idx32) idx32[o] = key_idx(key);
+            if (idx64) idx64[o] = key_idx(key);
+            if (dist_out) dist_out[o] = key_dist(key);
         }
     }
 }
