@@ -226,7 +226,6 @@ constexpr unsigned long long BF_EMPTY = 0xff8000007fffffffull;          // (+inf
 constexpr int BF_QPW = 8;                // max consecutive (Morton-adjacent) queries per warp
 constexpr int BF_CTA_WARPS = 8;
 constexpr unsigned BF_NONE = 0xffffffffu;
-constexpr int BF_SMALL_K = 12;           // up to here survivors are inserted one by one, beyond in merged batches
 constexpr int BF_FEW = 5;                // flush of up to this many survivors: one by one
 constexpr int BF_FLUSH = 24;             // merge the buffered survivors when this many are waiting (checked per tile)
 constexpr int BF_BUF = BF_FLUSH + 64;    // a tile adds at most 64
@@ -234,8 +233,8 @@ constexpr int BF_BUF = BF_FLUSH + 64;    // a tile adds at most 64
 // The K best of a query live DISTRIBUTED over the warp: lane j holds the j-th smallest (distance, index).
 // Candidates are tested 32 at a time (one per lane); those that pass the current K-th distance are appended
 // to a small per-warp buffer (ballot + popc) and merged into the list two dozen at a time by a sorting
-// network of shuffles (sort the batch, pair it reversed with the list, half-cleaners): ~7 instructions per
-// survivor instead of ~27 for one-at-a-time insertion, no divergence, no per-thread sorted list.
+// network of shuffles (sort the batch, pair it reversed with the list, half-cleaners), or one by one (ballot +
+// shuffle-up) when only a handful are waiting; no divergence, no per-thread sorted list.
 // Tiles are 1 KB coalesced reads that stay in L1/L2.
 // Each lane ranks KEYS tiles (tile = e*32 + lane) by the query's own lower bound; the warp pops the
 // nearest remaining tile with one redux.min.
@@ -392,18 +391,8 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
                     key = make_key(d, i);
                     sort32(key);
                     tau = kth();
-                } else if (k <= BF_SMALL_K) {
-                    // small K: few survivors, insert them one by one (ballot + shuffle-up)
-                    unsigned mask = __ballot_sync(0xffffffffu, d <= tau);
-                    const unsigned long long mine = make_key(d, i);
-                    while (mask) {
-                        const int l = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        insert_one(__shfl_sync(0xffffffffu, mine, l));
-                    }
-                    tau = fminf(tau, kth());
                 } else {
-                    // larger K: survivors of the (possibly stale) K-th distance are only APPENDED to the warp's buffer ...
+                    // survivors of the (possibly stale) K-th distance are only APPENDED to the warp's buffer ...
                     const bool pass = d <= tau;
                     const unsigned mask = __ballot_sync(0xffffffffu, pass);
                     if (pass) buf[warp][nb + __popc(mask & ((1u << lane) - 1u))] = make_key(d, i);
