@@ -188,6 +188,8 @@ long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out);
 /* operand pipeline stages of the fused PointConv (default 2: the rest of the SM's L1/shared array serves the
  * neighbour gathers; measured 5% faster end to end than 3). */
 void kdpc_pointconv_set_stages(int n);
+/* A/B switch for measurements: 0 = per-thread register gathers everywhere instead of the cp.async staging (same results) */
+void kdpc_pointconv_set_staged(int on);
 int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
                          const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
                          const void *wpacked, const float *scale, const float *shift, float slope,

@@ -17,10 +17,10 @@ namespace tc {
 // bf16 hi/lo tile images: out[chunk][part][n_pad][128 B].
 //   mode 0: packed column kc <- source column kc.
 //   mode 1 (PointConv, weightnet width wn): the fused kernel orders channels as
-//           [features 0..D-1, dx, dy, dz, zero] (so that feature rows gather as aligned float4),
-//           while the reference concatenates [dx,dy,dz, features] (pointconv_util.py:153,178) and
-//           flattens c-major with wn innermost (:249).  packed kc = c'*wn + w  <-  source (c*wn + w)
-//           with c = c'+3 for c' < D, c = c'-D for D <= c' < D+3, zero for c' = D+3.
+//           [dx, dy, dz, zero, features 0..D-1] (so that feature rows gather as aligned float4 and the
+//           coordinate chunk comes first), the reference concatenates [dx,dy,dz, features]
+//           (pointconv_util.py:153,178) and flattens c-major with wn innermost (:249).
+//           packed kc = c'*wn + w  <-  source (c*wn + w) with c = c' for c' < 3, zero for c' = 3, c = c'-1 above.
 __global__ void pack_weight_kernel(int n, int k_src, int n_pad, int num_chunks, int mode, int d, int wn,
                                    const float *__restrict__ w, unsigned char *__restrict__ out) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (chunk, row, unit)
@@ -38,8 +38,8 @@ __global__ void pack_weight_kernel(int n, int k_src, int n_pad, int num_chunks, 
             src = kc < k_src ? kc : -1;
         } else {
             const int cp = kc / wn, wi = kc - cp * wn;
-            if (cp < d) src = (cp + 3) * wn + wi;
-            else if (cp < d + 3) src = (cp - d) * wn + wi;
+            if (cp < 3) src = cp * wn + wi;
+            else if (cp > 3 && cp < d + 4) src = (cp - 1) * wn + wi;
         }
         v[j] = (row < n && src >= 0) ? w[(size_t)row * k_src + src] : 0.f;
     }

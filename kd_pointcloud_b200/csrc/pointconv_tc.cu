@@ -13,7 +13,7 @@
 //     agg[ch][w] += g[k][ch] * wn[k][w] and writes the bf16 hi/lo split straight into the swizzled
 //     A-operand tile in shared memory;
 //   * the Linear runs on tcgen05 (tc_gemm.cuh) with the weight pre-permuted to the producer's
-//     channel order [features, dx, dy, dz, 0] (linear_tc.cu: pack mode 1);
+//     channel order [dx, dy, dz, 0, features] (linear_tc.cu: pack mode 1);
 //   * bias / BatchNorm(eval) / LeakyReLU in the TMEM epilogue.
 #include <cstring>
 #include "tc_gemm.cuh"
@@ -24,12 +24,27 @@ namespace tc {
 // KN neighbours in NPASS passes of NB = KN / NPASS: the aggregation is linear in the neighbours, so pass p
 // contributes sum_{k in pass p} g_k (x) wn_k as its own run of K-chunks accumulated into the same TMEM tile (the
 // weight chunks repeat).  K = 16 (PointConvD) runs as 2 x 8, which keeps wn[NB][8] in registers.
-template <int KN, int NPASS>
+// K-chunk 0 of a pass = channels (dx, dy, dz, 0); chunk i >= 1 = feature channels 4(i-1) .. 4(i-1)+3.
+//
+// STAGED = true (whenever the shared memory fits: Cout <= 128, no split-K): the neighbours' feature rows are
+// gathered by 16-byte cp.async into a double-buffered staging area two K-chunks (32 bytes = one L2 sector per
+// neighbour row) at a time, one group ahead of the arithmetic: lane pairs fetch the two halves of a sector, every
+// byte crosses the L2 -> SM link once, and the FFMA loop reads conflict-free 16-byte shared-memory words.  The
+// register path (STAGED = false) has every thread (row, half) load its own 16 bytes per neighbour per chunk: both
+// halves fetch the same data, every lane of a request touches a different line (32 tag look-ups per instruction:
+// the L1 pipe ran at 55-65 % with the kernel still latency bound) and each sector is fetched about twice.
+template <int KN, int NPASS, bool STAGED>
 struct PointConvProducer {
     static constexpr int kWarps = 8, kGroups = 1;
     static constexpr bool kAsync = false;
-    static constexpr int kIssuers = 0, kLookahead = 0;
+    // 12 warps (the MMA issuer lives in the first epilogue warp): 168 registers per thread, so wn[NB][8] really
+    // stays in registers (at 128 it was spilled and re-read from local memory every K-chunk: 85 LDL per chunk,
+    // 1.1 GB of L2 traffic per launch at flow0)
+    static constexpr bool kMergedIssuer = true;
+    static constexpr bool kOwnsLoop = true;                  // run_tile() below instead of fill()
+    static constexpr int kIssuers = STAGED ? 256 : 0, kLookahead = 0;
     static constexpr int NB = KN / NPASS;
+    static constexpr int kRawBytes = NB * 2 * TILE_M * 16;   // one staging buffer: [neighbour][piece][row][16 B]
     struct Args {
         const float *cand_xyz;    // [B,N,3]
         const float *query_xyz;   // [B,S,3]
@@ -42,36 +57,45 @@ struct PointConvProducer {
     const Args &a;
     const GemmShape &g;
     float wn[NB][8];
-    int nb[NB];
-    const float *fbase, *cbase;
+    uint32_t nb[NB];              // element offset of each neighbour's feature row from a.feats
     const int *ip;
     float qx, qy, qz;
-    int half, cur_pass;
+    int half, boff;
+    uint32_t icount, ccount;      // staging groups issued / consumed so far (buffer = count & 1, phase = count >> 1)
 
-    __device__ PointConvProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
+    __device__ PointConvProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_), icount(0), ccount(0) {}
 
     __device__ __forceinline__ void begin_tile(long long tile, int ptid) {
         const int r = ptid & 127;
         half = ptid >> 7;
         long long row = tile * TILE_M + r;
         if (row >= g.m) row = g.m - 1;                       // padded rows recompute the last point; never stored
-        const long long b = row / a.s;
+        boff = (int)(row / a.s) * a.n_cand;
         ip = a.idx + row * KN;
         const float *qp = a.query_xyz + row * 3;
         qx = qp[0]; qy = qp[1]; qz = qp[2];
-        cbase = a.cand_xyz + b * a.n_cand * 3;
-        fbase = a.feats + b * (long long)a.n_cand * a.d;
-        cur_pass = -1;
     }
 
-    // neighbour indices + this thread's 8 WeightNet outputs for the neighbours of one pass
-    __device__ __forceinline__ void load_pass(int pass) {
-        cur_pass = pass;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) nb[k] = __ldg(ip + pass * NB + k);
+    __device__ __forceinline__ void load_idx(int pass, int (&gi)[NB]) {
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            const float *cp = cbase + (long long)nb[k] * 3;
+            gi[k] = boff + __ldg(ip + pass * NB + k);
+            nb[k] = (uint32_t)gi[k] * (uint32_t)a.d;
+        }
+    }
+
+    // This thread's 8 WeightNet outputs for the neighbours of one pass.  The relative coordinates are in registers
+    // here anyway, so the pass's first K-chunk - channels (dx, dy, dz, 0) - is produced right here: the hot feature
+    // loop carries no coordinate state and no branch.
+    __device__ __forceinline__ void weightnet(const int (&gi)[NB], bool emit_xyz, unsigned char *a_hi, unsigned char *a_lo, int r) {
+        float acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const float *cp = a.cand_xyz + (long long)gi[k] * 3;
             const float dx = __ldg(cp) - qx, dy = __ldg(cp + 1) - qy, dz = __ldg(cp + 2) - qz;
             float h1[8], h2[8];
 #pragma unroll
@@ -101,43 +125,42 @@ struct PointConvProducer {
                     wn[k][o] = fmaxf(t, 0.f);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(dx, wn[k][j], acc[0][j]);
+                acc[1][j] = fmaf(dy, wn[k][j], acc[1][j]);
+                acc[2][j] = fmaf(dz, wn[k][j], acc[2][j]);
+            }
+        }
+        if (emit_xyz) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                if (c < 3) split8(acc[c < 3 ? c : 0], hi, lo);
+                const uint32_t off = sw128_offset(r, c * 2 + half);
+                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+            }
         }
     }
 
-    __device__ __forceinline__ void fill(int chunk, unsigned char *a_hi, unsigned char *a_lo, int ptid) {
-        const int r = ptid & 127;
-        const int pass = chunk / g.wchunks;
-        chunk -= pass * g.wchunks;
-        if (pass != cur_pass) load_pass(pass);
+    // one K-chunk of 4 feature channels: v(k) = the 4 channels of neighbour k
+    template <class Fetch>
+    __device__ __forceinline__ void features(Fetch &&v4, unsigned char *a_hi, unsigned char *a_lo, int r) {
         float acc[4][8];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
-        if (chunk * 4 < a.d) {
-            const float *fp = fbase + chunk * 4;
 #pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(fp + (long long)nb[k] * a.d));
+        for (int k = 0; k < NB; ++k) {
+            const float4 v = v4(k);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    acc[0][j] = fmaf(v.x, wn[k][j], acc[0][j]);
-                    acc[1][j] = fmaf(v.y, wn[k][j], acc[1][j]);
-                    acc[2][j] = fmaf(v.z, wn[k][j], acc[2][j]);
-                    acc[3][j] = fmaf(v.w, wn[k][j], acc[3][j]);
-                }
-            }
-        } else {                                             // last chunk: channels (dx, dy, dz, 0)
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                const float *cp = cbase + (long long)nb[k] * 3;
-                const float dx = __ldg(cp) - qx, dy = __ldg(cp + 1) - qy, dz = __ldg(cp + 2) - qz;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    acc[0][j] = fmaf(dx, wn[k][j], acc[0][j]);
-                    acc[1][j] = fmaf(dy, wn[k][j], acc[1][j]);
-                    acc[2][j] = fmaf(dz, wn[k][j], acc[2][j]);
-                }
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(v.x, wn[k][j], acc[0][j]);
+                acc[1][j] = fmaf(v.y, wn[k][j], acc[1][j]);
+                acc[2][j] = fmaf(v.z, wn[k][j], acc[2][j]);
+                acc[3][j] = fmaf(v.w, wn[k][j], acc[3][j]);
             }
         }
 #pragma unroll
@@ -149,32 +172,140 @@ struct PointConvProducer {
             *reinterpret_cast<uint4 *>(a_lo + off) = lo;
         }
     }
+
+    template <class Acquire, class Release>
+    __device__ __forceinline__ void run_tile(long long tile, int c_begin, int c_end, int ptid, unsigned char *raw_base,
+                                             uint64_t *raw_full, Acquire &&acquire, Release &&release) {
+        const int r = ptid & 127;
+        begin_tile(tile, ptid);
+        if constexpr (!STAGED) {
+            int c = c_begin;
+            while (c < c_end) {
+                const int pass = c / g.wchunks;
+                const int base = pass * g.wchunks;
+                int gi[NB];
+                load_idx(pass, gi);
+                if (c == base) {
+                    unsigned char *a_hi = acquire(c);
+                    weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
+                    release();
+                    ++c;
+                } else {
+                    weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
+                }
+                const int stop = min(c_end, base + g.wchunks);
+#pragma unroll 1
+                for (; c < stop; ++c) {
+                    unsigned char *a_hi = acquire(c);
+                    const float *fp = a.feats + (c - base - 1) * 4;
+                    features([&](int k) { return __ldg(reinterpret_cast<const float4 *>(fp + nb[k])); }, a_hi,
+                             a_hi + A_PART_BYTES, r);
+                    release();
+                }
+            }
+        } else {
+            // (launched without split-K: c_begin = 0, c_end = NPASS * wchunks)
+            const int lane = ptid & 31;
+            const int nf = g.wchunks - 1;                    // feature chunks per pass
+            const int ngroups = (nf + 1) >> 1;               // staging groups of two chunks
+            // gather issue: lane pairs fetch the two 16-byte halves of one neighbour row's 32-byte piece; this warp
+            // (row quarter q, half h) issues for rows 32q + 16h + (lane >> 1), whose offsets live in lane 16h + (lane >> 1)
+            const int src_lane = half * 16 + (lane >> 1);
+            const int irow = (r & ~31) + src_lane;
+            const int e = lane & 1;
+            for (int pass = 0; pass < NPASS; ++pass) {
+                int gi[NB];
+                load_idx(pass, gi);
+                auto issue = [&](int grp) {
+                    const uint32_t buf = icount & 1u;
+                    const int fch = grp * 2 + e;
+                    const uint32_t dst = smem_u32(raw_base + (size_t)buf * kRawBytes) + (uint32_t)(e * TILE_M + irow) * 16u;
+                    const float *src = a.feats + fch * 4;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const uint32_t off = __shfl_sync(0xffffffffu, nb[k], src_lane);
+                        if (fch < nf) cp_async_16(dst + (uint32_t)k * (2u * TILE_M * 16u), src + off);
+                    }
+                    cp_async_mbar_arrive(&raw_full[buf]);
+                    ++icount;
+                };
+                // every producer has finished reading both staging buffers (previous pass / tile)
+                asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
+                issue(0);
+                if (ngroups > 1) issue(1);
+                {                                            // WeightNet + the coordinate chunk while the first gathers fly
+                    unsigned char *a_hi = acquire(pass * g.wchunks);
+                    weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
+                    release();
+                }
+#pragma unroll 1
+                for (int grp = 0; grp < ngroups; ++grp) {
+                    const uint32_t buf = ccount & 1u;
+                    mbar_wait(&raw_full[buf], (ccount >> 1) & 1u);
+                    const unsigned char *stg = raw_base + (size_t)buf * kRawBytes + (size_t)r * 16;
+#pragma unroll 1
+                    for (int ee = 0; ee < 2; ++ee) {
+                        const int fch = grp * 2 + ee;
+                        if (fch >= nf) break;
+                        unsigned char *a_hi = acquire(pass * g.wchunks + 1 + fch);
+                        const unsigned char *sp = stg + (size_t)ee * TILE_M * 16;
+                        features([&](int k) { return *reinterpret_cast<const float4 *>(sp + (size_t)k * (2 * TILE_M * 16)); },
+                                 a_hi, a_hi + A_PART_BYTES, r);
+                        release();
+                    }
+                    ++ccount;
+                    if (grp + 2 < ngroups) {
+                        asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");   // buffer `buf` is free
+                        issue(grp + 2);
+                    }
+                }
+            }
+        }
+    }
 };
 
-// (An asynchronous cp.async variant of the gathers was measured 30 % SLOWER: it bypasses L1, and eight consecutive
-// K-chunks share each 128-byte line of a neighbour row - the synchronous __ldg path lives on those L1 hits.)
 static int kdpc_pointconv_stages = 2;
+static int kdpc_pointconv_staged = 1;
 
-template <int KN, int NPASS>
-static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS>::Args &pa, const void *wpacked,
-                            StoreEpilogue::Args ea, void *ws, cudaStream_t st) {
-    using P = PointConvProducer<KN, NPASS>;
-    GemmShape g = make_shape(m, n_out, (pa.d + 4) * 16, wpacked);
-    g.num_chunks = g.wchunks * NPASS;                        // one run of the weight's K-chunks per neighbour pass
-    g.chunks_per_split = g.num_chunks;
-    if (ws != nullptr) plan_split_k(g);
-    ea.partial = reinterpret_cast<float *>(ws);
-    // the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand stages are
-    // enough to keep the MMA fed and leave ~100 KB of the unified L1/shared array to the cache
-    if (g.stages > kdpc_pointconv_stages) g.stages = kdpc_pointconv_stages;
-    const size_t smem = smem_bytes(g.n_pad, g.stages);
+template <int KN, int NPASS, bool STAGED>
+static int launch_pointconv_v(GemmShape g, const typename PointConvProducer<KN, NPASS, false>::Args &pa0, StoreEpilogue::Args ea,
+                              cudaStream_t st) {
+    using P = PointConvProducer<KN, NPASS, STAGED>;
+    typename P::Args pa;
+    static_assert(sizeof(pa) == sizeof(pa0), "Args layout");
+    memcpy(&pa, &pa0, sizeof(pa));
+    const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
     auto kern = tc_gemm_kernel<P, StoreEpilogue>;
-    KDPC_ENSURE_SMEM(kern, 201 * 1024);
+    KDPC_ENSURE_SMEM(kern, 208 * 1024);
     const long long work = g.num_tiles * g.splits;
     const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
     kern<<<grid, num_threads<P>(), smem, st>>>(g, pa, ea);
     if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
     return (int)cudaGetLastError();
+}
+
+template <int KN, int NPASS>
+static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS, false>::Args &pa, const void *wpacked,
+                            StoreEpilogue::Args ea, void *ws, cudaStream_t st) {
+    GemmShape g = make_shape(m, n_out, (pa.d + 4) * 16, wpacked);
+    g.num_chunks = g.wchunks * NPASS;                        // one run of the weight's K-chunks per neighbour pass
+    g.chunks_per_split = g.num_chunks;
+    if (ws != nullptr) plan_split_k(g);
+    ea.partial = reinterpret_cast<float *>(ws);
+    // staged gathers: two staging buffers next to >= 2 operand stages (static shared memory: 18.5 KB)
+    constexpr int RAW = PointConvProducer<KN, NPASS, true>::kRawBytes;
+    const size_t staged_smem = smem_bytes(g.n_pad, 2, 2 * RAW);
+    if (kdpc_pointconv_staged && g.splits == 1 && staged_smem <= 208 * 1024) {
+        g.raw_bytes = RAW;
+        g.raw_stages = 2;
+        g.stages = 2;
+        while (g.stages < MAX_STAGES && smem_bytes(g.n_pad, g.stages + 1, 2 * RAW) <= 208 * 1024) ++g.stages;
+        return launch_pointconv_v<KN, NPASS, true>(g, pa, ea, st);
+    }
+    // register path: the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand
+    // stages are enough to keep the MMA fed and leave ~100 KB of the unified L1/shared array to the cache
+    if (g.stages > kdpc_pointconv_stages) g.stages = kdpc_pointconv_stages;
+    return launch_pointconv_v<KN, NPASS, false>(g, pa, ea, st);
 }
 
 static GemmShape pointconv_shape(long long m, int n_out, int d, int k) {
@@ -192,6 +323,8 @@ using namespace kdpc;
 using namespace kdpc::tc;
 
 KDPC_API void kdpc_pointconv_set_stages(int n) { kdpc::tc::kdpc_pointconv_stages = n < 2 ? 2 : n; }
+/* A/B switch: 0 = register-path gathers everywhere (same results) */
+KDPC_API void kdpc_pointconv_set_staged(int on) { kdpc::tc::kdpc_pointconv_staged = on; }
 
 KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out) {
     if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;
@@ -209,7 +342,7 @@ KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, 
     if ((reinterpret_cast<uintptr_t>(feats) % 16) != 0 || (reinterpret_cast<uintptr_t>(out) % 16) != 0 ||
         (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0 || (reinterpret_cast<uintptr_t>(ws) % 16) != 0)
         return KDPC_EINVAL;
-    PointConvProducer<9, 1>::Args pa;                        // (the Args layout does not depend on KN / NPASS)
+    PointConvProducer<9, 1, false>::Args pa;                 // (the Args layout does not depend on the template arguments)
     pa.cand_xyz = cand_xyz; pa.query_xyz = query_xyz; pa.feats = feats; pa.idx = idx;
     pa.n_cand = n; pa.s = s; pa.d = d;
     const float *p = wn_params;
@@ -221,7 +354,7 @@ KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, 
     for (int i = 0; i < 16; ++i) pa.b3[i] = *p++;
     StoreEpilogue::Args ea{scale, shift, slope, 1.f, 0.f, nullptr, out, n_out, nullptr};
     if (k == 9) return launch_pointconv<9, 1>((long long)b * s, n_out, pa, wpacked, ea, ws, to_stream(stream));
-    PointConvProducer<16, 2>::Args pb;
+    PointConvProducer<16, 2, false>::Args pb;
     static_assert(sizeof(pb) == sizeof(pa), "Args layout");
     memcpy(&pb, &pa, sizeof(pa));
     return launch_pointconv<16, 2>((long long)b * s, n_out, pb, wpacked, ea, ws, to_stream(stream));

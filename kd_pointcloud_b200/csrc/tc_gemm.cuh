@@ -22,8 +22,19 @@ namespace kdpc {
 namespace tc {
 
 constexpr int MAX_STAGES = 4;
-// threads of a kernel instance: PW producer warps + MMA warp + 4 epilogue warps
-template <class Producer> constexpr int num_threads() { return (Producer::kWarps + 5) * 32; }
+// threads of a kernel instance: PW producer warps + MMA warp + 4 epilogue warps.  Producers that declare
+// kMergedIssuer run the MMA issuer INSIDE the first epilogue warp (12 warps instead of 13): the register file is
+// split per SM sub-partition, so 13 warps (4 on one sub-partition) cap every thread at 128 registers while 12 warps
+// (3 per sub-partition) allow 168 - what a producer that keeps a whole neighbourhood in registers needs.
+template <class P, class = void> struct merged_issuer { static constexpr bool value = false; };
+template <class P> struct merged_issuer<P, decltype((void)P::kMergedIssuer)> { static constexpr bool value = P::kMergedIssuer; };
+// Producers that declare kOwnsLoop implement run_tile(tile, c_begin, c_end, ptid, raw_base, raw_full, acquire, release)
+// instead of fill(); with kIssuers > 0 they own the raw staging area and its mbarriers (kIssuers arrivals each)
+template <class P, class = void> struct owns_loop { static constexpr bool value = false; };
+template <class P> struct owns_loop<P, decltype((void)P::kOwnsLoop)> { static constexpr bool value = P::kOwnsLoop; };
+template <class Producer> constexpr int num_threads() {
+    return (Producer::kWarps + (merged_issuer<Producer>::value ? 4 : 5)) * 32;
+}
 
 struct GemmShape {
     long long m;          // rows
@@ -112,7 +123,7 @@ static inline size_t split_k_ws_bytes(const GemmShape &g) {
 //   struct E { struct Args {...};
 //              __device__ void tile(const Args&, const GemmShape&, long long tile, int split, uint32_t tmem_acc, int quarter, int lane); };
 template <class Producer, class Epilogue>
-__global__ void __launch_bounds__((Producer::kWarps + 5) * 32, 1)      // 13 warps are allocated as 16: 128 registers per thread
+__global__ void __launch_bounds__(num_threads<Producer>(), 1)
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
@@ -121,6 +132,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
     __shared__ uint32_t tmem_base_smem;
 
     constexpr int PW = Producer::kWarps;                                     // 4 or 8: epilogue warps PW+1..PW+4 have (warp & 3) = 1,2,3,0
+    constexpr bool MG = merged_issuer<Producer>::value;                      // warp PW = issuer AND epilogue of quarter 0
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);       // 1024-byte aligned tiles
@@ -135,7 +147,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             mbar_init(&full_b[s], 1);        // expect_tx arrive of the W loader
             mbar_init(&empty[s], 1);         // tcgen05.commit
         }
-        if constexpr (Producer::kAsync)
+        if constexpr (Producer::kIssuers > 0)
             for (int r = 0; r < MAX_RAW_STAGES; ++r) mbar_init(&raw_full[r], Producer::kIssuers);   // arrive.expect_tx per issuing thread
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);     // tcgen05.commit
@@ -210,6 +222,28 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             const long long tile = w / g.splits;
             const int c_begin = (int)(w - tile * g.splits) * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
+            if constexpr (owns_loop<Producer>::value) {
+                // the producer drives the K loop of its tile itself (tight inner loops with its state in registers):
+                // acquire(c) waits for a free operand stage, starts the weight TMA and returns the A tile; release()
+                // publishes it to the MMA issuer
+                int s = 0;
+                auto acquire = [&](int c) -> unsigned char * {
+                    s = it % g.stages;
+                    mbar_wait(&empty[s], ((it / g.stages) & 1) ^ 1);
+                    if (ptid == 0) {
+                        mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
+                        tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(c % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    }
+                    return a_base + (size_t)s * A_STAGE_BYTES;
+                };
+                auto release = [&]() {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_a[s]);
+                    ++it;
+                };
+                prod.run_tile(tile, c_begin, c_end, ptid, raw_base, raw_full, acquire, release);
+            } else {
             bool began = false;
             for (int c = c_begin; c < c_end; ++c, ++it) {
                 if (PG > 1 && (int)(it % PG) != grp) continue;
@@ -227,13 +261,26 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_a[s]);
             }
+            }
         }
         }
     } else if (warp == PW) {
-        // ================= MMA issuer =================
+        // ================= MMA issuer (+ epilogue of TMEM lane quarter 0 when merged) =================
         const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
         uint32_t it = 0, tcount = 0;
         const long long work = g.num_tiles * g.splits;
+        Epilogue epi;
+        long long owed = -1;                                      // merged: work item whose epilogue this warp still owes
+        auto run_epilogue = [&](long long w, uint32_t tc) {
+            const long long tile = w / g.splits;
+            const uint32_t acc = tc & 1;
+            mbar_wait(&tmem_full[acc], (tc >> 1) & 1);
+            fence_after_sync();
+            epi.tile(ea, g, tile, (int)(w - tile * g.splits), tmem_base + acc * (uint32_t)g.acc_stride, 0, lane);
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        };
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
             const int c_begin = (int)(w % g.splits) * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
@@ -265,8 +312,16 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                     if (c == c_end - 1) umma_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
+                if constexpr (MG) {
+                    // the previous tile's accumulator completes while the producers fill this tile's second chunk:
+                    // drain this warp's quarter of it now (the MMAs just issued keep the tensor pipe busy meanwhile)
+                    if (c == c_begin && owed >= 0) { run_epilogue(owed, tcount - 1); owed = -1; }
+                }
             }
+            if constexpr (MG) owed = w;
         }
+        if constexpr (MG)
+            if (owed >= 0) run_epilogue(owed, tcount - 1);
     } else {
         // ================= epilogue =================
         const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
