@@ -194,7 +194,9 @@ def kernel_rooflines(torch, dev, B, hbm_peak, tc_peak):
     wp = K.pack_weight(lin.weight.detach(), 1, D, 16)
     params = KF._weightnet_host_params(wn.mlp_convs)
     bias = lin.bias.detach()
-    t = timeit(lambda: K.pointconv_fused(xyz, xyz, feats, idx9, params, wp, Cout, None, bias, 0.1))
+    KF._knn_compute(Kn, xyz, xyz)                          # the model's kNN leaves the cloud's Morton order in the sort cache
+    order = KF.morton_order(xyz)                           # (what PointConv.forward passes: functional.fused_pointconv)
+    t = timeit(lambda: K.pointconv_fused(xyz, xyz, feats, idx9, params, wp, Cout, None, bias, 0.1, order))
     S = B * N
     flops = 2.0 * S * (D + 3) * Kn * 16 + 2.0 * S * 16 * (D + 3) * Cout + 2.0 * S * Kn * 216
     byts = B * (4 * N * Kn + 24 * N + 4 * N * D + 4 * N * Cout)

@@ -188,12 +188,22 @@ long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out);
 /* operand pipeline stages of the fused PointConv (default 2: the rest of the SM's L1/shared array serves the
  * neighbour gathers; measured 5% faster end to end than 3). */
 void kdpc_pointconv_set_stages(int n);
-/* A/B switch for measurements: 0 = per-thread register gathers everywhere instead of the cp.async staging (same results) */
-void kdpc_pointconv_set_staged(int on);
 int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
                          const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
                          const void *wpacked, const float *scale, const float *shift, float slope,
                          void *ws, float *out, kdpc_stream_t stream);
+/* Same, processing the queries of every cloud in a caller-given order (same results, bit for bit): tile position i of
+ * cloud b handles query row_order[b * order_stride + i] (a permutation of 0..s-1 per cloud, order_stride >= s).  With a
+ * spatially coherent order - the Morton order kdpc_spatial_sort leaves in its workspace - the 128 queries of a tile
+ * share most of their neighbours, so the neighbour gathers hit in L1 instead of L2.  Ignored for split-K shapes. */
+int kdpc_pointconv_fused_ordered(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
+                                 const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
+                                 const void *wpacked, const float *scale, const float *shift, float slope,
+                                 const int *row_order, int order_stride, void *ws, float *out, kdpc_stream_t stream);
+/* int32 element offset of the sorted-position -> original-index table inside one cloud's block of a
+ * kdpc_spatial_sort workspace, and the size of that block in int32 elements (= the order_stride to pass above) */
+int kdpc_spatial_sort_order_offset(int n);
+int kdpc_spatial_sort_order_stride(int n);
 
 /* CrossLayerLight.cross (pointconv_util.py:1826-1850) with a single-layer mlp, fused: out[b,i,:] =
  * max_k leaky(W act(p2[idx[b,i,k]] + p1[b,i] + pos_w (xyz2[idx]-xyz1[i]) + pos_b) + bias, slope_post).

@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libkdpc.so")
+LIB_PATH = os.environ.get("KDPC_LIB") or os.path.join(_HERE, "libkdpc.so")   # KDPC_LIB: an experiment build (A/B measurements)
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
            "scatter.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -37,7 +37,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every kernel for sm_100a with nvcc (cross-compiles without a GPU): one object per
     source (in parallel, rebuilt only when stale) under csrc/build/, then one link."""
-    if not force and not needs_build():
+    if os.environ.get("KDPC_LIB") or (not force and not needs_build()):
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -68,6 +68,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _P = c_void_p
 _SIGNATURES = {
     # name: argtypes (restype is int unless noted)
+    "kdpc_pointconv_fused_ordered": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, c_int,
+                                     _P, _P, _P],
+    "kdpc_spatial_sort_order_offset": [c_int],
+    "kdpc_spatial_sort_order_stride": [c_int],
     "kdpc_fps": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_gather": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_gather_grad": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
@@ -146,10 +150,6 @@ def lib() -> ctypes.CDLL:
         L.kdpc_pointconv_set_stages.argtypes = [c_int]
         if os.environ.get("KDPC_PC_STAGES"):
             L.kdpc_pointconv_set_stages(int(os.environ["KDPC_PC_STAGES"]))
-        L.kdpc_pointconv_set_staged.restype = None
-        L.kdpc_pointconv_set_staged.argtypes = [c_int]
-        if os.environ.get("KDPC_PC_STAGED", "1") == "0":
-            L.kdpc_pointconv_set_staged(0)
         if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
             L.kdpc_tc_set_async(0)
         if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements
@@ -161,7 +161,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_staged",
+            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 

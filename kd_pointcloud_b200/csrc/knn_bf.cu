@@ -461,6 +461,12 @@ static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cw
 
 using namespace kdpc;
 
+KDPC_API int kdpc_spatial_sort_order_offset(int n) {
+    const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;
+    return (int)(((size_t)n * 16 + nt * 32) / 4);
+}
+KDPC_API int kdpc_spatial_sort_order_stride(int n) { return (int)(sorted_cloud_bytes(n) / 4); }
+
 KDPC_API long long kdpc_spatial_sort_bytes(int b, int n) {
     if (b <= 0 || n <= 0) return 0;
     return (long long)sorted_cloud_bytes(n) * b;

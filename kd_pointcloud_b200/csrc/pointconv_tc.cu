@@ -26,14 +26,17 @@ namespace tc {
 // weight chunks repeat).  K = 16 (PointConvD) runs as 2 x 8, which keeps wn[NB][8] in registers.
 // K-chunk 0 of a pass = channels (dx, dy, dz, 0); chunk i >= 1 = feature channels 4(i-1) .. 4(i-1)+3.
 //
-// STAGED = true (whenever the shared memory fits: Cout <= 128, no split-K): the neighbours' feature rows are
-// gathered by 16-byte cp.async into a double-buffered staging area two K-chunks (32 bytes = one L2 sector per
-// neighbour row) at a time, one group ahead of the arithmetic: lane pairs fetch the two halves of a sector, every
-// byte crosses the L2 -> SM link once, and the FFMA loop reads conflict-free 16-byte shared-memory words.  The
-// register path (STAGED = false) has every thread (row, half) load its own 16 bytes per neighbour per chunk: both
-// halves fetch the same data, every lane of a request touches a different line (32 tag look-ups per instruction:
-// the L1 pipe ran at 55-65 % with the kernel still latency bound) and each sector is fetched about twice.
-template <int KN, int NPASS, bool STAGED>
+// Neighbour gathers: thread (row, half) reads the 16 bytes (4 channels) of each neighbour's row straight into
+// registers; the two half-lanes of a row are adjacent lanes, so a warp request touches 16 rows and the pair is one
+// coalesced access; eight consecutive K-chunks share each 128-byte line (L1 hits), and with a Morton row order the
+// 128 queries of a tile share most of their neighbours.
+// Rejected by measurement on the same box (same results, tools/bench_pointconv.py, tools/trace_pointconv.py):
+//   * cp.async staging of the gathers in shared memory (per CTA, per row quarter and per warp; double buffered; also
+//     interleaved into the FFMA loop): never faster - a warp-level LDGSTS whose lanes touch 16 lines blocks the
+//     issuing warp for ~150 cycles, and the 74 KB of staging take the L1 away;
+//   * software pipelining (chunk c+1's loads issued after chunk c's FFMAs, stage acquired after the FFMAs): 5 %
+//     slower, the extra live registers spill in the WeightNet phase.
+template <int KN, int NPASS>
 struct PointConvProducer {
     static constexpr int kWarps = 8, kGroups = 1;
     static constexpr bool kAsync = false;
@@ -42,15 +45,16 @@ struct PointConvProducer {
     // 1.1 GB of L2 traffic per launch at flow0)
     static constexpr bool kMergedIssuer = true;
     static constexpr bool kOwnsLoop = true;                  // run_tile() below instead of fill()
-    static constexpr int kIssuers = STAGED ? 256 : 0, kLookahead = 0;
+    static constexpr int kIssuers = 0, kLookahead = 0;
     static constexpr int NB = KN / NPASS;
-    static constexpr int kRawBytes = NB * 2 * TILE_M * 16;   // one staging buffer: [neighbour][piece][row][16 B]
     struct Args {
         const float *cand_xyz;    // [B,N,3]
         const float *query_xyz;   // [B,S,3]
         const float *feats;       // [B,N,D]
         const int *idx;           // [B,S,KN]
         int n_cand, s, d;
+        const int *order;         // optional [B] x order_stride: tile position i of cloud b processes query order[b][i]
+        int order_stride;
         float w1[24], b1[8], w2[64], b2[8], w3[128], b3[16];    // WeightNet 3 -> 8 -> 8 -> 16, ReLU after each
     };
     static __device__ __forceinline__ void prologue(const Args &, int, int) {}
@@ -61,16 +65,22 @@ struct PointConvProducer {
     const int *ip;
     float qx, qy, qz;
     int half, boff;
-    uint32_t icount, ccount;      // staging groups issued / consumed so far (buffer = count & 1, phase = count >> 1)
 
-    __device__ PointConvProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_), icount(0), ccount(0) {}
+    __device__ PointConvProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
 
+    // Thread mapping: producer warp w owns tile rows 16w .. 16w+15, lane = 2 * (row & 15) + half.  A warp is then the
+    // only reader of its rows' gathered data (no cross-warp hand-over of staging buffers), the two half-lanes of a row
+    // read the same 16 bytes (one broadcast shared-memory word / one coalesced global request), and lane (row, h)
+    // fetches piece h of its own row's neighbours - no index exchange.
+    static __device__ __forceinline__ int tile_row(int ptid) { return (ptid >> 5) * 16 + ((ptid & 31) >> 1); }
     __device__ __forceinline__ void begin_tile(long long tile, int ptid) {
-        const int r = ptid & 127;
-        half = ptid >> 7;
+        const int r = tile_row(ptid);
+        half = ptid & 1;
         long long row = tile * TILE_M + r;
         if (row >= g.m) row = g.m - 1;                       // padded rows recompute the last point; never stored
-        boff = (int)(row / a.s) * a.n_cand;
+        const int bq = (int)(row / a.s);
+        if (a.order != nullptr) row = (long long)bq * a.s + __ldg(a.order + (long long)bq * a.order_stride + (row - (long long)bq * a.s));
+        boff = bq * a.n_cand;
         ip = a.idx + row * KN;
         const float *qp = a.query_xyz + row * 3;
         qx = qp[0]; qy = qp[1]; qz = qp[2];
@@ -144,168 +154,91 @@ struct PointConvProducer {
         }
     }
 
-    // one K-chunk of 4 feature channels: v(k) = the 4 channels of neighbour k
-    template <class Fetch>
-    __device__ __forceinline__ void features(Fetch &&v4, unsigned char *a_hi, unsigned char *a_lo, int r) {
-        float acc[4][8];
+    __device__ __forceinline__ void gather(int fchunk, float4 (&v)[NB]) const {
+        const float *fp = a.feats + fchunk * 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            const float4 v = v4(k);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[0][j] = fmaf(v.x, wn[k][j], acc[0][j]);
-                acc[1][j] = fmaf(v.y, wn[k][j], acc[1][j]);
-                acc[2][j] = fmaf(v.z, wn[k][j], acc[2][j]);
-                acc[3][j] = fmaf(v.w, wn[k][j], acc[3][j]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint4 hi, lo;
-            split8(acc[c], hi, lo);
-            const uint32_t off = sw128_offset(r, c * 2 + half);
-            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-        }
+        for (int k = 0; k < NB; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(fp + nb[k]));
     }
 
     template <class Acquire, class Release>
-    __device__ __forceinline__ void run_tile(long long tile, int c_begin, int c_end, int ptid, unsigned char *raw_base,
-                                             uint64_t *raw_full, Acquire &&acquire, Release &&release) {
-        const int r = ptid & 127;
+    __device__ __forceinline__ void run_tile(long long tile, int c_begin, int c_end, int ptid, unsigned char *, uint64_t *,
+                                             Acquire &&acquire, Release &&release) {
+        const int r = tile_row(ptid);
         begin_tile(tile, ptid);
-        if constexpr (!STAGED) {
-            int c = c_begin;
-            while (c < c_end) {
-                const int pass = c / g.wchunks;
-                const int base = pass * g.wchunks;
-                int gi[NB];
-                load_idx(pass, gi);
-                if (c == base) {
-                    unsigned char *a_hi = acquire(c);
-                    weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
-                    release();
-                    ++c;
-                } else {
-                    weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
-                }
-                const int stop = min(c_end, base + g.wchunks);
-#pragma unroll 1
-                for (; c < stop; ++c) {
-                    unsigned char *a_hi = acquire(c);
-                    const float *fp = a.feats + (c - base - 1) * 4;
-                    features([&](int k) { return __ldg(reinterpret_cast<const float4 *>(fp + nb[k])); }, a_hi,
-                             a_hi + A_PART_BYTES, r);
-                    release();
-                }
+        int c = c_begin;
+        while (c < c_end) {
+            const int pass = c / g.wchunks;
+            const int base = pass * g.wchunks;
+            const int stop = min(c_end, base + g.wchunks);
+            int gi[NB];
+            load_idx(pass, gi);
+            if (c == base) {
+                unsigned char *a_hi = acquire(c);
+                weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
+                release();
+                ++c;
+            } else {
+                weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
             }
-        } else {
-            // (launched without split-K: c_begin = 0, c_end = NPASS * wchunks)
-            const int lane = ptid & 31;
-            const int nf = g.wchunks - 1;                    // feature chunks per pass
-            const int ngroups = (nf + 1) >> 1;               // staging groups of two chunks
-            // gather issue: lane pairs fetch the two 16-byte halves of one neighbour row's 32-byte piece; this warp
-            // (row quarter q, half h) issues for rows 32q + 16h + (lane >> 1), whose offsets live in lane 16h + (lane >> 1)
-            const int src_lane = half * 16 + (lane >> 1);
-            const int irow = (r & ~31) + src_lane;
-            const int e = lane & 1;
-            for (int pass = 0; pass < NPASS; ++pass) {
-                int gi[NB];
-                load_idx(pass, gi);
-                auto issue = [&](int grp) {
-                    const uint32_t buf = icount & 1u;
-                    const int fch = grp * 2 + e;
-                    const uint32_t dst = smem_u32(raw_base + (size_t)buf * kRawBytes) + (uint32_t)(e * TILE_M + irow) * 16u;
-                    const float *src = a.feats + fch * 4;
+#pragma unroll 1
+            for (; c < stop; ++c) {
+                unsigned char *a_hi = acquire(c);
+                float4 v[NB];
+                gather(c - base - 1, v);
+                float acc[4][8];
 #pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const uint32_t off = __shfl_sync(0xffffffffu, nb[k], src_lane);
-                        if (fch < nf) cp_async_16(dst + (uint32_t)k * (2u * TILE_M * 16u), src + off);
-                    }
-                    cp_async_mbar_arrive(&raw_full[buf]);
-                    ++icount;
-                };
-                // every producer has finished reading both staging buffers (previous pass / tile)
-                asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
-                issue(0);
-                if (ngroups > 1) issue(1);
-                {                                            // WeightNet + the coordinate chunk while the first gathers fly
-                    unsigned char *a_hi = acquire(pass * g.wchunks);
-                    weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
-                    release();
-                }
-#pragma unroll 1
-                for (int grp = 0; grp < ngroups; ++grp) {
-                    const uint32_t buf = ccount & 1u;
-                    mbar_wait(&raw_full[buf], (ccount >> 1) & 1u);
-                    const unsigned char *stg = raw_base + (size_t)buf * kRawBytes + (size_t)r * 16;
-#pragma unroll 1
-                    for (int ee = 0; ee < 2; ++ee) {
-                        const int fch = grp * 2 + ee;
-                        if (fch >= nf) break;
-                        unsigned char *a_hi = acquire(pass * g.wchunks + 1 + fch);
-                        const unsigned char *sp = stg + (size_t)ee * TILE_M * 16;
-                        features([&](int k) { return *reinterpret_cast<const float4 *>(sp + (size_t)k * (2 * TILE_M * 16)); },
-                                 a_hi, a_hi + A_PART_BYTES, r);
-                        release();
-                    }
-                    ++ccount;
-                    if (grp + 2 < ngroups) {
-                        asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");   // buffer `buf` is free
-                        issue(grp + 2);
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[ch][j] = 0.f;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc[0][j] = fmaf(v[k].x, wn[k][j], acc[0][j]);
+                        acc[1][j] = fmaf(v[k].y, wn[k][j], acc[1][j]);
+                        acc[2][j] = fmaf(v[k].z, wn[k][j], acc[2][j]);
+                        acc[3][j] = fmaf(v[k].w, wn[k][j], acc[3][j]);
                     }
                 }
+                unsigned char *a_lo = a_hi + A_PART_BYTES;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint4 hi, lo;
+                    split8(acc[ch], hi, lo);
+                    const uint32_t off = sw128_offset(r, ch * 2 + half);
+                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                }
+                release();
             }
         }
     }
 };
 
 static int kdpc_pointconv_stages = 2;
-static int kdpc_pointconv_staged = 1;
-
-template <int KN, int NPASS, bool STAGED>
-static int launch_pointconv_v(GemmShape g, const typename PointConvProducer<KN, NPASS, false>::Args &pa0, StoreEpilogue::Args ea,
-                              cudaStream_t st) {
-    using P = PointConvProducer<KN, NPASS, STAGED>;
-    typename P::Args pa;
-    static_assert(sizeof(pa) == sizeof(pa0), "Args layout");
-    memcpy(&pa, &pa0, sizeof(pa));
-    const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
-    auto kern = tc_gemm_kernel<P, StoreEpilogue>;
-    KDPC_ENSURE_SMEM(kern, 208 * 1024);
-    const long long work = g.num_tiles * g.splits;
-    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
-    kern<<<grid, num_threads<P>(), smem, st>>>(g, pa, ea);
-    if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
-    return (int)cudaGetLastError();
-}
+static long long *kdpc_pointconv_trace = nullptr;
 
 template <int KN, int NPASS>
-static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS, false>::Args &pa, const void *wpacked,
+static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS>::Args &pa, const void *wpacked,
                             StoreEpilogue::Args ea, void *ws, cudaStream_t st) {
+    using P = PointConvProducer<KN, NPASS>;
     GemmShape g = make_shape(m, n_out, (pa.d + 4) * 16, wpacked);
     g.num_chunks = g.wchunks * NPASS;                        // one run of the weight's K-chunks per neighbour pass
     g.chunks_per_split = g.num_chunks;
     if (ws != nullptr) plan_split_k(g);
     ea.partial = reinterpret_cast<float *>(ws);
-    // staged gathers: two staging buffers next to >= 2 operand stages (static shared memory: 18.5 KB)
-    constexpr int RAW = PointConvProducer<KN, NPASS, true>::kRawBytes;
-    const size_t staged_smem = smem_bytes(g.n_pad, 2, 2 * RAW);
-    if (kdpc_pointconv_staged && g.splits == 1 && staged_smem <= 208 * 1024) {
-        g.raw_bytes = RAW;
-        g.raw_stages = 2;
-        g.stages = 2;
-        while (g.stages < MAX_STAGES && smem_bytes(g.n_pad, g.stages + 1, 2 * RAW) <= 208 * 1024) ++g.stages;
-        return launch_pointconv_v<KN, NPASS, true>(g, pa, ea, st);
-    }
-    // register path: the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand
-    // stages are enough to keep the MMA fed and leave ~100 KB of the unified L1/shared array to the cache
+    g.trace = kdpc_pointconv_trace;
+    // the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand stages are
+    // enough to keep the MMA fed and leave ~80 KB of the unified L1/shared array to the cache
     if (g.stages > kdpc_pointconv_stages) g.stages = kdpc_pointconv_stages;
-    return launch_pointconv_v<KN, NPASS, false>(g, pa, ea, st);
+    const size_t smem = smem_bytes(g.n_pad, g.stages);
+    auto kern = tc_gemm_kernel<P, StoreEpilogue>;
+    KDPC_ENSURE_SMEM(kern, 201 * 1024);
+    const long long work = g.num_tiles * g.splits;
+    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
+    kern<<<grid, num_threads<P>(), smem, st>>>(g, pa, ea);
+    if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
+    return (int)cudaGetLastError();
 }
 
 static GemmShape pointconv_shape(long long m, int n_out, int d, int k) {
@@ -323,26 +256,28 @@ using namespace kdpc;
 using namespace kdpc::tc;
 
 KDPC_API void kdpc_pointconv_set_stages(int n) { kdpc::tc::kdpc_pointconv_stages = n < 2 ? 2 : n; }
-/* A/B switch: 0 = register-path gathers everywhere (same results) */
-KDPC_API void kdpc_pointconv_set_staged(int on) { kdpc::tc::kdpc_pointconv_staged = on; }
+/* debug: device buffer of 200 x 16 int64 receiving CTA 0's per-chunk clock64 stamps (tools/trace_pointconv.py); NULL = off */
+KDPC_API void kdpc_pointconv_set_trace(void *p) { kdpc::tc::kdpc_pointconv_trace = reinterpret_cast<long long *>(p); }
 
 KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out) {
     if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;
     return (long long)split_k_ws_bytes(pointconv_shape((long long)b * s, n_out, d, k));
 }
 
-KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
-                                  const float *query_xyz, const float *feats, const int *idx,
-                                  const float *wn_params /* host: w1[24] b1[8] w2[64] b2[8] w3[128] b3[16] */,
-                                  const void *wpacked, const float *scale, const float *shift, float slope,
-                                  void *ws, float *out, kdpc_stream_t stream) {
+KDPC_API int kdpc_pointconv_fused_ordered(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
+                                          const float *query_xyz, const float *feats, const int *idx,
+                                          const float *wn_params /* host: w1[24] b1[8] w2[64] b2[8] w3[128] b3[16] */,
+                                          const void *wpacked, const float *scale, const float *shift, float slope,
+                                          const int *row_order, int order_stride, void *ws, float *out,
+                                          kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(cand_xyz && query_xyz && feats && idx && wn_params && wpacked && out && b > 0 && n > 0 && s > 0 &&
                     d > 0 && n_out > 0);
     if (n_out > 256 || (d & 3) != 0 || (k != 9 && k != 16)) return KDPC_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(feats) % 16) != 0 || (reinterpret_cast<uintptr_t>(out) % 16) != 0 ||
         (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0 || (reinterpret_cast<uintptr_t>(ws) % 16) != 0)
         return KDPC_EINVAL;
-    PointConvProducer<9, 1, false>::Args pa;                 // (the Args layout does not depend on the template arguments)
+    if (row_order != nullptr && order_stride < s) return KDPC_EINVAL;
+    PointConvProducer<9, 1>::Args pa;                 // (the Args layout does not depend on the template arguments)
     pa.cand_xyz = cand_xyz; pa.query_xyz = query_xyz; pa.feats = feats; pa.idx = idx;
     pa.n_cand = n; pa.s = s; pa.d = d;
     const float *p = wn_params;
@@ -353,9 +288,22 @@ KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, 
     for (int i = 0; i < 128; ++i) pa.w3[i] = *p++;
     for (int i = 0; i < 16; ++i) pa.b3[i] = *p++;
     StoreEpilogue::Args ea{scale, shift, slope, 1.f, 0.f, nullptr, out, n_out, nullptr};
+    // the row order only pays (and is only supported) without split-K: small layers keep the natural order
+    const bool ordered = row_order != nullptr && pointconv_shape((long long)b * s, n_out, d, k).splits == 1;
+    pa.order = ordered ? row_order : nullptr;
+    pa.order_stride = ordered ? order_stride : 0;
+    if (ordered) { ea.row_order = row_order; ea.order_stride = order_stride; ea.rows_per_cloud = s; }
     if (k == 9) return launch_pointconv<9, 1>((long long)b * s, n_out, pa, wpacked, ea, ws, to_stream(stream));
-    PointConvProducer<16, 2, false>::Args pb;
+    PointConvProducer<16, 2>::Args pb;
     static_assert(sizeof(pb) == sizeof(pa), "Args layout");
     memcpy(&pb, &pa, sizeof(pa));
     return launch_pointconv<16, 2>((long long)b * s, n_out, pb, wpacked, ea, ws, to_stream(stream));
+}
+
+KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
+                                  const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
+                                  const void *wpacked, const float *scale, const float *shift, float slope,
+                                  void *ws, float *out, kdpc_stream_t stream) {
+    return kdpc_pointconv_fused_ordered(b, n, s, k, d, n_out, cand_xyz, query_xyz, feats, idx, wn_params, wpacked, scale,
+                                        shift, slope, nullptr, 0, ws, out, stream);
 }

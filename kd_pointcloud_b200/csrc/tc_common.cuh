@@ -52,6 +52,12 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of the (converged) warp: the predicate ptxas recognises for single-thread tcgen05 issue
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -52,6 +52,7 @@ struct GemmShape {
     int raw_stages;       // lookahead + 1
     long long num_tiles;
     const unsigned char *wpacked;   // [chunk][hi|lo][n_pad][128 B]
+    long long *trace;     // debug: per-chunk clock64 stamps of CTA 0 (nullptr = off)
 };
 
 constexpr int MAX_RAW_STAGES = 4;
@@ -90,6 +91,7 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.stages = pick_stages(g.n_pad, raw_bytes * raw_stages);
     g.num_tiles = (m + TILE_M - 1) / TILE_M;
     g.wpacked = reinterpret_cast<const unsigned char *>(wpacked);
+    g.trace = nullptr;
     return g;
 }
 
@@ -217,6 +219,8 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             }
         } else {
         uint32_t it = 0;
+        int ol_s = 0, ol_wc = 0;                                  // kOwnsLoop cursors: operand stage, its phase, weight chunk
+        uint32_t ol_ph = 0;
         const long long work = g.num_tiles * g.splits;
         for (long long w = blockIdx.x; w < work; w += gridDim.x) {
             const long long tile = w / g.splits;
@@ -226,22 +230,33 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 // the producer drives the K loop of its tile itself (tight inner loops with its state in registers):
                 // acquire(c) waits for a free operand stage, starts the weight TMA and returns the A tile; release()
                 // publishes it to the MMA issuer
-                int s = 0;
-                auto acquire = [&](int c) -> unsigned char * {
-                    s = it % g.stages;
-                    mbar_wait(&empty[s], ((it / g.stages) & 1) ^ 1);
+                // (stage / phase / weight-chunk cursors are carried incrementally: a runtime % and / per chunk cost
+                // more instructions than the hi/lo split of the chunk)
+                auto stamp = [&](int ev) {                        // debug trace of CTA 0 (kdpc_pointconv_set_trace)
+                    if (g.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == PW - 1) && it < 200)
+                        g.trace[it * 16 + (warp == 0 ? 0 : 4) + ev] = clock64();
+                };
+                auto acquire = [&](int /*c*/) -> unsigned char * {
+                    stamp(0);
+                    mbar_wait(&empty[ol_s], ol_ph ^ 1u);
+                    stamp(1);
                     if (ptid == 0) {
-                        mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                        tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(c % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                        mbar_expect_tx(&full_b[ol_s], (uint32_t)bbytes);
+                        tma_load_1d(b_base + (size_t)ol_s * bbytes, g.wpacked + (size_t)ol_wc * bbytes, (uint32_t)bbytes, &full_b[ol_s]);
                     }
-                    return a_base + (size_t)s * A_STAGE_BYTES;
+                    return a_base + (size_t)ol_s * A_STAGE_BYTES;
                 };
                 auto release = [&]() {
+                    stamp(2);
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_a[s]);
+                    if (lane == 0) mbar_arrive(&full_a[ol_s]);
+                    stamp(3);
                     ++it;
+                    if (++ol_s == g.stages) { ol_s = 0; ol_ph ^= 1u; }
+                    if (++ol_wc == g.wchunks) ol_wc = 0;
                 };
+                ol_wc = c_begin % g.wchunks;
                 prod.run_tile(tile, c_begin, c_end, ptid, raw_base, raw_full, acquire, release);
             } else {
             bool began = false;
@@ -267,7 +282,9 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
     } else if (warp == PW) {
         // ================= MMA issuer (+ epilogue of TMEM lane quarter 0 when merged) =================
         const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
-        uint32_t it = 0, tcount = 0;
+        const uint32_t a_base_u32 = smem_u32(a_base), b_base_u32 = smem_u32(b_base);
+        uint32_t it = 0, tcount = 0, mph = 0;
+        int ms = 0;                                               // operand stage / phase of iteration `it`
         const long long work = g.num_tiles * g.splits;
         Epilogue epi;
         long long owed = -1;                                      // merged: work item whose epilogue this warp still owes
@@ -288,28 +305,45 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             fence_after_sync();
             const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
+            int wc = c_begin % g.wchunks;                         // weight chunk of iteration c
             for (int c = c_begin; c < c_end; ++c, ++it) {
-                const int s = it % g.stages;
-                const uint32_t ph = (it / g.stages) & 1;
+                const int s = ms;
+                const uint32_t ph = mph;
+                if (++ms == g.stages) { ms = 0; mph ^= 1u; }
+                const bool trm = g.trace != nullptr && blockIdx.x == 0 && lane == 0 && it < 200;
+                if (trm) g.trace[it * 16 + 8] = clock64();
                 mbar_wait(&full_a[s], ph);
+                if (trm) g.trace[it * 16 + 9] = clock64();
                 mbar_wait(&full_b[s], ph);
+                if (trm) g.trace[it * 16 + 10] = clock64();
                 fence_after_sync();
-                if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(a_base + (size_t)s * A_STAGE_BYTES);
+                {
+                    // Everything here is warp-uniform and computed by ALL lanes, only the tcgen05 instructions sit
+                    // under the elect predicate: descriptors then live in uniform registers.  (Issuing from inside an
+                    // `if (lane == 0)` block made ptxas wrap every MMA in an ELECT + 7x R2UR waterfall loop: ~155
+                    // cycles of issue per MMA, twice the MMA's own 64 cycles.)
+                    const uint32_t a_hi = a_base_u32 + (uint32_t)s * A_STAGE_BYTES;
                     const uint32_t a_lo = a_hi + A_PART_BYTES;
-                    const uint32_t b_hi = smem_u32(b_base + (size_t)s * bbytes);
+                    const uint32_t b_hi = b_base_u32 + (uint32_t)s * (uint32_t)bbytes;
                     const uint32_t b_lo = b_hi + (uint32_t)g.n_pad * 128u;
-                    const int ksteps = min(CHUNK_K / UMMA_K, (g.k_total - (c % g.wchunks) * CHUNK_K) / UMMA_K);
+                    const int ksteps = min(CHUNK_K / UMMA_K, (g.k_total - wc * CHUNK_K) / UMMA_K);
+                    const bool leader = elect_one();
                     for (int kk = 0; kk < ksteps; ++kk) {
                         const uint32_t off = (uint32_t)kk * (UMMA_K * 2);
                         const uint64_t dah = make_smem_desc_sw128(a_hi + off), dal = make_smem_desc_sw128(a_lo + off);
                         const uint64_t dbh = make_smem_desc_sw128(b_hi + off), dbl = make_smem_desc_sw128(b_lo + off);
-                        umma_bf16(d_addr, dah, dbh, idesc, (c != c_begin) || (kk != 0));
-                        umma_bf16(d_addr, dah, dbl, idesc, 1);
-                        umma_bf16(d_addr, dal, dbh, idesc, 1);
+                        if (leader) {
+                            umma_bf16(d_addr, dah, dbh, idesc, (c != c_begin) || (kk != 0));
+                            umma_bf16(d_addr, dah, dbl, idesc, 1);
+                            umma_bf16(d_addr, dal, dbh, idesc, 1);
+                        }
                     }
-                    umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
-                    if (c == c_end - 1) umma_commit(&tmem_full[acc]);
+                    if (leader) {
+                        umma_commit(&empty[s]);                   // frees the smem stage when the MMAs retire
+                        if (c == c_end - 1) umma_commit(&tmem_full[acc]);
+                        if (trm) g.trace[it * 16 + 11] = clock64();
+                    }
+                    if (++wc == g.wchunks) wc = 0;
                 }
                 __syncwarp();
                 if constexpr (MG) {
@@ -363,6 +397,11 @@ struct StoreEpilogue {
         float *out;
         int ldo;
         float *partial;          // split-K workspace [splits][M][n_pad] (g.splits > 1): raw sums, epilogue applied by the reducer
+        // optional row order (never with split-K): tile row p = b * rows_per_cloud + i is output row
+        // b * rows_per_cloud + row_order[b * order_stride + i] (the producer processed that row at position p)
+        const int *row_order = nullptr;
+        int order_stride = 0;
+        int rows_per_cloud = 0;
     };
     // tcgen05.ld hands each lane ONE ROW of the 32 x 32 block (v[j] = column j).  Storing that directly makes every
     // store instruction touch 32 different rows, 16 bytes each: measured 4x slower than the whole rest of the kernel
@@ -405,10 +444,15 @@ struct StoreEpilogue {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = i * 4 + rsub;
-                const long long row = row0 + r;
+                const long long prow = row0 + r;
                 const float4 t = *reinterpret_cast<const float4 *>(st + r * TP + c4);
                 float y[4] = {t.x, t.y, t.z, t.w};
-                if (row < g.m && col < ncols) {
+                if (prow < g.m && col < ncols) {
+                    long long row = prow;
+                    if (e.row_order != nullptr) {
+                        const long long b = prow / e.rows_per_cloud;
+                        row = b * e.rows_per_cloud + __ldg(e.row_order + b * e.order_stride + (prow - b * e.rows_per_cloud));
+                    }
                     float *o = obase + row * ld + col;
                     if (!partial) {
 #pragma unroll

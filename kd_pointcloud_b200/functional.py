@@ -16,8 +16,10 @@ from __future__ import annotations
 from collections import OrderedDict
 from typing import Optional, Tuple
 
+import os
 import torch
 
+from . import _lib
 from . import ops  # noqa: F401  (registers torch.ops.kdpc)
 
 K = torch.ops.kdpc
@@ -450,13 +452,37 @@ def fused_pointconv_available(weightnet, linear, bn, nsample: int, feats: torch.
 FUSED_POINTCONV_K = (9, 16)
 
 
+def morton_order(xyz_d: torch.Tensor):
+    """int32 [B,N] view (row stride = one cloud's block) of the Morton order of a cloud that has ALREADY been
+    spatially sorted for a kNN call (cached), else None.  No kernel is launched here."""
+    if not _CACHE_ENABLED or not xyz_d.is_contiguous():
+        return None
+    hit = _SORT_CACHE.get(_tkey(xyz_d))
+    if hit is None:
+        return None
+    B, N, _ = xyz_d.shape
+    L = _lib.lib()
+    stride, off = L.kdpc_spatial_sort_order_stride(N), L.kdpc_spatial_sort_order_offset(N)
+    buf = hit[0]
+    if buf.numel() != B * stride * 4:
+        return None
+    return buf.view(torch.int32).view(B, stride)[:, off:off + N]
+
+
 def fused_pointconv(cand_xyz, query_xyz, feats, idx, weightnet, linear, bn, slope: float) -> torch.Tensor:
-    """[B,S,Cout] = act(bn(Linear(sum_k [feats[idx], rel_xyz] (x) WeightNet(rel_xyz)))) in ONE kernel."""
+    """[B,S,Cout] = act(bn(Linear(sum_k [feats[idx], rel_xyz] (x) WeightNet(rel_xyz)))) in ONE kernel.
+    The queries are processed in Morton order when the kNN that produced ``idx`` left one behind (same results;
+    spatially coherent tiles share their neighbours, so the gathers hit in L1)."""
     d = feats.shape[2]
     wp = _packed_weight(linear.weight, 1, d, 16)
     scale, shift = _fold_affine(linear.bias, bn)
-    return K.pointconv_fused(cand_xyz.contiguous(), query_xyz.contiguous(), feats.contiguous(), _as_i32(idx),
-                             _weightnet_host_params(weightnet.mlp_convs), wp, linear.out_features, scale, shift, slope)
+    query_xyz = query_xyz.contiguous()
+    return K.pointconv_fused(cand_xyz.contiguous(), query_xyz, feats.contiguous(), _as_i32(idx),
+                             _weightnet_host_params(weightnet.mlp_convs), wp, linear.out_features, scale, shift, slope,
+                             morton_order(query_xyz) if USE_MORTON_ORDER else None)
+
+
+USE_MORTON_ORDER = os.environ.get("KDPC_PC_ORDER", "1") != "0"
 
 
 def fused_costvol(xyz1, xyz2, p1, p2, idx, pos, slope_pre: float, conv, slope_post: float) -> torch.Tensor:

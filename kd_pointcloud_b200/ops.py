@@ -528,7 +528,7 @@ _register("linear_simt(Tensor x, Tensor w, Tensor? scale, Tensor? shift, float s
 
 # ------------------------------------------------------------------- fused tcgen05 layers
 def _pointconv_fused(cand_xyz, query_xyz, feats, idx, wn_params, wpacked, n_out: int, scale, shift,
-                     slope: float) -> torch.Tensor:
+                     slope: float, order=None) -> torch.Tensor:
     import ctypes
     _req(cand_xyz, torch.float32, 3, "xyz")
     _req(query_xyz, torch.float32, 3, "new_xyz")
@@ -537,17 +537,26 @@ def _pointconv_fused(cand_xyz, query_xyz, feats, idx, wn_params, wpacked, n_out:
     B, N, _ = cand_xyz.shape
     _, S, K = idx.shape
     D = feats.shape[2]
+    if tuple(query_xyz.shape[:2]) != (B, S) or tuple(feats.shape[:2]) != (B, N) or idx.shape[0] != B:
+        raise ValueError(f"kdpc: pointconv_fused shape mismatch: xyz {tuple(cand_xyz.shape)}, new_xyz {tuple(query_xyz.shape)}, "
+                         f"points {tuple(feats.shape)}, idx {tuple(idx.shape)}")
     if len(wn_params) != 248:
         raise ValueError("kdpc: pointconv_fused expects the 248 WeightNet(3,8,8,16) parameters")
     host = (ctypes.c_float * 248)(*wn_params)
+    order_stride = 0
+    if order is not None:          # int32 [B,S] rows of a (possibly wider) table: only the row stride may differ from S
+        if order.dtype != torch.int32 or order.dim() != 2 or tuple(order.shape) != (B, S) or order.stride(1) != 1 \
+                or order.device != feats.device or (B > 1 and order.stride(0) < S):
+            raise ValueError("kdpc: pointconv_fused order must be int32 [B,S] with contiguous rows on the same device")
+        order_stride = order.stride(0) if B > 1 else S
     with _guard(feats):
         out = torch.empty((B, S, n_out), dtype=torch.float32, device=feats.device)
         nws = _lib.lib().kdpc_pointconv_fused_ws_bytes(B, S, K, D, n_out)
         ws = torch.empty((nws,), dtype=torch.uint8, device=feats.device) if nws else None
         if out.numel():
-            _call("kdpc_pointconv_fused", B, N, S, K, D, n_out, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx),
-                  ctypes.cast(host, ctypes.c_void_p), _p(wpacked), _p(scale), _p(shift), float(slope), _p(ws), _p(out),
-                  _stream())
+            _call("kdpc_pointconv_fused_ordered", B, N, S, K, D, n_out, _p(cand_xyz), _p(query_xyz), _p(feats), _p(idx),
+                  ctypes.cast(host, ctypes.c_void_p), _p(wpacked), _p(scale), _p(shift), float(slope),
+                  None if order is None else order.data_ptr(), order_stride, _p(ws), _p(out), _stream())
     return out
 
 
@@ -572,8 +581,9 @@ def _costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, slope_pre: float, wpac
 
 
 _register("pointconv_fused(Tensor cand_xyz, Tensor query_xyz, Tensor feats, Tensor idx, float[] wn_params, "
-          "Tensor wpacked, int n_out, Tensor? scale, Tensor? shift, float slope) -> Tensor", _pointconv_fused,
-          lambda c, q, f, idx, wn, wp, n, sc, sh, sl: f.new_empty((idx.shape[0], idx.shape[1], n)))
+          "Tensor wpacked, int n_out, Tensor? scale, Tensor? shift, float slope, Tensor? order=None) -> Tensor",
+          _pointconv_fused,
+          lambda c, q, f, idx, wn, wp, n, sc, sh, sl, order=None: f.new_empty((idx.shape[0], idx.shape[1], n)))
 _register("costvol_fused(Tensor xyz1, Tensor xyz2, Tensor p1, Tensor p2, Tensor idx, Tensor pos_w, Tensor pos_b, "
           "float slope_pre, Tensor wpacked, int n_out, Tensor? bias, float slope_post) -> Tensor", _costvol_fused,
           lambda x1, x2, p1, p2, idx, pw, pb, s0, wp, n, b, s1: p1.new_empty((p1.shape[0], p1.shape[1], n)))

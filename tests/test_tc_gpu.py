@@ -137,6 +137,16 @@ def test_pointconv_fused_matches_fp64(B, N, S, D, Cout, KN):
     assert y.shape == (B, S, Cout)
     assert _err(y, ref) < 2e-5
     assert torch.equal(y, K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, scale, shift, 0.1))
+    # any per-cloud row order gives the same bits (rows are independent): a random permutation with a wider row
+    # stride, and the Morton order the kNN leaves in the sort cache (what PointConv.forward passes)
+    table = torch.stack([torch.randperm(S, device=DEV) for _ in range(B)]).int()
+    wide = torch.cat([table, torch.full((B, 5), -1, dtype=torch.int32, device=DEV)], 1)
+    assert torch.equal(y, K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, scale, shift, 0.1, wide[:, :S]))
+    if KF.ops.SORT_MIN_N <= N:
+        KF._knn_compute(KN, cand, query)
+        mo = KF.morton_order(query)
+        assert mo is not None and torch.equal(mo.sort(dim=1).values, torch.arange(S, device=DEV).int().expand(B, S))
+        assert torch.equal(y, K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, scale, shift, 0.1, mo))
 
 
 @pytest.mark.parametrize("B,N1,N2,D", [(2, 1024, 1024, 32), (1, 333, 500, 64), (2, 256, 256, 256), (1, 8192, 8192, 32),
