@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Top stall sites of an .ncu-rep (source page): tools/ncu_hot.py REP [N]"""
+"""Top stall sites of an .ncu-rep (source page): tools/ncu_hot.py REP [N] [extra ncu import filters, e.g. -s 7 -c 1]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sys.argv[3:], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]

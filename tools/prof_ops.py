@@ -32,13 +32,13 @@ for _ in range(2):
     if "pointconv" in what:
         from kd_pointcloud_b200 import pointconv_util as P
         D, Cout = 128, 128
-        idx9 = K.knn(xyz, xyz, 9)
+        idx9 = KF._knn_compute(9, xyz, xyz)            # (leaves the Morton order in the sort cache)
         feats = torch.randn(8, 8192, D, device=dev)
         wn = P.WeightNet(3, 16).to(dev)
         lin = torch.nn.Linear(16 * (D + 3), Cout).to(dev)
         wp = K.pack_weight(lin.weight.detach(), 1, D, 16)
         params = KF._weightnet_host_params(wn.mlp_convs)
-        K.pointconv_fused(xyz, xyz, feats, idx9, params, wp, Cout, None, lin.bias.detach(), 0.1)
+        K.pointconv_fused(xyz, xyz, feats, idx9, params, wp, Cout, None, lin.bias.detach(), 0.1, KF.morton_order(xyz))
     if "linear" in what:
         x = torch.randn(65536, 2096, device=dev)
         w = torch.randn(128, 2096, device=dev)
