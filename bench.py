@@ -357,8 +357,10 @@ def run_kdpc(args):
                                    "8192-pt pairs, seeded synthetic weights", "npoints": NPOINTS, "pairs_per_gpu_per_step": B,
                        "global_pairs_per_step": B * world, "sharding": "batch-sharded, no collectives",
                        "cuda_graph": bool(graphed), "l2": "256 MB flush between timed iterations",
-                       "epe3d_last_step": epe_last},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                       "epe3d_last_step": epe_last,
+                       "metrics_last_step": dict(zip(("EPE3D", "ACC3DS", "ACC3DR", "Outliers3D", "EPE2D", "ACC2D"),
+                                                     [round(float(v), 6) for v in runner.out_metrics.tolist()]))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24},
             "gpu_launches": int(launches),
             "clocks": clocks,
             # dominant kernel of the step (profiles/: 8 launches, largest single share): the fused PointConv

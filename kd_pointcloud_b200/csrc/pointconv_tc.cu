@@ -36,7 +36,10 @@ namespace tc {
 //     issuing warp for ~150 cycles, and the 74 KB of staging take the L1 away;
 //   * software pipelining (chunk c+1's loads issued after chunk c's FFMAs, stage acquired after the FFMAs): 5 %
 //     slower, the extra live registers spill in the WeightNet phase;
-//   * prefetch.global.L1 of every neighbour row's next 128-byte line two to six chunks ahead: 5 % slower.
+//   * prefetch.global.L1 of every neighbour row's next 128-byte line two to six chunks ahead: 5 % slower;
+//   * 4 threads per row (16 producer warps at 96 registers, wn[9][4] each) for more latency hiding: 15 % slower - the
+//     kernel is bound by L1 line accesses (every warp request touches 16 neighbour rows = 16 wavefronts, 1152 per
+//     chunk) and by issue slots, not by exposed latency; the redundant hidden-layer work and 8-byte stores cost more.
 template <int KN, int NPASS>
 struct PointConvProducer {
     static constexpr int kWarps = 8, kGroups = 1;

@@ -698,3 +698,39 @@ _register("scatter_rows_csr(Tensor g, Tensor? wgt, Tensor offsets, Tensor perm, 
           _scatter_rows_csr, lambda g, w, o, p, n, gdiv: g.new_empty((o.shape[0], n, g.shape[-1])))
 
 kdpc = torch.ops.kdpc
+
+
+# ------------------------------------------------------------------------------------ evaluation metrics (8f-2)
+_METRIC_WS = {}
+
+
+def _flow_metrics(pred: torch.Tensor, gt: torch.Tensor, pc1, calib, point_major: bool) -> torch.Tensor:
+    """float32 [6] on the device: EPE3D, Acc3DS, Acc3DR, Outliers3D, EPE2D, Acc2D of one batch (include/kdpc.h)."""
+    _req(pred, torch.float32, 3, "pred_flow")
+    _req(gt, torch.float32, 3, "gt_flow")
+    B, N, C = gt.shape
+    if C != 3 or tuple(pred.shape) != ((B, N, 3) if point_major else (B, 3, N)):
+        raise ValueError("kdpc: flow_metrics expects gt [B,N,3] and pred [B,3,N] (or [B,N,3] when point_major)")
+    if pc1 is not None:
+        _req(pc1, torch.float32, 3, "pc1")
+        if tuple(pc1.shape) != (B, N, 3):
+            raise ValueError("kdpc: flow_metrics pc1 must be [B,N,3]")
+    if calib is not None:
+        _req(calib, torch.float32, 2, "calib")
+        if tuple(calib.shape) != (B, 6):
+            raise ValueError("kdpc: flow_metrics calib must be [B,6] (f, cx, cy, constx, consty, constz)")
+    dev = gt.device
+    with _guard(gt):
+        ws = _METRIC_WS.get(dev)
+        if ws is None:
+            ws = _METRIC_WS[dev] = torch.zeros(((_lib.lib().kdpc_flow_metrics_workspace_bytes() + 7) // 8,),
+                                               dtype=torch.int64, device=dev)
+        out = torch.zeros((6,), dtype=torch.float32, device=dev)
+        if B * N > 0:
+            _call("kdpc_flow_metrics", B, N, 1 if point_major else 0, _p(pred), _p(gt), _p(pc1), _p(calib), _p(ws), _p(out),
+                  _stream())
+    return out
+
+
+_register("flow_metrics(Tensor pred, Tensor gt, Tensor? pc1, Tensor? calib, bool point_major) -> Tensor", _flow_metrics,
+          lambda pred, gt, pc1, calib, pm: gt.new_empty((6,)))

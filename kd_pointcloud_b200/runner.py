@@ -16,7 +16,7 @@ import torch
 
 from . import functional as KF
 from . import ops
-from .losses import epe3d
+from .evaluation_utils import scene_flow_metrics
 
 KEYS = ("pos1", "pos2", "color1", "color2", "flow")
 
@@ -29,9 +29,10 @@ class FlowRunner:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out_flow: Optional[torch.Tensor] = None
         self.out_epe: Optional[torch.Tensor] = None
+        self.out_metrics: Optional[torch.Tensor] = None    # EPE3D, Acc3DS, Acc3DR, Outliers3D, EPE2D, Acc2D (device)
         self.launches_per_step = 0
         self.use_graph = use_graph
-        self._epe_host = torch.zeros(1, pin_memory=True)
+        self._metrics_host = torch.zeros(6, pin_memory=True)
 
     def _forward(self):
         KF.clear_caches()                                  # never reuse indices across batches
@@ -39,7 +40,9 @@ class FlowRunner:
         with torch.no_grad():
             flows = self.model(s["pos1"], s["pos2"], s["color1"], s["color2"])[0]
             self.out_flow = flows[0]
-            self.out_epe = epe3d(flows[0], s["flow"]).reshape(1)
+            # evaluate_bid_pointconv.py:121-145 in one kernel (csrc/metrics.cu): EPE3D is element 0
+            self.out_metrics = scene_flow_metrics(s["pos1"], flows[0], s["flow"])
+            self.out_epe = self.out_metrics[:1]
         KF.clear_caches()
 
     def warmup_and_capture(self, sample: Dict[str, torch.Tensor], warmup: int = 2) -> bool:
@@ -85,6 +88,6 @@ class FlowRunner:
         """End-to-end: pinned host batch -> EPE3D as a Python float (H2D + forward + D2H)."""
         self.load(host_batch)
         self.step()
-        self._epe_host.copy_(self.out_epe, non_blocking=True)
+        self._metrics_host.copy_(self.out_metrics, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return float(self._epe_host[0])
+        return float(self._metrics_host[0])
