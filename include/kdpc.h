@@ -238,6 +238,20 @@ int kdpc_flow_loss(int b, int nscales, int point_major, const int *n, const floa
 int kdpc_hint_loss(long long n, const float *fs, const float *ft, float weight, float *grad_fs, void *ws,
                    float *loss, kdpc_stream_t stream);
 
+/* ---- evaluation metrics ------------------------------------------------ */
+
+/* evaluate_3d + evaluate_2d (evaluation_utils.py:17-50) over one batch, with the 2-D flows of
+ * geometry.get_batch_2d_flow(pc1, pc1+gt, pc1+pred) / project_3d_to_2d (utils/geometry.py:6-65) computed on the fly.
+ * pred: [B,3,N] (point_major = 0, the model's output layout) or [B,N,3] (1); gt, pc1: [B,N,3]; calib: NULL
+ * (FlyingThings3D intrinsics f=-1050, cx=479.5, cy=269.5) or [B,6] = f, cx, cy, constx, consty, constz per sample
+ * (KITTI P_rect_02, geometry.py:25-38); pc1 may be NULL (no 2-D metrics).  out: 6 floats on the device = EPE3D,
+ * Acc3DS, Acc3DR, Outliers3D, EPE2D, Acc2D (batch means, as the reference's per-batch AverageMeter updates).
+ * Per-point arithmetic is the reference's float32 sequence with IEEE rounding, so the accuracy counts are exact;
+ * deterministic.  ws: kdpc_flow_metrics_workspace_bytes() bytes, 8-byte aligned, zeroed ONCE before first use. */
+long long kdpc_flow_metrics_workspace_bytes(void);
+int kdpc_flow_metrics(int b, int n, int point_major, const float *pred, const float *gt, const float *pc1,
+                      const float *calib, void *ws, float *out, kdpc_stream_t stream);
+
 /* ---- deterministic backward plumbing ------------------------------------------------- */
 
 /* Inverse of an index list: idx int32 [B,M] with values in [0,N)  ->  offsets int32 [B,N+1] and

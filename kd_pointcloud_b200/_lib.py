@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("KDPC_LIB") or os.path.join(_HERE, "libkdpc.so")   # KDPC_LIB: an experiment build (A/B measurements)
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu"]
+           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 LINK_FLAGS = ARCH_FLAGS + ["-shared"]
@@ -72,6 +72,7 @@ _SIGNATURES = {
                                      _P, _P, _P],
     "kdpc_spatial_sort_order_offset": [c_int],
     "kdpc_spatial_sort_order_stride": [c_int],
+    "kdpc_flow_metrics": [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_fps": [c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_gather": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_gather_grad": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
@@ -133,6 +134,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_linear_tc_ws_bytes.argtypes = [c_longlong, c_int, c_int]
         L.kdpc_pointconv_fused_ws_bytes.restype = c_longlong
         L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+        L.kdpc_flow_metrics_workspace_bytes.restype = c_longlong
+        L.kdpc_flow_metrics_workspace_bytes.argtypes = []
         L.kdpc_costvol_fused_ws_bytes.restype = c_longlong
         L.kdpc_costvol_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
         L.kdpc_loss_workspace_bytes.restype = c_longlong
@@ -161,7 +164,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages",
+            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 
