@@ -131,16 +131,42 @@ struct CostVolAsyncProducer {
     static __device__ __forceinline__ void prologue(const Args &, int, int) {}
     const Args &a;
     const GemmShape &g;
-    int idx_pref;                                            // neighbour index of this thread's row in the NEXT issued tile
+    // Gather issue mapping: 8 consecutive lanes copy the (up to two) 128-byte halves of ONE neighbour row's chunk slice,
+    // 16 bytes each, so a warp-level LDGSTS touches 4 lines; thread t serves rows (t >> 3) + 32 j, j = 0..3.  (With one
+    // thread per row copying its row's pieces one after the other every request touched 32 lines and the load/store
+    // unit needed ~1350 of the 2650 cycles of a pipeline iteration just to accept them - tools/trace_costvol.py.)
+    // All per-row address arithmetic happens once per tile, one iteration ahead (load_rows): the issue itself is an
+    // add and a predicated LDGSTS per row.
+    int nbr[4];                   // neighbour index of tile row (t >> 3) + 32 j in the NEXT issued tile (loaded one iteration ahead,
+                                  // first used at that issue: the load latency never stalls the issuing warp)
+    uint32_t cloud_off[4];        // (cloud of that row) * n
+    uint32_t pt_off;              // element offset into p1q of the point row this thread copies a piece of (threads >= 128)
+    uint32_t dst0;                // byte offset of this thread's piece inside a raw staging buffer (row j = 0)
 
-    __device__ CostVolAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_), idx_pref(0) {}
+    __device__ CostVolAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
 
-    // rows < 2^31 (checked on the host): all index arithmetic in 32 bits
+    // rows < 2^31, p1q / p2q elements < 2^32 (checked on the host): all index arithmetic in 32 bits
     __device__ __forceinline__ unsigned row_of(int tile, int r) const {
         const unsigned row = (unsigned)tile * TILE_M + (unsigned)r;
         return row < (unsigned)g.m ? row : (unsigned)g.m - 1u;   // padded rows repeat the last row; never stored
     }
-    __device__ __forceinline__ void prime(int tile, int ptid) { idx_pref = __ldg(a.idx + row_of(tile, ptid & 127)); }
+    __device__ __forceinline__ void load_rows(int tile, int ptid) {
+        const unsigned s = (unsigned)a.s, pt0 = (unsigned)tile * (TILE_M / CV_K);
+        const unsigned b0 = pt0 / s, left = (b0 + 1u) * s - pt0;  // points of the tile before the next cloud starts
+        const unsigned last_pt = (unsigned)(g.m >> 5) - 1u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                             // tile row (t >> 3) + 32 j belongs to point pt0 + j
+            const unsigned b = b0 + ((unsigned)j >= left ? ((unsigned)j - left) / s + 1u : 0u);
+            nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + 32 * j));
+            cloud_off[j] = b * (unsigned)a.n;
+        }
+        const unsigned pt = min(pt0 + (unsigned)((ptid >> 5) & 3), last_pt);
+        pt_off = pt * (unsigned)a.d;
+    }
+    __device__ __forceinline__ void prime(int tile, int ptid) {
+        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + (ptid & 7) * 16);
+        load_rows(tile, ptid);
+    }
 
     // channels [c0, c0 + 64) of a chunk are split between the two half-threads of a row: units of 8 channels,
     // half 0 takes the first ceil(units/2)
@@ -151,28 +177,25 @@ struct CostVolAsyncProducer {
         nu = half ? units - first : first;
     }
 
-    __device__ __forceinline__ void issue(int tile, int chunk, int next_tile, unsigned char *raw, uint64_t *bar, int ptid) {
-        const int r = ptid & 127, half = ptid >> 7, k = r & 31;
-        const unsigned row = row_of(tile, r);
-        const unsigned pt = row >> 5, b = pt / (unsigned)a.s;
-        const int j = idx_pref;
-        if (next_tile >= 0) idx_pref = __ldg(a.idx + row_of(next_tile, r));       // consumed by the next issue
+    __device__ __forceinline__ void issue(int /*tile*/, int chunk, int next_tile, unsigned char *raw, uint64_t *bar, int ptid) {
+        const int q = ptid & 7;
         const int c0 = chunk * CHUNK_K;
-        int u0, nu;
-        split_units(chunk, half, u0, nu);
-        {   // this half-thread's channels of the gathered row: two 16-byte pieces per unit
-            const float *src = a.p2q + ((size_t)b * a.n + j) * (size_t)a.d + c0 + u0 * 8;
-            const uint32_t dst = smem_u32(raw + r * ROW_PITCH + u0 * 32);
+        const int ppr = min(CHUNK_K, a.d - c0) >> 2;             // 16-byte pieces per row in this chunk (d % 8 == 0)
+        const uint32_t dst = smem_u32(raw) + dst0;
+        const float *src = a.p2q + c0 + q * 4;
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (e < 2 * nu) cp_async_16(dst + e * 16, src + e * 4);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t row_off = (cloud_off[j] + (uint32_t)nbr[j]) * (uint32_t)a.d;
+            if (q < ppr) cp_async_16(dst + j * (32 * ROW_PITCH), src + row_off);
+            if (q + 8 < ppr) cp_async_16(dst + j * (32 * ROW_PITCH) + 128, src + row_off + 32);
         }
-        if (half == 1) {                                         // the point's own row, spread over its 32 neighbour rows
-            const int pieces = min(CHUNK_K, a.d - c0) >> 2;
-            if (k < pieces)
-                cp_async_16(smem_u32(raw + (TILE_M + (r >> 5)) * ROW_PITCH) + k * 16, a.p1q + (size_t)pt * a.d + c0 + k * 4);
+        if (ptid >= TILE_M) {                                    // the 4 points' own rows, one 16-byte piece per lane
+            const int k = ptid & 31;
+            if (k < ppr)
+                cp_async_16(smem_u32(raw + (TILE_M + ((ptid >> 5) & 3)) * ROW_PITCH) + k * 16, a.p1q + pt_off + c0 + k * 4);
         }
         cp_async_mbar_arrive(bar);                               // arrives once this thread's copies have landed
+        if (next_tile >= 0) load_rows(next_tile, ptid);          // consumed by the next issue
     }
 
     __device__ __forceinline__ void convert(int tile, int chunk, const unsigned char *raw, unsigned char *a_hi,
@@ -258,12 +281,24 @@ struct MaxKEpilogue {
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
             tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // lane = neighbour k, v[j] = channel c0+j
-            int mine = 0;
+            // max over the 32 lanes (neighbours) of every column, lane j ending up with column j: recursive halving -
+            // at distance 16, 8, .. 1 every lane keeps the half of its columns that matches its lane bit and trades the
+            // other half with its partner: 31 SHFL + 31 integer max.  (32 x redux.sync.max was ~1800 cycles per tile:
+            // the REDUX results come back through the uniform datapath one at a time, ~56 cycles each.)
+            int w[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int m = __reduce_max_sync(0xffffffffu, f2ord(v[j]));
-                if (lane == j) mine = m;
+            for (int j = 0; j < 32; ++j) w[j] = f2ord(v[j]);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                const bool up = (lane & m) != 0;
+#pragma unroll
+                for (int j = 0; j < m; ++j) {
+                    const int keep = up ? w[j + m] : w[j];
+                    const int give = up ? w[j] : w[j + m];
+                    w[j] = max(keep, __shfl_xor_sync(0xffffffffu, give, m));
+                }
             }
+            const int mine = w[0];
             const int col = c0 + lane;
             if (pt < e.points && col < g.n) {
                 float y = ord2f(mine);
@@ -292,7 +327,8 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
                                 float slope_post, void *ws, float *out, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(xyz1 && xyz2 && p1 && p2 && idx && pos_w && pos_b && wpacked && out && b > 0 && s > 0 && n > 0 &&
                     d > 0 && d_out > 0);
-    if (k != CV_K || d > CV_MAX_D || (d & 7) != 0 || d_out > 256 || (long long)b * s * CV_K >= (1ll << 31)) return KDPC_EUNSUPPORTED;
+    if (k != CV_K || d > CV_MAX_D || (d & 7) != 0 || d_out > 256 || (long long)b * s * CV_K >= (1ll << 31) ||
+        (long long)b * n * d >= (1ll << 32) || (long long)b * s * d >= (1ll << 32)) return KDPC_EUNSUPPORTED;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(wpacked) |
                          reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(pos_b);
     if (al % 16 != 0) return KDPC_EINVAL;

@@ -93,6 +93,11 @@ using namespace kdpc::tc;
 static int g_tc_async = 1;
 KDPC_API int kdpc_tc_async_enabled(void) { return g_tc_async; }
 KDPC_API void kdpc_tc_set_async(int on) { g_tc_async = on; }
+static void *g_tc_trace = nullptr;
+KDPC_API void *kdpc_tc_trace_buffer(void) { return g_tc_trace; }
+/* debug (tools/trace_*.py): every tcgen05 kernel launched while a buffer is set writes CTA 0's per-iteration clock64
+ * stamps into it (200 x 16 int64, device memory); NULL = off */
+KDPC_API void kdpc_tc_set_trace(void *p) { g_tc_trace = p; }
 
 KDPC_API long long kdpc_packed_weight_bytes(int n, int k_packed) {
     const int n_pad = (n + 15) / 16 * 16;

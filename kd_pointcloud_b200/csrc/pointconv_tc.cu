@@ -220,7 +220,6 @@ struct PointConvProducer {
 };
 
 static int kdpc_pointconv_stages = 2;
-static long long *kdpc_pointconv_trace = nullptr;
 
 template <int KN, int NPASS>
 static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS>::Args &pa, const void *wpacked,
@@ -231,7 +230,6 @@ static int launch_pointconv(long long m, int n_out, const typename PointConvProd
     g.chunks_per_split = g.num_chunks;
     if (ws != nullptr) plan_split_k(g);
     ea.partial = reinterpret_cast<float *>(ws);
-    g.trace = kdpc_pointconv_trace;
     // the neighbour gathers live on L1 hits (8 consecutive K-chunks share a 128-byte line): two operand stages are
     // enough to keep the MMA fed and leave ~80 KB of the unified L1/shared array to the cache
     if (g.stages > kdpc_pointconv_stages) g.stages = kdpc_pointconv_stages;
@@ -260,8 +258,6 @@ using namespace kdpc;
 using namespace kdpc::tc;
 
 KDPC_API void kdpc_pointconv_set_stages(int n) { kdpc::tc::kdpc_pointconv_stages = n < 2 ? 2 : n; }
-/* debug: device buffer of 200 x 16 int64 receiving CTA 0's per-chunk clock64 stamps (tools/trace_pointconv.py); NULL = off */
-KDPC_API void kdpc_pointconv_set_trace(void *p) { kdpc::tc::kdpc_pointconv_trace = reinterpret_cast<long long *>(p); }
 
 KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out) {
     if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;

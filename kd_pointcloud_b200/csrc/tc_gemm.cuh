@@ -17,6 +17,8 @@
 
 // A/B switch (kdpc_tc_set_async): 0 = synchronous register-staged producers everywhere
 extern "C" int kdpc_tc_async_enabled(void);
+// debug: device buffer of 200 x 16 int64 receiving CTA 0's per-iteration clock64 stamps (kdpc_tc_set_trace); NULL = off
+extern "C" void *kdpc_tc_trace_buffer(void);
 
 namespace kdpc {
 namespace tc {
@@ -91,7 +93,7 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.stages = pick_stages(g.n_pad, raw_bytes * raw_stages);
     g.num_tiles = (m + TILE_M - 1) / TILE_M;
     g.wpacked = reinterpret_cast<const unsigned char *>(wpacked);
-    g.trace = nullptr;
+    g.trace = reinterpret_cast<long long *>(kdpc_tc_trace_buffer());
     return g;
 }
 
@@ -198,21 +200,33 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 if (issued < total) issue_next();
             int s = 0, cu_slot = 0;
             uint32_t ph = 0, raw_ph = 0;
+            const bool b_resident = g.wchunks == 1;               // one weight chunk: each stage's copy is loaded once
+            auto stamp = [&](int i, int ev) {                     // debug trace of CTA 0 (kdpc_tc_set_trace)
+                if (g.trace != nullptr && blockIdx.x == 0 && tid == 0 && i < 200) g.trace[i * 16 + ev] = clock64();
+            };
             for (int i = 0; i < total; ++i) {
-                fence_async_smem();                               // my generic reads of the slot about to be refilled
-                asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");   // every producer finished converting i-1
+                stamp(i, 0);
+                // every producer finished converting i-1: its raw slot may be refilled.  (Reads and cp.async writes are
+                // both generic-proxy accesses: the barrier orders them, no proxy fence is needed here.)
+                asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
+                stamp(i, 1);
                 if (issued < total) issue_next();
+                stamp(i, 2);
                 mbar_wait(&empty[s], ph ^ 1);
-                if (ptid == 0) {
+                stamp(i, 3);
+                if (ptid == 0 && (!b_resident || i < g.stages)) {
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(b_resident ? 0 : cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
                 }
                 mbar_wait(&raw_full[cu_slot], raw_ph);
+                stamp(i, 4);
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
                 prod.convert(cu_tile, cu_chunk, raw_base + (size_t)cu_slot * g.raw_bytes, a_hi, a_hi + A_PART_BYTES, ptid);
+                stamp(i, 5);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_a[s]);
+                stamp(i, 6);
                 step(cu_tile, cu_chunk);
                 if (++s == g.stages) { s = 0; ph ^= 1; }
                 if (++cu_slot == RAW) { cu_slot = 0; raw_ph ^= 1; }
@@ -314,7 +328,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 if (trm) g.trace[it * 16 + 8] = clock64();
                 mbar_wait(&full_a[s], ph);
                 if (trm) g.trace[it * 16 + 9] = clock64();
-                mbar_wait(&full_b[s], ph);
+                if (!(Producer::kAsync && g.wchunks == 1 && it >= (uint32_t)g.stages)) mbar_wait(&full_b[s], ph);   // (resident weights)
                 if (trm) g.trace[it * 16 + 10] = clock64();
                 fence_after_sync();
                 {
@@ -365,13 +379,17 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
             const long long tile = w / g.splits;
             const uint32_t acc = tcount & 1;
+            const bool tre = g.trace != nullptr && blockIdx.x == 0 && quarter == 1 && lane == 0 && tcount < 200;
+            if (tre) g.trace[tcount * 16 + 12] = clock64();
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            if (tre) g.trace[tcount * 16 + 13] = clock64();
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
             epi.tile(ea, g, tile, (int)(w - tile * g.splits), t_acc, quarter, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (tre) g.trace[tcount * 16 + 14] = clock64();
         }
     }
 

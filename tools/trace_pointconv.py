@@ -19,13 +19,13 @@ wp = K.pack_weight(lin.weight.detach(), 1, D, 16)
 params = KF._weightnet_host_params(wn.mlp_convs)
 L = _lib.lib()
 import ctypes
-L.kdpc_pointconv_set_trace.restype = None
-L.kdpc_pointconv_set_trace.argtypes = [ctypes.c_void_p]
+L.kdpc_tc_set_trace.restype = None
+L.kdpc_tc_set_trace.argtypes = [ctypes.c_void_p]
 tr = torch.zeros(200 * 16, dtype=torch.int64, device=dev)
-L.kdpc_pointconv_set_trace(tr.data_ptr())
+L.kdpc_tc_set_trace(tr.data_ptr())
 y = K.pointconv_fused(cand, cand, feats, idx, params, wp, Cout, None, lin.bias.detach(), 0.1)
 torch.cuda.synchronize()
-L.kdpc_pointconv_set_trace(None)
+L.kdpc_tc_set_trace(None)
 t = tr.cpu().view(200, 16)
 t0 = int(t[0, 0])
 print("it | w0: acq_start acquired filled arrived | w7: same | mma: wait_start full_a full_b issued  (cycles from start)")
