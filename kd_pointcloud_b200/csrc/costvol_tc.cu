@@ -131,6 +131,8 @@ struct CostVolAsyncProducer {
     static __device__ __forceinline__ void prologue(const Args &, int, int) {}
     const Args &a;
     const GemmShape &g;
+    // (Measured and rejected: L1-allocating cp.async.ca with the queries in Morton order - no gain; the cost is per
+    // LDGSTS instruction, ~28 cycles of load/store-unit time each, whatever the hit rate.)
     // Gather issue mapping: 8 consecutive lanes copy the (up to two) 128-byte halves of ONE neighbour row's chunk slice,
     // 16 bytes each, so a warp-level LDGSTS touches 4 lines; thread t serves rows (t >> 3) + 32 j, j = 0..3.  (With one
     // thread per row copying its row's pieces one after the other every request touched 32 lines and the load/store
