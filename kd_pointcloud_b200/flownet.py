@@ -158,37 +158,41 @@ class PointConvBidirection(nn.Module):
         feat1_l3, feat2_l3 = h(f_l3)
 
         # ---- l3 -------------------------------------------------------------------------------
-        c_feat1_l3, c_feat2_l3 = h(cat_c(f_l3, f_l4_3))
-        feat1_new_l3, feat2_new_l3, cross3 = self.cross3.forward_pm(pc1_l3, pc2_l3, c_feat1_l3, c_feat2_l3)
+        c_feat_l3 = cat_c(f_l3, f_l4_3)
+        c_feat1_l3, c_feat2_l3 = h(c_feat_l3)
+        feat1_new_l3, feat2_new_l3, cross3 = self.cross3.forward_pm(pc1_l3, pc2_l3, c_feat1_l3, c_feat2_l3, c_feat_l3)
         feat3, flow3 = self.flow3.forward_pm(pc1_l3, feat1_l3, cross3)
 
         f_l3_2 = self.deconv3_2.forward_pm(up(pc_l2, pc_l3, both(feat1_new_l3, feat2_new_l3), idx=up32))
-        c_feat1_l2, c_feat2_l2 = h(cat_c(f_l2, f_l3_2))
+        c_feat_l2 = cat_c(f_l2, f_l3_2)
+        c_feat1_l2, c_feat2_l2 = h(c_feat_l2)
 
         # ---- l2 -------------------------------------------------------------------------------
         up_flow2 = up(pc1_l2, pc1_l3, self.scale * flow3, idx=up32[:B])
         pc2_l2_warp = self.warping.forward_pm(pc1_l2, pc2_l2, up_flow2)
-        feat1_new_l2, feat2_new_l2, cross2 = self.cross2.forward_pm(pc1_l2, pc2_l2_warp, c_feat1_l2, c_feat2_l2)
+        feat1_new_l2, feat2_new_l2, cross2 = self.cross2.forward_pm(pc1_l2, pc2_l2_warp, c_feat1_l2, c_feat2_l2, c_feat_l2)
         feat3_up = up(pc1_l2, pc1_l3, feat3, idx=up32[:B])
         feat2, flow2 = self.flow2.forward_pm(pc1_l2, cat_c(feat1_l2, feat3_up), cross2, up_flow2)
 
         f_l2_1 = self.deconv2_1.forward_pm(up(pc_l1, pc_l2, both(feat1_new_l2, feat2_new_l2), idx=up21))
-        c_feat1_l1, c_feat2_l1 = h(cat_c(f_l1, f_l2_1))
+        c_feat_l1 = cat_c(f_l1, f_l2_1)
+        c_feat1_l1, c_feat2_l1 = h(c_feat_l1)
 
         # ---- l1 -------------------------------------------------------------------------------
         up_flow1 = up(pc1_l1, pc1_l2, self.scale * flow2, idx=up21[:B])
         pc2_l1_warp = self.warping.forward_pm(pc1_l1, pc2_l1, up_flow1)
-        feat1_new_l1, feat2_new_l1, cross1 = self.cross1.forward_pm(pc1_l1, pc2_l1_warp, c_feat1_l1, c_feat2_l1)
+        feat1_new_l1, feat2_new_l1, cross1 = self.cross1.forward_pm(pc1_l1, pc2_l1_warp, c_feat1_l1, c_feat2_l1, c_feat_l1)
         feat2_up = up(pc1_l1, pc1_l2, feat2, idx=up21[:B])
         feat1, flow1 = self.flow1.forward_pm(pc1_l1, cat_c(feat1_l1, feat2_up), cross1, up_flow1)
 
         f_l1_0 = self.deconv1_0.forward_pm(up(pc_l0, pc_l1, both(feat1_new_l1, feat2_new_l1), idx=up10))
-        c_feat1_l0, c_feat2_l0 = h(cat_c(f_l0, f_l1_0))
+        c_feat_l0 = cat_c(f_l0, f_l1_0)
+        c_feat1_l0, c_feat2_l0 = h(c_feat_l0)
 
         # ---- l0 -------------------------------------------------------------------------------
         up_flow0 = up(pc1_l0, pc1_l1, self.scale * flow1, idx=up10[:B])
         pc2_l0_warp = self.warping.forward_pm(pc1_l0, pc2_l0, up_flow0)
-        _, _, cross0 = self.cross0.forward_pm(pc1_l0, pc2_l0_warp, c_feat1_l0, c_feat2_l0)
+        _, _, cross0 = self.cross0.forward_pm(pc1_l0, pc2_l0_warp, c_feat1_l0, c_feat2_l0, c_feat_l0)
         feat1_up = up(pc1_l0, pc1_l1, feat1, idx=up10[:B])
         _, flow0 = self.flow0.forward_pm(pc1_l0, cat_c(feat1_l0, feat1_up), cross0, up_flow0)
 

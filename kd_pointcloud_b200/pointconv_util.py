@@ -326,11 +326,18 @@ class CrossLayerLight(nn.Module):
         """Reference signature (pointconv_util.py:1826): channel-major in, [B,D',N1] out."""
         return cm(self.cross_pm(pm(xyz1), pm(xyz2), pm(points1), pm(points2), pos, mlp, bn))
 
-    def forward_pm(self, pc1, pc2, feat1, feat2):
-        a = self.cross_pm(pc1, pc2, _linear_pm(self.cross_t11, feat1), _linear_pm(self.cross_t22, feat2),
-                          self.pos1, self.mlp1, self.bn1)
-        b = self.cross_pm(pc2, pc1, _linear_pm(self.cross_t11, feat2), _linear_pm(self.cross_t22, feat1),
-                          self.pos1, self.mlp1, self.bn1)
+    def forward_pm(self, pc1, pc2, feat1, feat2, feat_both=None):
+        """``feat_both``: optionally the [2B,N,C] tensor whose halves are feat1 and feat2 (the encoder keeps both clouds
+        in one batch): cross_t11 / cross_t22 then run once over 2B clouds instead of once per cloud (same values)."""
+        if feat_both is not None and feat_both.shape[0] == 2 * feat1.shape[0] and feat1.shape == feat2.shape:
+            B = feat1.shape[0]
+            t11, t22 = _linear_pm(self.cross_t11, feat_both), _linear_pm(self.cross_t22, feat_both)
+            t11_1, t11_2, t22_1, t22_2 = t11[:B], t11[B:], t22[:B], t22[B:]
+        else:
+            t11_1, t22_2 = _linear_pm(self.cross_t11, feat1), _linear_pm(self.cross_t22, feat2)
+            t11_2, t22_1 = _linear_pm(self.cross_t11, feat2), _linear_pm(self.cross_t22, feat1)
+        a = self.cross_pm(pc1, pc2, t11_1, t22_2, self.pos1, self.mlp1, self.bn1)
+        b = self.cross_pm(pc2, pc1, t11_2, t22_1, self.pos1, self.mlp1, self.bn1)
         if self.mlp2 is False:
             return a, b
         a = _linear_pm(self.cross_t1, a)
