@@ -26,7 +26,9 @@ from .pointconv_util import (Conv1d, CrossLayerLight, PointConvD, PointWarping, 
 
 scale = 1.0
 OVERLAP_SAMPLING = False     # opt-in: measured 11 % SLOWER on B200 - the cluster FPS wants all its SMs at once and the
-                             # persistent tcgen05 kernels of the main stream hold every SM (results are identical)
+                             # persistent tcgen05 kernels of the main stream hold every SM (results are identical);
+                             # with those grids capped to the 84 SMs the FPS clusters leave free it is 15 % slower:
+                             # the co-resident kNN warps stretch the FPS latency chain
 _SIDE_STREAMS = {}
 
 
