@@ -158,7 +158,8 @@ struct CostVolAsyncProducer {
         const unsigned last_pt = (unsigned)(g.m >> 5) - 1u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                             // tile row (t >> 3) + 32 j belongs to point pt0 + j
-            const unsigned b = b0 + ((unsigned)j >= left ? ((unsigned)j - left) / s + 1u : 0u);
+            const unsigned jj = min((unsigned)j, last_pt - pt0);  // (rows past the end repeat the last point's last row)
+            const unsigned b = b0 + (jj >= left ? (jj - left) / s + 1u : 0u);
             nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + 32 * j));
             cloud_off[j] = b * (unsigned)a.n;
         }

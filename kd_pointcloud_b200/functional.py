@@ -406,14 +406,59 @@ def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
         return K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
     if n <= 256:
         return K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
-    # wider layers: column blocks of 256 (level3_1: 256 -> 512)
-    outs = []
+    # wider layers: column blocks of 256 written in place (level3_1: 256 -> 512; input gradients of the PointConv linears)
+    if res is not None:
+        outs = []
+        for c0 in range(0, n, 256):
+            c1 = min(n, c0 + 256)
+            outs.append(K.linear_tc(x, _packed_weight(w2d[c0:c1]), c1 - c0, None if scale is None else scale[c0:c1].contiguous(),
+                                    None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi, res[..., c0:c1].contiguous()))
+        return torch.cat(outs, dim=-1)
+    out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
     for c0 in range(0, n, 256):
         c1 = min(n, c0 + 256)
-        outs.append(K.linear_tc(x, _packed_weight(w2d[c0:c1]), c1 - c0, None if scale is None else scale[c0:c1].contiguous(),
-                                None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi,
-                                None if res is None else res[..., c0:c1].contiguous()))
-    return torch.cat(outs, dim=-1)
+        ops.linear_tc_into(x, _packed_weight(w2d[c0:c1]), c1 - c0, out, c0, None if scale is None else scale[c0:c1].contiguous(),
+                           None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi)
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b for the TRAINING path: forward and the input gradient dX = dY W run on tcgen05 (bf16 hi/lo split,
+    fp32-level accuracy - the same kernel as inference); dW = dY^T X and db are reductions over all rows and stay
+    torch ops.  (torch's own fp32 matmul runs on the CUDA cores: 48 % of the KD training step before this.)"""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias):
+        ctx.save_for_backward(x, w2d)
+        ctx.has_bias = bias is not None
+        return fused_linear(x.detach(), w2d.detach(), None if bias is None else bias.detach())
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w2d = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = fused_linear(gy, w2d.detach().t().contiguous(), None)
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.needs_input_grad[1]:
+            gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def linear_tc_autograd_available(x: torch.Tensor, w2d: torch.Tensor) -> bool:
+    n, k = w2d.shape
+    return (USE_TC_TRAINING and x.is_cuda and x.dtype == torch.float32 and k >= 16 and n >= 16 and k % 4 == 0 and n % 4 == 0
+            and x.numel() // max(k, 1) >= 128)
+
+
+def linear_tc_autograd(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    return _LinearTC.apply(x, w2d, bias)
+
+
+USE_TC_TRAINING = os.environ.get("KDPC_TC_TRAINING", "1") != "0"
 
 
 # ------------------------------------------------------------------- fused PointConv / cost volume

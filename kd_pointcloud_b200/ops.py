@@ -502,6 +502,23 @@ def _linear_tc(x, wpacked, n: int, scale, shift, slope: float, lo: float, hi: fl
     return out
 
 
+def linear_tc_into(x: torch.Tensor, wpacked: torch.Tensor, n: int, out: torch.Tensor, col0: int, scale=None, shift=None,
+                   slope: float = 1.0, lo: float = 1.0, hi: float = 0.0) -> None:
+    """out[..., col0:col0+n] = epilogue(x W^T) written in place into a column block of a wider contiguous tensor
+    (the kernel takes the output row stride): wide layers / wide input gradients need no torch.cat afterwards.
+    Not a dispatcher op (it mutates ``out``): inference and hand-written backward only."""
+    m, k = _linear_args(x, n, scale, shift, None)
+    ntot = out.shape[-1]
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != m * ntot or col0 % 4 != 0 or col0 + n > ntot:
+        raise ValueError("kdpc: linear_tc_into needs a contiguous float32 [..., Ntot] output and a 4-aligned column offset")
+    with _guard(x):
+        nws = _lib.lib().kdpc_linear_tc_ws_bytes(m, n, k)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=x.device) if nws else None
+        if m * n:
+            _call("kdpc_linear_tc", m, n, k, _p(x), k, _p(wpacked), _p(scale), _p(shift), float(slope), float(lo),
+                  float(hi), None, _p(ws), out.data_ptr() + 4 * col0, ntot, _stream())
+
+
 def _linear_simt(x, w, scale, shift, slope: float, lo: float, hi: float, residual) -> torch.Tensor:
     _req(w, torch.float32, 2, "weight")
     n = w.shape[0]

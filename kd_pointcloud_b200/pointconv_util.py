@@ -53,7 +53,11 @@ def _linear_pm(conv: nn.Module, x: torch.Tensor, norm: Optional[nn.Module] = Non
     slope = 1.0 if act is None else _slope(act)
     if KF.fused_linear_available(x, w, conv.bias, bn):
         return KF.fused_linear(x, w, conv.bias, bn, slope, clamp, residual)
-    y = F.linear(x, w.reshape(w.shape[0], -1), conv.bias)
+    w2d = w.reshape(w.shape[0], -1)
+    if KF.linear_tc_autograd_available(x, w2d):
+        y = KF.linear_tc_autograd(x, w2d, conv.bias)        # tcgen05 forward + input gradient (training path)
+    else:
+        y = F.linear(x, w2d, conv.bias)
     if bn is not None:
         y = bn(y.reshape(-1, y.shape[-1])).view(y.shape)
     if act is not None:

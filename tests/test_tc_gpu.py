@@ -150,7 +150,7 @@ def test_pointconv_fused_matches_fp64(B, N, S, D, Cout, KN):
 
 
 @pytest.mark.parametrize("B,N1,N2,D", [(2, 1024, 1024, 32), (1, 333, 500, 64), (2, 256, 256, 256), (1, 8192, 8192, 32),
-                                        (1, 2048, 2048, 128)])
+                                        (1, 2048, 2048, 128), (3, 333, 500, 32), (5, 3, 40, 64), (2, 130, 64, 128)])
 def test_costvol_fused_matches_fp64(B, N1, N2, D):
     torch.manual_seed(N1 + D)
     xyz1 = torch.rand(B, N1, 3, device=DEV) * 4
@@ -195,3 +195,35 @@ def test_fused_layers_match_unfused_modules():
             KF.FUSED_POINTCONV_K, P.FUSED_COSTVOL = saved
     for a, b in zip(fused, plain):
         assert _err(a, b.double()) < 5e-5
+
+
+@pytest.mark.parametrize("M,Kin,N", [(4096, 128, 128), (1000, 2096, 128), (300, 64, 512), (8192, 3120, 128), (130, 16, 16)])
+def test_linear_tc_autograd_matches_fp64(M, Kin, N):
+    """Training path: forward and input gradient on tcgen05 (bf16 hi/lo), dW / db by torch; against an fp64 reference."""
+    torch.manual_seed(M + N)
+    x = torch.randn(2, M // 2, Kin, device=DEV, requires_grad=True)
+    lin = torch.nn.Linear(Kin, N).to(DEV)
+    gy = torch.randn(2, M // 2, N, device=DEV)
+    assert KF.linear_tc_autograd_available(x, lin.weight)
+    y = KF.linear_tc_autograd(x, lin.weight, lin.bias)
+    y.backward(gy)
+    xd = x.detach().double().requires_grad_(True)
+    wd, bd = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    assert rel(y, yd) < 1e-5 and rel(x.grad, xd.grad) < 1e-5
+    assert rel(lin.weight.grad, wd.grad) < 1e-5 and rel(lin.bias.grad, bd.grad) < 1e-5
+
+
+def test_wide_linear_blocks_written_in_place():
+    """N > 256: column blocks go straight into the output (no torch.cat), same values as the per-block results."""
+    torch.manual_seed(5)
+    x = torch.randn(3, 700, 256, device=DEV)
+    lin = torch.nn.Linear(256, 512).to(DEV)
+    with torch.no_grad():
+        y = KF.fused_linear(x, lin.weight, lin.bias, None, 0.1)
+        ref = torch.nn.functional.leaky_relu(torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double()), 0.1)
+        lo = KF.fused_linear(x, lin.weight[:256], lin.bias[:256], None, 0.1)
+    assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    assert torch.equal(y[..., :256], lo)
