@@ -325,15 +325,16 @@ def run_kdpc(args):
     epe_last = float(runner.out_epe.item())
 
     # ---------------- end to end through the public call, host buffers --------------------------
-    for i in range(min(2, args.warmup)):
-        runner.run_host(host[i % pool])
+    # (the public streaming call: pinned host batches in, one EPE3D per batch out; the H2D of batch i+1 overlaps the
+    # kernels of batch i, every step still moves its own inputs and reads its own result)
+    runner.run_host_pipelined(host[i % pool] for i in range(min(2, args.warmup)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        runner.run_host(host[i % pool])
+    epes = runner.run_host_pipelined(host[i % pool] for i in range(args.steps))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
+    assert len(epes) == args.steps and abs(epes[-1] - runner.run_host(host[(args.steps - 1) % pool])) < 1e-6
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -408,7 +409,7 @@ def run_train(args):
     from kd_pointcloud_b200.flownet import student, teacher
     from kd_pointcloud_b200.sharding import FlatGradAllReduce
     from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
-    from kd_pointcloud_b200.training import kd_step
+    from kd_pointcloud_b200.training import GraphedKDStep, kd_step
 
     B = args.batch
     t = teacher()
@@ -416,7 +417,7 @@ def run_train(args):
     s = student()
     s.load_state_dict(synthetic_state_dict(s.state_dict(), MODEL_SEED + 1))
     t, s = t.to(dev), s.to(dev)
-    opt = torch.optim.Adam(s.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(s.parameters(), lr=1e-3, capturable=not args.no_graph)
     reducer = FlatGradAllReduce(s.parameters()) if world > 1 else None
     kind = "kitti" if world > 1 else "ft3d"
     pool = [make_pairs(B, NPOINTS, seed=4321 + 1000 * rank + i, kind=kind, device=dev) for i in range(2)]
@@ -427,14 +428,20 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    n_step0 = ops.LAUNCHES
+    kd_step(t, s, pool[0], opt, reducer)
+    launches_per_step = ops.LAUNCHES - n_step0
+    stepper = None if args.no_graph else GraphedKDStep(t, s, pool[0], opt, reducer)
+    graphed = stepper is not None and stepper.graph is not None
+    run = stepper.step if graphed else (lambda batch: kd_step(t, s, batch, opt, reducer))
     for i in range(args.warmup):
-        kd_step(t, s, pool[i % 2], opt, reducer)
+        run(pool[i % 2])
     barrier()
     n0 = ops.LAUNCHES
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(args.steps):
-        loss = kd_step(t, s, pool[i % 2], opt, reducer)
+        loss = run(pool[i % 2])
     b.record()
     barrier()
     ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -449,8 +456,9 @@ def run_train(args):
             "config": {"workload": "configs[3]/[4]: teacher fwd (no grad) + student fwd/bwd + fused KD loss + Adam; "
                                    f"{kind}-shaped synthetic 8192-pt pairs", "pairs_per_gpu_per_step": B,
                        "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else "none",
-                       "grad_elements": None if reducer is None else reducer.numel, "final_loss": float(loss.item())},
-            "gpu_launches": int(ops.LAUNCHES - n0)}))
+                       "grad_elements": None if reducer is None else reducer.numel, "final_loss": float(loss.item()),
+                       "cuda_graph": graphed},
+            "gpu_launches": int(launches_per_step * args.steps if graphed else ops.LAUNCHES - n0)}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -130,6 +130,11 @@ int kdpc_weightnet(long long rows, const float *in, int in_stride, int h1, int h
  * sum_k grouped[r,k,c] * wn[r,k,w].  grouped [R,K,C], wn [R,K,wout] -> out [R, C*wout]. */
 int kdpc_pointconv_agg(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
                        float *out, kdpc_stream_t stream);
+/* Its backward (autograd of pointconv_util.py:249; torch runs two bmm of B*S tiny matrices): grad_out [R, C*wout] ->
+ * grad_grouped[r,k,c] = sum_w wn[r,k,w] grad_out[r,c,w] and grad_wn[r,k,w] = sum_c grouped[r,k,c] grad_out[r,c,w]
+ * (either may be NULL).  wout = 16, k <= 16.  Deterministic. */
+int kdpc_pointconv_agg_grad(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
+                            const float *grad_out, float *grad_grouped, float *grad_wn, kdpc_stream_t stream);
 
 /* CrossLayerLight.cross front half, pointconv_util.py:1836-1843:
  * out[b,s,k,:] = act(p2[b,idx[b,s,k],:] + p1[b,s,:] + pos_w (xyz2[idx]-xyz1[s]) + pos_b),

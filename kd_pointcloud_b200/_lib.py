@@ -91,6 +91,7 @@ _SIGNATURES = {
     "kdpc_group_concat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_weightnet": [c_longlong, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_pointconv_agg": [c_longlong, c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_pointconv_agg_grad": [c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_costvol_pre": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P],
     "kdpc_max_over_k": [c_longlong, c_int, c_int, _P, _P, _P, _P],
     "kdpc_interp3": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],

@@ -85,9 +85,116 @@ pointconv_agg_kernel(long long rows, int k, int c, const float *__restrict__ gro
     }
 }
 
+// Backward of the aggregation (autograd of pointconv_util.py:249, two bmm of B*S tiny matrices in torch):
+//   g_grouped[r,k,c] = sum_w wn[r,k,w] * g[r,c,w]          g_wn[r,k,w] = sum_c grouped[r,k,c] * g[r,c,w]
+// One CTA per point r, thread = channel c (same mapping as the forward): it reads its 64-byte slice g[r,c,:] once,
+// produces g_grouped[r,:,c] (coalesced across c) and adds grouped[r,k,c] * g[r,c,:] into per-thread partial sums of
+// g_wn, which a fixed shuffle + shared-memory tree then reduces over the channels (deterministic).
+template <int WOUT, int KCH>
+__global__ void __launch_bounds__(AGG_THREADS)
+pointconv_agg_grad_kernel(long long rows, int k, int c, const float *__restrict__ grouped, const float *__restrict__ wn,
+                          const float *__restrict__ g, float *__restrict__ g_grouped, float *__restrict__ g_wn) {
+    extern __shared__ float swn[];                            // [k][WOUT]
+    __shared__ __align__(16) float sred[AGG_THREADS / 32][KCH * WOUT];
+    const long long r = blockIdx.x;
+    const float *wr = wn + r * (long long)k * WOUT;
+    for (int i = threadIdx.x; i < k * WOUT; i += AGG_THREADS) swn[i] = wr[i];
+    __syncthreads();
+    const float *gr = grouped + r * (long long)k * c;
+    const float *grow = g + r * (long long)c * WOUT;
+    float *ogr = g_grouped != nullptr ? g_grouped + r * (long long)k * c : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < k; k0 += KCH) {                     // neighbours in chunks of KCH: KCH x WOUT partial sums per thread
+        float part[KCH][WOUT];
+#pragma unroll
+        for (int kk = 0; kk < KCH; ++kk)
+#pragma unroll
+            for (int w = 0; w < WOUT; ++w) part[kk][w] = 0.f;
+        for (int ci = threadIdx.x; ci < c; ci += AGG_THREADS) {
+            float gv[WOUT];
+            const float4 *g4 = reinterpret_cast<const float4 *>(grow + (size_t)ci * WOUT);
+#pragma unroll
+            for (int w = 0; w < WOUT; w += 4) {
+                const float4 t = __ldg(g4 + (w >> 2));
+                gv[w] = t.x; gv[w + 1] = t.y; gv[w + 2] = t.z; gv[w + 3] = t.w;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KCH; ++kk) {
+                if (k0 + kk < k) {
+                    if (ogr != nullptr) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int w = 0; w < WOUT; ++w) a = fmaf(swn[(k0 + kk) * WOUT + w], gv[w], a);
+                        ogr[(size_t)(k0 + kk) * c + ci] = a;
+                    }
+                    if (g_wn != nullptr) {
+                        const float x = __ldg(gr + (size_t)(k0 + kk) * c + ci);
+#pragma unroll
+                        for (int w = 0; w < WOUT; ++w) part[kk][w] = fmaf(x, gv[w], part[kk][w]);
+                    }
+                }
+            }
+        }
+        if (g_wn == nullptr) continue;
+        // warp-level sum of the KCH x WOUT partials.  The first 128 of them by recursive halving (reduce-scatter): at lane
+        // distance 16, 8, .. 1 every lane keeps the half that matches its lane bit and adds its partner's copy of it -
+        // 124 shuffles, lane l ends up with the warp sums of values 4l .. 4l+3 (a butterfly all-reduce of every value was
+        // 5 shuffles each: 720 per row, more than the arithmetic).  Values beyond 128 (KCH = 9): plain butterfly.
+        static_assert(WOUT == 16 && (KCH == 8 || KCH == 9), "reduction layout");
+        {
+            float *v = &part[0][0];
+#pragma unroll
+            for (int m = 16, n = 64; m >= 1; m >>= 1, n >>= 1) {
+                const bool up = (lane & m) != 0;
+#pragma unroll
+                for (int j = 0; j < n; ++j) {
+                    const float keep = up ? v[j + n] : v[j];
+                    const float give = up ? v[j] : v[j + n];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, give, m);
+                }
+            }
+            *reinterpret_cast<float4 *>(&sred[warp][4 * lane]) = make_float4(v[0], v[1], v[2], v[3]);
+            if (KCH == 9) {
+#pragma unroll
+                for (int w = 0; w < WOUT; ++w) {
+                    float t = part[KCH - 1][w];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0) sred[warp][128 + w] = t;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < KCH * WOUT; i += AGG_THREADS) {
+            if (k0 + i / WOUT < k) {
+                float v = 0.f;
+#pragma unroll
+                for (int wp = 0; wp < AGG_THREADS / 32; ++wp) v += sred[wp][i];
+                g_wn[r * (long long)k * WOUT + (size_t)k0 * WOUT + i] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace kdpc
 
 using namespace kdpc;
+
+KDPC_API int kdpc_pointconv_agg_grad(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
+                                     const float *grad_out, float *grad_grouped, float *grad_wn, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(grouped && wn && grad_out && (grad_grouped || grad_wn) && rows > 0 && k > 0 && c > 0);
+    if ((reinterpret_cast<uintptr_t>(grad_out) % 16) != 0 || rows > 0x7fffffffLL) return KDPC_EINVAL;
+    if (wout != 16) return KDPC_EUNSUPPORTED;
+    const size_t smem = (size_t)k * wout * sizeof(float);
+    if (smem > 32 * 1024) return KDPC_EUNSUPPORTED;
+    cudaStream_t st = to_stream(stream);
+    if (k <= 9)
+        pointconv_agg_grad_kernel<16, 9><<<(unsigned)rows, AGG_THREADS, smem, st>>>(rows, k, c, grouped, wn, grad_out, grad_grouped, grad_wn);
+    else
+        pointconv_agg_grad_kernel<16, 8><<<(unsigned)rows, AGG_THREADS, smem, st>>>(rows, k, c, grouped, wn, grad_out, grad_grouped, grad_wn);
+    KDPC_RETURN_LAST();
+}
 
 KDPC_API int kdpc_weightnet(long long rows, const float *in, int in_stride, int h1, int h2, int wout,
                             const float *w1, const float *b1, const float *w2, const float *b2,

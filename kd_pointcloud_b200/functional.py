@@ -554,11 +554,15 @@ class _PointConvAgg(torch.autograd.Function):
         grouped, wn = ctx.saved_tensors
         B, S, Kn, C = grouped.shape
         W = wn.shape[3]
+        want_g, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if W == 16 and grad_out.is_cuda:                       # one kernel for both gradients (csrc/pointconv.cu)
+            gg, gw = K.pointconv_agg_grad(grouped, wn, grad_out.contiguous(), want_g, want_w)
+            return (gg if want_g else None), (gw if want_w else None)
         g = grad_out.reshape(B * S, C, W)
         g_grouped = g_wn = None
-        if ctx.needs_input_grad[0]:
+        if want_g:
             g_grouped = torch.bmm(wn.reshape(B * S, Kn, W), g.transpose(1, 2)).view(B, S, Kn, C)
-        if ctx.needs_input_grad[1]:
+        if want_w:
             g_wn = torch.bmm(grouped.reshape(B * S, Kn, C), g).view(B, S, Kn, W)
         return g_grouped, g_wn
 

@@ -397,8 +397,28 @@ def _pointconv_agg(grouped: torch.Tensor, wn: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _pointconv_agg_grad(grouped: torch.Tensor, wn: torch.Tensor, grad_out: torch.Tensor, want_grouped: bool, want_wn: bool):
+    _req(grouped, torch.float32, 4, "grouped")
+    _req(wn, torch.float32, 4, "weights")
+    _req(grad_out, torch.float32, 3, "grad_out")
+    B, S, K, C = grouped.shape
+    W = wn.shape[3]
+    if tuple(wn.shape[:3]) != (B, S, K) or tuple(grad_out.shape) != (B, S, C * W):
+        raise ValueError("kdpc: pointconv_agg_grad shape mismatch")
+    with _guard(grouped):
+        gg = torch.empty_like(grouped) if want_grouped else torch.empty((0,), device=grouped.device)
+        gw = torch.empty_like(wn) if want_wn else torch.empty((0,), device=grouped.device)
+        if B * S and (want_grouped or want_wn):
+            _call("kdpc_pointconv_agg_grad", B * S, K, C, W, _p(grouped), _p(wn), _p(grad_out),
+                  _p(gg) if want_grouped else None, _p(gw) if want_wn else None, _stream())
+    return gg, gw
+
+
 _register("weightnet(Tensor x, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor w3, Tensor b3) -> Tensor",
           _weightnet, lambda x, w1, b1, w2, b2, w3, b3: x.new_empty(tuple(x.shape[:-1]) + (w3.shape[0],)))
+_register("pointconv_agg_grad(Tensor grouped, Tensor wn, Tensor grad_out, bool want_grouped, bool want_wn) -> (Tensor, Tensor)",
+          _pointconv_agg_grad,
+          lambda g, w, go, a, b: (g.new_empty(g.shape if a else (0,)), w.new_empty(w.shape if b else (0,))))
 _register("pointconv_agg(Tensor grouped, Tensor wn) -> Tensor", _pointconv_agg,
           lambda g, w: g.new_empty((g.shape[0], g.shape[1], g.shape[3] * w.shape[3])))
 

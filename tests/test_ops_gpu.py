@@ -327,3 +327,29 @@ def test_interp3_matches_oracle_and_grad(c):
     fr = feat.clone().requires_grad_(True)
     O.upsample_flow(dense.permute(0, 2, 1), sparse.permute(0, 2, 1), fr.permute(0, 2, 1)).permute(0, 2, 1).backward(go)
     assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,Kn,C", [(2, 300, 9, 131), (1, 77, 16, 67), (2, 64, 9, 515), (1, 5, 3, 4)])
+def test_pointconv_agg_grad_matches_fp64(B, S, Kn, C):
+    """Backward of the PointConv aggregation (one kernel for both gradients) against the two fp64 bmm of autograd."""
+    from kd_pointcloud_b200 import functional as KF
+    torch.manual_seed(S + C)
+    dev = "cuda:0"
+    grouped = torch.randn(B, S, Kn, C, device=dev, requires_grad=True)
+    wn = torch.rand(B, S, Kn, 16, device=dev, requires_grad=True)
+    go = torch.randn(B, S, C * 16, device=dev)
+    out = KF.pointconv_agg(grouped, wn)
+    out.backward(go)
+    gd, wd = grouped.detach().double().requires_grad_(True), wn.detach().double().requires_grad_(True)
+    ref = torch.einsum("bskc,bskw->bscw", gd, wd).reshape(B, S, C * 16)
+    ref.backward(go.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    assert rel(out, ref) < 1e-5 and rel(grouped.grad, gd.grad) < 1e-5 and rel(wn.grad, wd.grad) < 1e-5
+    # only one of the two gradients requested; deterministic
+    g2 = grouped.detach().clone().requires_grad_(True)
+    KF.pointconv_agg(g2, wn.detach()).backward(go)
+    assert torch.equal(g2.grad, grouped.grad)
+    w2 = wn.detach().clone().requires_grad_(True)
+    KF.pointconv_agg(grouped.detach(), w2).backward(go)
+    assert torch.equal(w2.grad, wn.grad)
