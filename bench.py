@@ -417,7 +417,8 @@ def run_train(args):
     s = student()
     s.load_state_dict(synthetic_state_dict(s.state_dict(), MODEL_SEED + 1))
     t, s = t.to(dev), s.to(dev)
-    opt = torch.optim.Adam(s.parameters(), lr=1e-3, capturable=not args.no_graph)
+    use_graph = not args.no_graph and world == 1           # (the NCCL all-reduce is not captured: multi-GPU steps run eagerly)
+    opt = torch.optim.Adam(s.parameters(), lr=1e-3, capturable=use_graph)
     reducer = FlatGradAllReduce(s.parameters()) if world > 1 else None
     kind = "kitti" if world > 1 else "ft3d"
     pool = [make_pairs(B, NPOINTS, seed=4321 + 1000 * rank + i, kind=kind, device=dev) for i in range(2)]
@@ -431,7 +432,7 @@ def run_train(args):
     n_step0 = ops.LAUNCHES
     kd_step(t, s, pool[0], opt, reducer)
     launches_per_step = ops.LAUNCHES - n_step0
-    stepper = None if args.no_graph else GraphedKDStep(t, s, pool[0], opt, reducer)
+    stepper = GraphedKDStep(t, s, pool[0], opt, reducer) if use_graph else None
     graphed = stepper is not None and stepper.graph is not None
     run = stepper.step if graphed else (lambda batch: kd_step(t, s, batch, opt, reducer))
     for i in range(args.warmup):

@@ -61,7 +61,9 @@ class GraphedKDStep:
     bookkeeping from Python and is bound by the host (71 ms of CPU per 73 ms of GPU time, tools/prof_train.py).
 
     The optimizer must be created with ``capturable=True``; batches are copied into static input buffers.
-    Falls back to the eager step (``self.graph is None``) when the capture fails."""
+    Falls back to the eager step (``self.graph is None``) when the capture fails, and ALWAYS runs eagerly when a gradient
+    ``reducer`` is given: capturing the NCCL all-reduce hung the 2-GPU run (round 1), so multi-GPU training stays eager
+    until that is understood."""
 
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, example_batch: Dict[str, torch.Tensor],
                  optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None, warmup: int = 3, **kw):
@@ -69,6 +71,8 @@ class GraphedKDStep:
         self.static = {k: v.clone() for k, v in example_batch.items()}
         self.loss: Optional[torch.Tensor] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if reducer is not None:
+            return
         dev = next(student.parameters()).device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
