@@ -163,6 +163,10 @@ long long kdpc_packed_weight_bytes(int n, int k_packed);
 /* The fused tcgen05 layers stage their gathers asynchronously (bulk copies two pipeline iterations ahead);
  * kdpc_tc_set_async(0) selects the synchronous register-staged producers (same results; A/B measurements). */
 void kdpc_tc_set_async(int on);
+/* debug (tools/trace_pointconv.py, tools/trace_costvol.py): while a device buffer of 200 x 16 int64 is set, CTA 0 of every
+ * tcgen05 kernel writes per-iteration clock64 stamps of its producer, MMA and epilogue warps into it; NULL = off */
+void kdpc_tc_set_trace(void *device_buffer);
+void *kdpc_tc_trace_buffer(void);
 int kdpc_tc_async_enabled(void);
 int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const float *w, void *out, kdpc_stream_t stream);
 

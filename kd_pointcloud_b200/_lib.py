@@ -165,7 +165,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_pointconv_set_stages",
+            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 

@@ -6,10 +6,12 @@
 //   warps 0..PW-1 A producers: build the 128x64 A chunk IN SHARED MEMORY (plain fp32 rows, or the
 //                            PointConv gather+aggregate, or the cost-volume gather+add+act), split
 //                            fp32 -> bf16 hi/lo, write it in the canonical SWIZZLE_128B layout
-//   warp  PW   MMA issuer  : one elected thread, 3 tcgen05.mma per K-step (hi*hi, hi*lo, lo*hi)
-//                            (producer thread 0 also issues the 1-D bulk TMA of the pre-packed weight chunk
-//                            for the stage it is about to fill: no separate loader warp, more registers per thread)
+//   warp  PW   MMA issuer  : warp-uniform loop, the tcgen05 instructions under elect.sync: 3 tcgen05.mma per K-step
+//                            (hi*hi, hi*lo, lo*hi).  (Producer thread 0 also issues the 1-D bulk TMA of the pre-packed
+//                            weight chunk for the stage it is about to fill: no separate loader warp.)
 //   warps PW+1..PW+4 epilogue: tcgen05.ld the accumulator, scale/shift/activation, store
+//                            (kMergedIssuer producers: warp PW is issuer AND epilogue of TMEM lane quarter 0, the
+//                            epilogue warps are PW..PW+3 - 12 warps, 168 registers per thread)
 // Pipelines: smem stages (full_a/full_b/empty mbarriers) and two TMEM accumulator buffers
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -54,7 +56,8 @@ struct GemmShape {
     int raw_stages;       // lookahead + 1
     long long num_tiles;
     const unsigned char *wpacked;   // [chunk][hi|lo][n_pad][128 B]
-    long long *trace;     // debug: per-chunk clock64 stamps of CTA 0 (nullptr = off)
+    long long *trace;     // debug (tools/trace_*.py): per-iteration clock64 stamps of CTA 0; nullptr = off (one uniform
+                          // predicate per stamp site, nothing is written)
 };
 
 constexpr int MAX_RAW_STAGES = 4;
@@ -246,7 +249,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 // publishes it to the MMA issuer
                 // (stage / phase / weight-chunk cursors are carried incrementally: a runtime % and / per chunk cost
                 // more instructions than the hi/lo split of the chunk)
-                auto stamp = [&](int ev) {                        // debug trace of CTA 0 (kdpc_pointconv_set_trace)
+                auto stamp = [&](int ev) {                        // debug trace of CTA 0 (kdpc_tc_set_trace)
                     if (g.trace != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == PW - 1) && it < 200)
                         g.trace[it * 16 + (warp == 0 ? 0 : 4) + ev] = clock64();
                 };
