@@ -26,10 +26,12 @@ namespace tc {
 // weight chunks repeat).  K = 16 (PointConvD) runs as 2 x 8, which keeps wn[NB][8] in registers.
 // K-chunk 0 of a pass = channels (dx, dy, dz, 0); chunk i >= 1 = feature channels 4(i-1) .. 4(i-1)+3.
 //
-// Neighbour gathers: thread (row, half) reads the 16 bytes (4 channels) of each neighbour's row straight into
-// registers; the two half-lanes of a row are adjacent lanes, so a warp request touches 16 rows and the pair is one
-// coalesced access; eight consecutive K-chunks share each 128-byte line (L1 hits), and with a Morton row order the
-// 128 queries of a tile share most of their neighbours.
+// Neighbour gathers: straight into registers, feature chunks in PAIRS - the two half-lanes of a row are adjacent lanes
+// and fetch the two 16-byte halves of each neighbour's 32-byte sector once per pair (a warp request touches 16 rows,
+// one L1 line access per row and pair), then hand each other the half the current chunk needs by shuffle: 36 SHFL per
+// chunk buy half the L1 line accesses, the kernel's real limiter (-9 % at flow0, and the natural row order became as
+// fast as the Morton order).  Four consecutive chunk pairs share each 128-byte line (L1 hits), and with a Morton row
+// order the 128 queries of a tile share most of their neighbours.
 // Rejected by measurement on the same box (same results, tools/bench_pointconv.py, tools/trace_pointconv.py):
 //   * cp.async staging of the gathers in shared memory (per CTA, per row quarter and per warp; double buffered; also
 //     interleaved into the FFMA loop): never faster - a warp-level LDGSTS whose lanes touch 16 lines blocks the
@@ -164,6 +166,34 @@ struct PointConvProducer {
         for (int k = 0; k < NB; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(fp + nb[k]));
     }
 
+    // one K-chunk (4 feature channels x this thread's 8 WeightNet outputs) from the gathered channels v[k]
+    __device__ __forceinline__ void chunk_from(const float4 (&v)[NB], unsigned char *a_hi, int r) const {
+        float acc[4][8];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[ch][j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(v[k].x, wn[k][j], acc[0][j]);
+                acc[1][j] = fmaf(v[k].y, wn[k][j], acc[1][j]);
+                acc[2][j] = fmaf(v[k].z, wn[k][j], acc[2][j]);
+                acc[3][j] = fmaf(v[k].w, wn[k][j], acc[3][j]);
+            }
+        }
+        unsigned char *a_lo = a_hi + A_PART_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            uint4 hi, lo;
+            split8(acc[ch], hi, lo);
+            const uint32_t off = sw128_offset(r, ch * 2 + half);
+            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+        }
+    }
+
     template <class Acquire, class Release>
     __device__ __forceinline__ void run_tile(long long tile, int c_begin, int c_end, int ptid, unsigned char *, uint64_t *,
                                              Acquire &&acquire, Release &&release) {
@@ -184,36 +214,44 @@ struct PointConvProducer {
             } else {
                 weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
             }
-#pragma unroll 1
-            for (; c < stop; ++c) {
+            // Feature chunks in PAIRS: the two half-lanes of a row fetch the two 16-byte halves of every neighbour's
+            // 32-byte sector once (one L1 line access per row and pair instead of one per row and chunk) and hand each
+            // other the half the current chunk needs by shuffle.
+            const int lane = ptid & 31;
+            if (c < stop && ((c - base - 1) & 1)) {            // (a split-K work item that starts on an odd feature chunk)
                 unsigned char *a_hi = acquire(c);
                 float4 v[NB];
                 gather(c - base - 1, v);
-                float acc[4][8];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[ch][j] = 0.f;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        acc[0][j] = fmaf(v[k].x, wn[k][j], acc[0][j]);
-                        acc[1][j] = fmaf(v[k].y, wn[k][j], acc[1][j]);
-                        acc[2][j] = fmaf(v[k].z, wn[k][j], acc[2][j]);
-                        acc[3][j] = fmaf(v[k].w, wn[k][j], acc[3][j]);
-                    }
-                }
-                unsigned char *a_lo = a_hi + A_PART_BYTES;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint4 hi, lo;
-                    split8(acc[ch], hi, lo);
-                    const uint32_t off = sw128_offset(r, ch * 2 + half);
-                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-                }
+                chunk_from(v, a_hi, r);
                 release();
+                ++c;
+            }
+#pragma unroll 1
+            for (; c < stop; c += 2) {
+                const int f0 = c - base - 1;                    // even feature chunk of the pair
+                float4 mine[NB];
+                if ((f0 + half) * 4 < a.d) {
+                    gather(f0 + half, mine);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) mine[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) {
+                    if (c + e >= stop) break;
+                    unsigned char *a_hi = acquire(c + e);
+                    const int src = (lane & ~1) | e;
+                    float4 v[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        v[k].x = __shfl_sync(0xffffffffu, mine[k].x, src);
+                        v[k].y = __shfl_sync(0xffffffffu, mine[k].y, src);
+                        v[k].z = __shfl_sync(0xffffffffu, mine[k].z, src);
+                        v[k].w = __shfl_sync(0xffffffffu, mine[k].w, src);
+                    }
+                    chunk_from(v, a_hi, r);
+                    release();
+                }
             }
         }
     }
