@@ -192,11 +192,15 @@ int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const f
  * (k = 9 or 16) -> out [B,S,n_out].  wn_params: HOST array of 248 floats (w1[8x3] b1[8] w2[8x8] b2[8]
  * w3[16x8] b3[16], nn.Conv2d layouts) passed to the kernel as launch parameters.  wpacked: the Linear
  * weight packed with kdpc_pack_weight(mode 1, d, 16).  Neither [B,S,k,3+d] nor [B,S,16(d+3)] touches HBM.
- * ws: kdpc_pointconv_fused_ws_bytes(b,s,k,d,n_out) bytes or NULL (split-K workspace, as for kdpc_linear_tc). */
+ * ws: kdpc_pointconv_fused_ws_bytes(b,s,k,d,n_out) bytes or NULL (split-K partial sums, as for kdpc_linear_tc, followed by
+ * the WeightNet outputs [b*s, k, 16] of a small pre-pass; with NULL both happen inside the fused kernel, slower). */
 long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out);
 /* operand pipeline stages of the fused PointConv (default 2: the rest of the SM's L1/shared array serves the
  * neighbour gathers; measured 5% faster end to end than 3). */
 void kdpc_pointconv_set_stages(int n);
+/* WeightNet pre-pass (a small kernel that leaves the WeightNet outputs in the workspace; needs ws != NULL): 1 (default) =
+ * where it pays (>= 32768 rows, or split-K), 0 = never (evaluated inside the fused kernel), 2 = always.  Same results. */
+void kdpc_pointconv_set_precompute(int on);
 int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
                          const float *query_xyz, const float *feats, const int *idx, const float *wn_params,
                          const void *wpacked, const float *scale, const float *shift, float slope,

@@ -154,6 +154,10 @@ def lib() -> ctypes.CDLL:
         L.kdpc_pointconv_set_stages.argtypes = [c_int]
         if os.environ.get("KDPC_PC_STAGES"):
             L.kdpc_pointconv_set_stages(int(os.environ["KDPC_PC_STAGES"]))
+        L.kdpc_pointconv_set_precompute.restype = None
+        L.kdpc_pointconv_set_precompute.argtypes = [c_int]
+        if os.environ.get("KDPC_PC_PRECOMPUTE", "1") == "0":
+            L.kdpc_pointconv_set_precompute(0)
         if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
             L.kdpc_tc_set_async(0)
         if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements
@@ -165,7 +169,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages",
+            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 

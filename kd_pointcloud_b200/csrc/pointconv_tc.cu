@@ -61,6 +61,7 @@ struct PointConvProducer {
         int n_cand, s, d;
         const int *order;         // optional [B] x order_stride: tile position i of cloud b processes query order[b][i]
         int order_stride;
+        const float *wn_pre;      // optional [B*S, KN, 16]: the WeightNet outputs, precomputed by pointconv_weightnet_kernel
         float w1[24], b1[8], w2[64], b2[8], w3[128], b3[16];    // WeightNet 3 -> 8 -> 8 -> 16, ReLU after each
     };
     static __device__ __forceinline__ void prologue(const Args &, int, int) {}
@@ -160,6 +161,45 @@ struct PointConvProducer {
         }
     }
 
+    // Same with the WeightNet outputs read back from pointconv_weightnet_kernel's buffer: the unrolled 9-neighbour MLP
+    // above is ~18 k cycles per tile inside this kernel (it spills around the wn[][] it is filling); precomputed, the
+    // phase is 18 coalesced 16-byte loads and the coordinate chunk.
+    __device__ __forceinline__ void weightnet_pre(const int (&gi)[NB], int pass, bool emit_xyz, unsigned char *a_hi,
+                                                  unsigned char *a_lo, int r) {
+        const float4 *wp = reinterpret_cast<const float4 *>(a.wn_pre + ((size_t)(ip - a.idx) + (size_t)pass * NB) * 16 + half * 8);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const float4 lo4 = __ldg(wp + k * 4), hi4 = __ldg(wp + k * 4 + 1);
+            wn[k][0] = lo4.x; wn[k][1] = lo4.y; wn[k][2] = lo4.z; wn[k][3] = lo4.w;
+            wn[k][4] = hi4.x; wn[k][5] = hi4.y; wn[k][6] = hi4.z; wn[k][7] = hi4.w;
+        }
+        if (!emit_xyz) return;
+        float acc[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const float *cp = a.cand_xyz + (long long)gi[k] * 3;
+            const float dx = __ldg(cp) - qx, dy = __ldg(cp + 1) - qy, dz = __ldg(cp + 2) - qz;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(dx, wn[k][j], acc[0][j]);
+                acc[1][j] = fmaf(dy, wn[k][j], acc[1][j]);
+                acc[2][j] = fmaf(dz, wn[k][j], acc[2][j]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if (c < 3) split8(acc[c < 3 ? c : 0], hi, lo);
+            const uint32_t off = sw128_offset(r, c * 2 + half);
+            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+        }
+    }
+
     __device__ __forceinline__ void gather(int fchunk, float4 (&v)[NB]) const {
         const float *fp = a.feats + fchunk * 4;
 #pragma unroll
@@ -208,11 +248,13 @@ struct PointConvProducer {
             load_idx(pass, gi);
             if (c == base) {
                 unsigned char *a_hi = acquire(c);
-                weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
+                if (a.wn_pre != nullptr) weightnet_pre(gi, pass, true, a_hi, a_hi + A_PART_BYTES, r);
+                else weightnet(gi, true, a_hi, a_hi + A_PART_BYTES, r);
                 release();
                 ++c;
             } else {
-                weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
+                if (a.wn_pre != nullptr) weightnet_pre(gi, pass, false, nullptr, nullptr, r);
+                else weightnet(gi, false, nullptr, nullptr, r);    // a split-K work item that starts inside a pass
             }
             // Feature chunks in PAIRS: the two half-lanes of a row fetch the two 16-byte halves of every neighbour's
             // 32-byte sector once (one L1 line access per row and pair instead of one per row and chunk) and hand each
@@ -257,7 +299,44 @@ struct PointConvProducer {
     }
 };
 
+// WeightNet(3 -> 8 -> 8 -> 16, ReLU after every layer, pointconv_util.py:184-215) of every (query, neighbour) pair, one
+// thread each, in exactly the fused kernel's operation order (bit-identical results): out [rows, KN, 16].
+template <class Args>
+__global__ void __launch_bounds__(256)
+pointconv_weightnet_kernel(long long pairs, int kn, const Args a, float *__restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pairs) return;
+    const long long row = e / kn;
+    const int b = (int)(row / a.s);
+    const int nbr = b * a.n_cand + __ldg(a.idx + e);
+    const float *qp = a.query_xyz + row * 3, *cp = a.cand_xyz + (long long)nbr * 3;
+    const float dx = __ldg(cp) - __ldg(qp), dy = __ldg(cp + 1) - __ldg(qp + 1), dz = __ldg(cp + 2) - __ldg(qp + 2);
+    float h1[8], h2[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+        h1[o] = fmaxf(a.b1[o] + a.w1[o * 3 + 0] * dx + a.w1[o * 3 + 1] * dy + a.w1[o * 3 + 2] * dz, 0.f);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float t = a.b2[o];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += a.w2[o * 8 + i] * h1[i];
+        h2[o] = fmaxf(t, 0.f);
+    }
+    float w[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float t = a.b3[o];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += a.w3[o * 8 + i] * h2[i];
+        w[o] = fmaxf(t, 0.f);
+    }
+    float4 *o4 = reinterpret_cast<float4 *>(out + e * 16);
+#pragma unroll
+    for (int o = 0; o < 16; o += 4) o4[o >> 2] = make_float4(w[o], w[o + 1], w[o + 2], w[o + 3]);
+}
+
 static int kdpc_pointconv_stages = 2;
+static int kdpc_pointconv_precompute = 1;                // 1 = where it pays (below), 0 = never, 2 = always (A/B measurements)
 
 template <int KN, int NPASS>
 static int launch_pointconv(long long m, int n_out, const typename PointConvProducer<KN, NPASS>::Args &pa, const void *wpacked,
@@ -296,10 +375,14 @@ using namespace kdpc;
 using namespace kdpc::tc;
 
 KDPC_API void kdpc_pointconv_set_stages(int n) { kdpc::tc::kdpc_pointconv_stages = n < 2 ? 2 : n; }
+/* A/B switch for measurements: 0 = WeightNet evaluated inside the fused kernel instead of by the small pre-pass (same results) */
+KDPC_API void kdpc_pointconv_set_precompute(int on) { kdpc::tc::kdpc_pointconv_precompute = on; }
 
 KDPC_API long long kdpc_pointconv_fused_ws_bytes(int b, int s, int k, int d, int n_out) {
     if (b <= 0 || s <= 0 || d <= 0 || n_out <= 0 || n_out > 256) return 0;
-    return (long long)split_k_ws_bytes(pointconv_shape((long long)b * s, n_out, d, k));
+    // split-K partial sums (16-byte multiple) followed by the precomputed WeightNet outputs [b*s, k, 16]
+    const long long splitk = ((long long)split_k_ws_bytes(pointconv_shape((long long)b * s, n_out, d, k)) + 15) / 16 * 16;
+    return splitk + (long long)b * s * k * 16 * (long long)sizeof(float);
 }
 
 KDPC_API int kdpc_pointconv_fused_ordered(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,
@@ -327,15 +410,28 @@ KDPC_API int kdpc_pointconv_fused_ordered(int b, int n, int s, int k, int d, int
     for (int i = 0; i < 16; ++i) pa.b3[i] = *p++;
     StoreEpilogue::Args ea{scale, shift, slope, 1.f, 0.f, nullptr, out, n_out, nullptr};
     // the row order only pays (and is only supported) without split-K: small layers keep the natural order
-    const bool ordered = row_order != nullptr && pointconv_shape((long long)b * s, n_out, d, k).splits == 1;
+    const GemmShape planned = pointconv_shape((long long)b * s, n_out, d, k);
+    pa.wn_pre = nullptr;
+    // the pre-pass pays where the in-kernel evaluation is expensive: many tiles per SM (the 18 k-cycle phase serialises
+    // with the chunk loop), or split-K (every work item of a tile would evaluate the same WeightNet again); measured
+    // slower for the layers in between (an extra launch for ~3 k rows per SM)
+    const bool pre = kdpc_pointconv_precompute == 2 || (kdpc_pointconv_precompute == 1 && (planned.splits > 1 || (long long)b * s >= 32768));
+    if (ws != nullptr && pre) {
+        float *wn_ws = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ws) + (split_k_ws_bytes(planned) + 15) / 16 * 16);
+        const long long pairs = (long long)b * s * k;
+        pointconv_weightnet_kernel<<<(unsigned)div_up_ll(pairs, 256), 256, 0, to_stream(stream)>>>(pairs, k, pa, wn_ws);
+        pa.wn_pre = wn_ws;
+    }
+    void *splitk_ws = planned.splits > 1 ? ws : nullptr;     // (the launcher plans split-K only when it gets a workspace)
+    const bool ordered = row_order != nullptr && planned.splits == 1;
     pa.order = ordered ? row_order : nullptr;
     pa.order_stride = ordered ? order_stride : 0;
     if (ordered) { ea.row_order = row_order; ea.order_stride = order_stride; ea.rows_per_cloud = s; }
-    if (k == 9) return launch_pointconv<9, 1>((long long)b * s, n_out, pa, wpacked, ea, ws, to_stream(stream));
+    if (k == 9) return launch_pointconv<9, 1>((long long)b * s, n_out, pa, wpacked, ea, splitk_ws, to_stream(stream));
     PointConvProducer<16, 2>::Args pb;
     static_assert(sizeof(pb) == sizeof(pa), "Args layout");
     memcpy(&pb, &pa, sizeof(pa));
-    return launch_pointconv<16, 2>((long long)b * s, n_out, pb, wpacked, ea, ws, to_stream(stream));
+    return launch_pointconv<16, 2>((long long)b * s, n_out, pb, wpacked, ea, splitk_ws, to_stream(stream));
 }
 
 KDPC_API int kdpc_pointconv_fused(int b, int n, int s, int k, int d, int n_out, const float *cand_xyz,

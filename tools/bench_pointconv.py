@@ -25,8 +25,9 @@ for (B, N, S, k, D, Cout) in shapes:
     out = {}
     KF._knn_compute(k, cand, query)                       # leaves the Morton order of the queries in the sort cache
     mo = KF.morton_order(query)
-    for staged in (0, 1):
-        order = mo if staged == 1 else None
+    for staged in (0, 1, 2):
+        order = mo if staged >= 1 else None
+        _lib.lib().kdpc_pointconv_set_precompute(0 if staged == 2 else 1)
         for _ in range(3):
             y = K.pointconv_fused(cand, query, feats, idx, params, wp, Cout, None, lin.bias.detach(), 0.1, order)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,7 +38,8 @@ for (B, N, S, k, D, Cout) in shapes:
         e1.record()
         torch.cuda.synchronize()
         out[staged] = (e0.elapsed_time(e1) / 20 * 1e3, y)
-    same = torch.equal(out[0][1], out[1][1])
+    same = torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][1], out[2][1])
     fl = 2.0 * B * S * (D + 3) * 16 * (k + Cout)
     print(f"B={B:2d} N={N:5d} S={S:5d} K={k:2d} D={D:3d} Cout={Cout:3d}: natural order {out[0][0]:7.1f} us   "
-          f"Morton order {out[1][0]:7.1f} us ({fl / out[1][0] / 1e6:6.1f} TF/s)   identical={same}")
+          f"Morton order {out[1][0]:7.1f} us ({fl / out[1][0] / 1e6:6.1f} TF/s)   Morton, WeightNet in-kernel {out[2][0]:7.1f} us   identical={same}")
+_lib.lib().kdpc_pointconv_set_precompute(1)
