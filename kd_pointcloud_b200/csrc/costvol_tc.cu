@@ -118,9 +118,14 @@ struct CostVolProducer {
 struct CostVolAsyncProducer {
     static constexpr int kWarps = 8, kGroups = 1;
     static constexpr bool kAsync = true;
-    static constexpr int kIssuers = 256, kLookahead = 2;
+    // 4 extra warps do nothing but issue the gathers (a warp-level LDGSTS costs ~28 cycles of load/store-unit time and
+    // blocks its warp meanwhile: issued by the converting warps it took 1000-1350 of the 2250-2650 cycles of a pipeline
+    // iteration, tools/trace_costvol.py); the 8 producer warps only convert
+    static constexpr int kIssuerWarps = 4;
+    static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
     static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
     static constexpr int kRawBytes = (TILE_M + TILE_M / CV_K) * ROW_PITCH;     // 128 neighbour rows + 4 point rows
+    static constexpr int RPT = TILE_M * 8 / kIssuers;        // neighbour rows per issuing thread (8 lanes per row)
     struct Args {
         const float *p1q;    // [B,S,D]  points1 + pos_b - pos_w xyz1
         const float *p2q;    // [B,N,D]  points2 + pos_w xyz2
@@ -134,15 +139,15 @@ struct CostVolAsyncProducer {
     // (Measured and rejected: L1-allocating cp.async.ca with the queries in Morton order - no gain; the cost is per
     // LDGSTS instruction, ~28 cycles of load/store-unit time each, whatever the hit rate.)
     // Gather issue mapping: 8 consecutive lanes copy the (up to two) 128-byte halves of ONE neighbour row's chunk slice,
-    // 16 bytes each, so a warp-level LDGSTS touches 4 lines; thread t serves rows (t >> 3) + 32 j, j = 0..3.  (With one
+    // 16 bytes each, so a warp-level LDGSTS touches 4 lines; issuing thread t serves rows (t >> 3) + 16 j, j = 0..7.  (With one
     // thread per row copying its row's pieces one after the other every request touched 32 lines and the load/store
     // unit needed ~1350 of the 2650 cycles of a pipeline iteration just to accept them - tools/trace_costvol.py.)
     // All per-row address arithmetic happens once per tile, one iteration ahead (load_rows): the issue itself is an
     // add and a predicated LDGSTS per row.
-    int nbr[4];                   // neighbour index of tile row (t >> 3) + 32 j in the NEXT issued tile (loaded one iteration ahead,
+    int nbr[RPT];                 // neighbour index of tile row (t >> 3) + 16 j in the NEXT issued tile (loaded one iteration ahead,
                                   // first used at that issue: the load latency never stalls the issuing warp)
-    uint32_t cloud_off[4];        // (cloud of that row) * n
-    uint32_t pt_off;              // element offset into p1q of the point row this thread copies a piece of (threads >= 128)
+    uint32_t cloud_off[RPT];      // (cloud of that row) * n
+    uint32_t pt_off;              // element offset into p1q of the point row this thread copies a piece of
     uint32_t dst0;                // byte offset of this thread's piece inside a raw staging buffer (row j = 0)
 
     __device__ CostVolAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
@@ -157,10 +162,10 @@ struct CostVolAsyncProducer {
         const unsigned b0 = pt0 / s, left = (b0 + 1u) * s - pt0;  // points of the tile before the next cloud starts
         const unsigned last_pt = (unsigned)(g.m >> 5) - 1u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                             // tile row (t >> 3) + 32 j belongs to point pt0 + j
-            const unsigned jj = min((unsigned)j, last_pt - pt0);  // (rows past the end repeat the last point's last row)
+        for (int j = 0; j < RPT; ++j) {                           // tile row (t >> 3) + 16 j belongs to point pt0 + (j >> 1)
+            const unsigned jj = min((unsigned)(j >> 1), last_pt - pt0);  // (rows past the end repeat the last point's last row)
             const unsigned b = b0 + (jj >= left ? (jj - left) / s + 1u : 0u);
-            nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + 32 * j));
+            nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + 16 * j));
             cloud_off[j] = b * (unsigned)a.n;
         }
         const unsigned pt = min(pt0 + (unsigned)((ptid >> 5) & 3), last_pt);
@@ -187,12 +192,12 @@ struct CostVolAsyncProducer {
         const uint32_t dst = smem_u32(raw) + dst0;
         const float *src = a.p2q + c0 + q * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const uint32_t row_off = (cloud_off[j] + (uint32_t)nbr[j]) * (uint32_t)a.d;
-            if (q < ppr) cp_async_16(dst + j * (32 * ROW_PITCH), src + row_off);
-            if (q + 8 < ppr) cp_async_16(dst + j * (32 * ROW_PITCH) + 128, src + row_off + 32);
+            if (q < ppr) cp_async_16(dst + j * (16 * ROW_PITCH), src + row_off);
+            if (q + 8 < ppr) cp_async_16(dst + j * (16 * ROW_PITCH) + 128, src + row_off + 32);
         }
-        if (ptid >= TILE_M) {                                    // the 4 points' own rows, one 16-byte piece per lane
+        {                                                        // the 4 points' own rows, one 16-byte piece per lane
             const int k = ptid & 31;
             if (k < ppr)
                 cp_async_16(smem_u32(raw + (TILE_M + ((ptid >> 5) & 3)) * ROW_PITCH) + k * 16, a.p1q + pt_off + c0 + k * 4);

@@ -36,8 +36,14 @@ template <class P> struct merged_issuer<P, decltype((void)P::kMergedIssuer)> { s
 // instead of fill(); with kIssuers > 0 they own the raw staging area and its mbarriers (kIssuers arrivals each)
 template <class P, class = void> struct owns_loop { static constexpr bool value = false; };
 template <class P> struct owns_loop<P, decltype((void)P::kOwnsLoop)> { static constexpr bool value = P::kOwnsLoop; };
+// Asynchronous producers that declare kIssuerWarps > 0 get that many extra warps which do nothing but issue the
+// cp.async gathers (blocking on the load/store unit as long as they like), kWarps warps only convert: issue and
+// conversion overlap instead of alternating in the same warps.  raw_full[] then counts the issuer threads
+// (kIssuers = 32 * kIssuerWarps) and raw_empty[] hands a staging slot back (one arrival per converting warp).
+template <class P, class = void> struct issuer_warps { static constexpr int value = 0; };
+template <class P> struct issuer_warps<P, decltype((void)P::kIssuerWarps)> { static constexpr int value = P::kIssuerWarps; };
 template <class Producer> constexpr int num_threads() {
-    return (Producer::kWarps + (merged_issuer<Producer>::value ? 4 : 5)) * 32;
+    return (Producer::kWarps + issuer_warps<Producer>::value + (merged_issuer<Producer>::value ? 4 : 5)) * 32;
 }
 
 struct GemmShape {
@@ -135,11 +141,14 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
-    __shared__ __align__(8) uint64_t raw_full[MAX_RAW_STAGES];
+    __shared__ __align__(8) uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
     __shared__ uint32_t tmem_base_smem;
 
     constexpr int PW = Producer::kWarps;                                     // 4 or 8: epilogue warps PW+1..PW+4 have (warp & 3) = 1,2,3,0
     constexpr bool MG = merged_issuer<Producer>::value;                      // warp PW = issuer AND epilogue of quarter 0
+    constexpr int IW = issuer_warps<Producer>::value;                        // dedicated gather-issue warps PW..PW+IW-1
+    constexpr int MW = PW + IW;                                              // the MMA issuer warp (epilogue warps follow)
+    static_assert(IW == 0 || (Producer::kAsync && !MG && ((MW + 1) & 3) == 1), "issuer warps: async producers, epilogue quarters 1,2,3,0");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);       // 1024-byte aligned tiles
@@ -155,7 +164,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             mbar_init(&empty[s], 1);         // tcgen05.commit
         }
         if constexpr (Producer::kIssuers > 0)
-            for (int r = 0; r < MAX_RAW_STAGES; ++r) mbar_init(&raw_full[r], Producer::kIssuers);   // arrive.expect_tx per issuing thread
+            for (int r = 0; r < MAX_RAW_STAGES; ++r) {
+                mbar_init(&raw_full[r], Producer::kIssuers);
+                mbar_init(&raw_empty[r], PW);                     // (issuer-warp producers) one arrival per converting warp
+            }   // arrive.expect_tx per issuing thread
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);     // tcgen05.commit
             mbar_init(&tmem_empty[a], 4);    // one arrive per epilogue warp
@@ -163,7 +175,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         mbar_fence_init();
     }
     Producer::prologue(pa, tid, (int)blockDim.x);                            // optional CTA-wide staging (before the role split)
-    if (warp == PW) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
+    if (warp == MW) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -190,7 +202,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             auto step = [&](int &t, int &c) { if (++c == nchunks) { c = 0; t += tile_step; } };
             step(nx_tile, nx_chunk);
             int ah_slot = 0, issued = 0;
-            prod.prime(ah_tile, ptid);
+            if constexpr (IW == 0) prod.prime(ah_tile, ptid);
             auto issue_next = [&]() {
                 prod.issue(ah_tile, ah_chunk, nx_tile < ntiles ? nx_tile : -1, raw_base + (size_t)ah_slot * g.raw_bytes,
                            &raw_full[ah_slot], ptid);
@@ -199,8 +211,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 ah_slot = ah_slot + 1 == RAW ? 0 : ah_slot + 1;
                 ++issued;
             };
-            for (int la = 0; la < LA; ++la)
-                if (issued < total) issue_next();
+            if constexpr (IW == 0) {
+                for (int la = 0; la < LA; ++la)
+                    if (issued < total) issue_next();
+            }
             int s = 0, cu_slot = 0;
             uint32_t ph = 0, raw_ph = 0;
             const bool b_resident = g.wchunks == 1;               // one weight chunk: each stage's copy is loaded once
@@ -211,9 +225,11 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 stamp(i, 0);
                 // every producer finished converting i-1: its raw slot may be refilled.  (Reads and cp.async writes are
                 // both generic-proxy accesses: the barrier orders them, no proxy fence is needed here.)
-                asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
-                stamp(i, 1);
-                if (issued < total) issue_next();
+                if constexpr (IW == 0) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
+                    stamp(i, 1);
+                    if (issued < total) issue_next();
+                }
                 stamp(i, 2);
                 mbar_wait(&empty[s], ph ^ 1);
                 stamp(i, 3);
@@ -228,7 +244,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 stamp(i, 5);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_a[s]);
+                if (lane == 0) {
+                    mbar_arrive(&full_a[s]);
+                    if constexpr (IW > 0) mbar_arrive(&raw_empty[cu_slot]);   // the issuers may refill this staging slot
+                }
                 stamp(i, 6);
                 step(cu_tile, cu_chunk);
                 if (++s == g.stages) { s = 0; ph ^= 1; }
@@ -296,7 +315,30 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             }
         }
         }
-    } else if (warp == PW) {
+    } else if (warp < MW) {
+        // ================= gather issuers (kIssuerWarps > 0) =================
+        if constexpr (IW > 0) {
+            const int itid = tid - PW * 32;
+            Producer prod(pa, g);
+            const int RAW = g.raw_stages;
+            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles, nchunks = g.num_chunks;
+            const int total = ((ntiles - (int)blockIdx.x + tile_step - 1) / tile_step) * nchunks;
+            int ah_tile = (int)blockIdx.x, ah_chunk = 0, nx_tile = ah_tile, nx_chunk = 0;
+            auto step = [&](int &t, int &c) { if (++c == nchunks) { c = 0; t += tile_step; } };
+            step(nx_tile, nx_chunk);
+            prod.prime(ah_tile, itid);
+            int slot = 0;
+            uint32_t eph = 0;                                     // parity of the slot's previous hand-back
+            for (int i = 0; i < total; ++i) {
+                if (i >= RAW) mbar_wait(&raw_empty[slot], eph);   // the converters are done with this slot's last use
+                prod.issue(ah_tile, ah_chunk, nx_tile < ntiles ? nx_tile : -1, raw_base + (size_t)slot * g.raw_bytes,
+                           &raw_full[slot], itid);
+                step(ah_tile, ah_chunk);
+                step(nx_tile, nx_chunk);
+                if (++slot == RAW) { slot = 0; if (i >= RAW) eph ^= 1u; }
+            }
+        }
+    } else if (warp == MW) {
         // ================= MMA issuer (+ epilogue of TMEM lane quarter 0 when merged) =================
         const uint32_t idesc = make_idesc_bf16(TILE_M, g.n_pad);
         const uint32_t a_base_u32 = smem_u32(a_base), b_base_u32 = smem_u32(b_base);
@@ -398,7 +440,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
 
     fence_before_sync();
     __syncthreads();
-    if (warp == PW) {
+    if (warp == MW) {
         fence_after_sync();
         tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
     }
