@@ -51,7 +51,8 @@ struct GemmShape {
     int n;                // logical output columns
     int n_pad;            // UMMA N: multiple of 16, 16..256
     int acc_stride;       // TMEM columns per accumulator buffer: round_up(n_pad, 32)
-    int tmem_cols;        // power of two >= 2 * acc_stride
+    int tmem_cols;        // power of two >= nacc * acc_stride
+    int nacc_log2;        // accumulator buffers in TMEM: 4 (log2 = 2) when 4 * acc_stride <= 512 columns, else 2
     int num_chunks;       // pipeline iterations per tile: K chunks of 64 (x neighbour passes of the PointConv producer)
     int wchunks;          // chunks of the packed weight: iteration c uses weight chunk c % wchunks
     int k_total;          // packed K (multiple of 16): K-steps beyond it are skipped
@@ -90,7 +91,8 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.n_pad = (n + 15) / 16 * 16;
     g.acc_stride = (g.n_pad + 31) / 32 * 32;
     int c = 32;
-    while (c < 2 * g.acc_stride) c <<= 1;
+    g.nacc_log2 = 4 * g.acc_stride <= 512 ? 2 : 1;               // more buffers: the MMA runs ahead of a slower epilogue
+    while (c < (g.acc_stride << g.nacc_log2)) c <<= 1;
     g.tmem_cols = c;
     g.k_total = (k_packed + 15) / 16 * 16;
     g.num_chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(num_threads<Producer>(), 1)
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
+    __shared__ __align__(8) uint64_t tmem_full[4], tmem_empty[4];
     __shared__ __align__(8) uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
     __shared__ uint32_t tmem_base_smem;
 
@@ -168,7 +170,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                 mbar_init(&raw_full[r], Producer::kIssuers);
                 mbar_init(&raw_empty[r], PW);                     // (issuer-warp producers) one arrival per converting warp
             }   // arrive.expect_tx per issuing thread
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(&tmem_full[a], 1);     // tcgen05.commit
             mbar_init(&tmem_empty[a], 4);    // one arrive per epilogue warp
         }
@@ -180,6 +182,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t nacc_mask = (1u << g.nacc_log2) - 1u;
 
     if (warp < PW) {
         // ================= A producers =================
@@ -349,8 +352,8 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         long long owed = -1;                                      // merged: work item whose epilogue this warp still owes
         auto run_epilogue = [&](long long w, uint32_t tc) {
             const long long tile = w / g.splits;
-            const uint32_t acc = tc & 1;
-            mbar_wait(&tmem_full[acc], (tc >> 1) & 1);
+            const uint32_t acc = tc & nacc_mask;
+            mbar_wait(&tmem_full[acc], (tc >> g.nacc_log2) & 1);
             fence_after_sync();
             epi.tile(ea, g, tile, (int)(w - tile * g.splits), tmem_base + acc * (uint32_t)g.acc_stride, 0, lane);
             fence_before_sync();
@@ -360,8 +363,8 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
             const int c_begin = (int)(w % g.splits) * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
-            const uint32_t acc = tcount & 1;
-            mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            const uint32_t acc = tcount & nacc_mask;
+            mbar_wait(&tmem_empty[acc], ((tcount >> g.nacc_log2) & 1) ^ 1);
             fence_after_sync();
             const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
             int wc = c_begin % g.wchunks;                         // weight chunk of iteration c
@@ -423,10 +426,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         const long long work = g.num_tiles * g.splits;
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
             const long long tile = w / g.splits;
-            const uint32_t acc = tcount & 1;
+            const uint32_t acc = tcount & nacc_mask;
             const bool tre = g.trace != nullptr && blockIdx.x == 0 && quarter == 1 && lane == 0 && tcount < 200;
             if (tre) g.trace[tcount * 16 + 12] = clock64();
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            mbar_wait(&tmem_full[acc], (tcount >> g.nacc_log2) & 1);
             if (tre) g.trace[tcount * 16 + 13] = clock64();
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
