@@ -367,7 +367,7 @@ def run_kdpc(args):
             # dominant kernel of the step (profiles/: 8 launches, largest single share): the fused PointConv
             "roofline": {"kernel": "tc_gemm_kernel<PointConvProducer<9,1>, StoreEpilogue> (fused PointConv, flow0 shape)",
                          "bound": "tensor", "achieved": pc["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
-                         "frac": pc["tflops"] / tc_peak, "traffic": 44.5e6, "peak_source": peak_src + ", burst bf16",
+                         "frac": pc["tflops"] / tc_peak, "traffic": 84.0e6, "peak_source": peak_src + ", burst bf16",
                          "algorithmic_flops_per_launch": pc["flops"], "algorithmic_bytes_per_launch": pc["bytes"],
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_pointconv.txt)",
                          "note": pc["note"]},
