@@ -137,6 +137,15 @@ static inline size_t split_k_ws_bytes(const GemmShape &g) {
 // Epilogue concept:
 //   struct E { struct Args {...};
 //              __device__ void tile(const Args&, const GemmShape&, long long tile, int split, uint32_t tmem_acc, int quarter, int lane); };
+// work item -> (tile, split): work items are < 2^31 (checked by the launchers' shapes) and almost always splits == 1; a
+// 64-bit division per tile in the single-warp MMA / epilogue loops cost ~1000 cycles of dependent integer code
+__device__ __forceinline__ void work_item(long long w, int splits, long long &tile, int &split) {
+    if (splits == 1) { tile = w; split = 0; return; }
+    const unsigned t = (unsigned)w / (unsigned)splits;
+    tile = t;
+    split = (int)((unsigned)w - t * (unsigned)splits);
+}
+
 template <class Producer, class Epilogue>
 __global__ void __launch_bounds__(num_threads<Producer>(), 1)
 tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
@@ -262,8 +271,10 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         uint32_t ol_ph = 0;
         const long long work = g.num_tiles * g.splits;
         for (long long w = blockIdx.x; w < work; w += gridDim.x) {
-            const long long tile = w / g.splits;
-            const int c_begin = (int)(w - tile * g.splits) * g.chunks_per_split;
+            long long tile;
+            int split_;
+            work_item(w, g.splits, tile, split_);
+            const int c_begin = split_ * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             if constexpr (owns_loop<Producer>::value) {
                 // the producer drives the K loop of its tile itself (tight inner loops with its state in registers):
@@ -295,7 +306,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
                     if (++ol_s == g.stages) { ol_s = 0; ol_ph ^= 1u; }
                     if (++ol_wc == g.wchunks) ol_wc = 0;
                 };
-                ol_wc = c_begin % g.wchunks;
+                ol_wc = c_begin == 0 ? 0 : c_begin % g.wchunks;
                 prod.run_tile(tile, c_begin, c_end, ptid, raw_base, raw_full, acquire, release);
             } else {
             bool began = false;
@@ -351,23 +362,30 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         Epilogue epi;
         long long owed = -1;                                      // merged: work item whose epilogue this warp still owes
         auto run_epilogue = [&](long long w, uint32_t tc) {
-            const long long tile = w / g.splits;
+            long long tile;
+            int split_;
+            work_item(w, g.splits, tile, split_);
             const uint32_t acc = tc & nacc_mask;
             mbar_wait(&tmem_full[acc], (tc >> g.nacc_log2) & 1);
             fence_after_sync();
-            epi.tile(ea, g, tile, (int)(w - tile * g.splits), tmem_base + acc * (uint32_t)g.acc_stride, 0, lane);
+            epi.tile(ea, g, tile, split_, tmem_base + acc * (uint32_t)g.acc_stride, 0, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         };
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
-            const int c_begin = (int)(w % g.splits) * g.chunks_per_split;
+            if (g.trace != nullptr && blockIdx.x == 0 && lane == 0 && it < 200) g.trace[it * 16 + 7] = clock64();
+            long long tile_;
+            int split_;
+            work_item(w, g.splits, tile_, split_);
+            const int c_begin = split_ * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             const uint32_t acc = tcount & nacc_mask;
             mbar_wait(&tmem_empty[acc], ((tcount >> g.nacc_log2) & 1) ^ 1);
+            if (g.trace != nullptr && blockIdx.x == 0 && lane == 0 && it < 200) g.trace[it * 16 + 15] = clock64();
             fence_after_sync();
             const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
-            int wc = c_begin % g.wchunks;                         // weight chunk of iteration c
+            int wc = c_begin == 0 ? 0 : c_begin % g.wchunks;      // weight chunk of iteration c
             for (int c = c_begin; c < c_end; ++c, ++it) {
                 const int s = ms;
                 const uint32_t ph = mph;
@@ -425,7 +443,9 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
         uint32_t tcount = 0;
         const long long work = g.num_tiles * g.splits;
         for (long long w = blockIdx.x; w < work; w += gridDim.x, ++tcount) {
-            const long long tile = w / g.splits;
+            long long tile;
+            int split_;
+            work_item(w, g.splits, tile, split_);
             const uint32_t acc = tcount & nacc_mask;
             const bool tre = g.trace != nullptr && blockIdx.x == 0 && quarter == 1 && lane == 0 && tcount < 200;
             if (tre) g.trace[tcount * 16 + 12] = clock64();
@@ -433,7 +453,7 @@ tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typena
             if (tre) g.trace[tcount * 16 + 13] = clock64();
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
-            epi.tile(ea, g, tile, (int)(w - tile * g.splits), t_acc, quarter, lane);
+            epi.tile(ea, g, tile, split_, t_acc, quarter, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

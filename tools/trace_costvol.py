@@ -28,7 +28,7 @@ f(); torch.cuda.synchronize()
 L.kdpc_tc_set_trace(None)
 t = tr.cpu().view(200, 16)
 t0 = int(t[0, 0])
-print("it | producer w0: top synced issued stage_free raw_ready converted arrived | mma: wait_start full_a full_b issued | epilogue q1: wait_start tmem_full done")
+print("it | producer w0: top synced issued stage_free raw_ready converted arrived | mma: tile_top tmem_free wait_start full_a full_b issued | epilogue q1: wait_start tmem_full done")
 for i in list(range(0, 8)) + list(range(40, 60)):
     r = [int(x) - t0 if int(x) else -1 for x in t[i, :16]]
-    print(f"{i:3d} | " + " ".join(f"{v:7d}" for v in r[0:7]) + " | " + " ".join(f"{v:7d}" for v in r[8:12]) + " | " + " ".join(f"{v:7d}" for v in r[12:15]))
+    print(f"{i:3d} | " + " ".join(f"{v:7d}" for v in r[0:7]) + " | " + f"{r[7]:7d} {r[15]:7d} " + " ".join(f"{v:7d}" for v in r[8:12]) + " | " + " ".join(f"{v:7d}" for v in r[12:15]))
