@@ -681,17 +681,23 @@ struct PlainAsyncProducer {
     const GemmShape &g;
     __device__ PlainAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
     __device__ __forceinline__ void prime(int, int) {}
+    // 16 consecutive lanes copy the (up to) 256 contiguous bytes of ONE row's chunk slice, thread t serves rows
+    // (t >> 4) + 16 j: a warp-level LDGSTS touches 4 lines.  (One thread per row-half copying its pieces one after the
+    // other made every request touch 32 lines - the load/store unit then needs ~28 cycles per request, see costvol_tc.cu.)
     __device__ __forceinline__ void issue(int tile, int chunk, int /*next_tile*/, unsigned char *raw, uint64_t *bar, int ptid) {
-        const int r = ptid & 127, half = ptid >> 7;
-        long long row = (long long)tile * TILE_M + r;
-        if (row >= g.m) row = g.m - 1;                       // padded rows repeat the last row; never stored
-        const int k0 = chunk * CHUNK_K + half * 32;
-        const int pieces = max(0, min(32, a.k - k0)) >> 2;
-        const float *src = a.x + row * a.ldx + k0;
-        const uint32_t dst = smem_u32(raw + r * ROW_PITCH + half * 128);
+        const int q = ptid & 15, rb = ptid >> 4;
+        const int k0 = chunk * CHUNK_K;
+        const int pieces = max(0, min(CHUNK_K, a.k - k0)) >> 2;
+        const long long row0 = (long long)tile * TILE_M;
+        if (q < pieces) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (e < pieces) cp_async_16(dst + e * 16, src + e * 4);
+            for (int j = 0; j < 8; ++j) {
+                const int r = rb + 16 * j;
+                long long row = row0 + r;
+                if (row >= g.m) row = g.m - 1;               // padded rows repeat the last row; never stored
+                cp_async_16(smem_u32(raw + r * ROW_PITCH + q * 16), a.x + row * a.ldx + k0 + q * 4);
+            }
+        }
         cp_async_mbar_arrive(bar);
     }
     __device__ __forceinline__ void convert(int /*tile*/, int chunk, const unsigned char *raw, unsigned char *a_hi,
