@@ -672,7 +672,9 @@ struct PlainProducer {
 struct PlainAsyncProducer {
     static constexpr int kWarps = 8, kGroups = 1;
     static constexpr bool kAsync = true;
-    static constexpr int kIssuers = 256, kLookahead = 2;
+    static constexpr int kIssuerWarps = 0;                   // dedicated issue warps: measured neutral for these streaming rows (4 tried)
+    static constexpr int kIssueThreads = kIssuerWarps > 0 ? 32 * kIssuerWarps : 256;
+    static constexpr int kIssuers = kIssueThreads, kLookahead = 2;
     static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
     static constexpr int kRawBytes = TILE_M * ROW_PITCH;
     using Args = PlainProducer::Args;
@@ -682,7 +684,7 @@ struct PlainAsyncProducer {
     __device__ PlainAsyncProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
     __device__ __forceinline__ void prime(int, int) {}
     // 16 consecutive lanes copy the (up to) 256 contiguous bytes of ONE row's chunk slice, thread t serves rows
-    // (t >> 4) + 16 j: a warp-level LDGSTS touches 4 lines.  (One thread per row-half copying its pieces one after the
+    // (t >> 4) + RSTEP j: a warp-level LDGSTS touches 4 lines.  (One thread per row-half copying its pieces one after the
     // other made every request touch 32 lines - the load/store unit then needs ~28 cycles per request, see costvol_tc.cu.)
     __device__ __forceinline__ void issue(int tile, int chunk, int /*next_tile*/, unsigned char *raw, uint64_t *bar, int ptid) {
         const int q = ptid & 15, rb = ptid >> 4;
@@ -690,9 +692,10 @@ struct PlainAsyncProducer {
         const int pieces = max(0, min(CHUNK_K, a.k - k0)) >> 2;
         const long long row0 = (long long)tile * TILE_M;
         if (q < pieces) {
+            constexpr int RSTEP = kIssueThreads / 16;        // rows covered by one pass of the issuing threads
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = rb + 16 * j;
+            for (int j = 0; j < TILE_M / RSTEP; ++j) {
+                const int r = rb + RSTEP * j;
                 long long row = row0 + r;
                 if (row >= g.m) row = g.m - 1;               // padded rows repeat the last row; never stored
                 cp_async_16(smem_u32(raw + r * ROW_PITCH + q * 16), a.x + row * a.ldx + k0 + q * 4);
