@@ -78,6 +78,21 @@ def test_kernel_full_size_and_meter():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(1, 1), (3, 1001), (2, 37), (5, 4099)])
+def test_kernel_ragged_sizes(B, N):
+    from kd_pointcloud_b200 import evaluation_utils as E
+    g = torch.Generator().manual_seed(B * 100 + N)
+    pc1 = torch.rand(B, N, 3, generator=g) * 20 + torch.tensor([0.0, 0.0, 5.0])
+    gt = torch.randn(B, N, 3, generator=g) * 0.5
+    pred = gt + torch.randn(B, N, 3, generator=g) * 0.1
+    calib = torch.tensor([[-721.5, 609.6, 172.9, 44.9, 0.22, 0.0027]]).repeat(B, 1)
+    for cal in (None, calib):
+        ref = O.scene_flow_metrics(pc1.numpy(), pred.numpy(), gt.numpy(), None if cal is None else cal.numpy())
+        m = E.scene_flow_metrics(pc1.cuda(), pred.permute(0, 2, 1).contiguous().cuda(), gt.cuda(), None if cal is None else cal.cuda())
+        _check(m, ref, B * N)
+
+
+@pytest.mark.gpu
 def test_kernel_rejects_bad_shapes():
     from kd_pointcloud_b200 import evaluation_utils as E
     dev = "cuda:0"
