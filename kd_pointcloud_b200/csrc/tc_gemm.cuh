@@ -110,7 +110,9 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
 
 // Split-K for small-M / large-K layers (a handful of 128-row tiles would otherwise leave most SMs idle while each
 // CTA walks >100 K-chunks): partial accumulators go to a workspace [splits][M][n_pad] and splitk_reduce_kernel adds
-// them in split order (deterministic) and applies the epilogue.
+// them in split order (deterministic) and applies the epilogue.  (Fusing that reduction into the GEMM - the last work item of
+// a tile to finish sums the partials - was measured 10 % slower end to end: one warp per tile quarter then walks
+// splits x 32 rows of L2 reads on the kernel's critical path.)
 static inline void plan_split_k(GemmShape &g) {
     g.splits = 1;
     g.chunks_per_split = g.num_chunks;
