@@ -160,7 +160,16 @@ def knn_point(nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.T
 
 
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
-    return K.square_distance(src.detach().contiguous(), dst.detach().contiguous())
+    """pointconv_util.square_distance (pointconv_util.py:73-94): [B,S,3], [B,N,3] -> [B,S,N], the kernel's values (the
+    reference's rounding).  Differentiable like the reference's torch expression when an input requires a gradient
+    (the self-supervised losses of models_bid_pointconv.py:574-638 use the distances by value): the gradient is that
+    of the same expansion, attached to the kernel's values."""
+    hard = K.square_distance(src.detach().contiguous(), dst.detach().contiguous())
+    if not (torch.is_grad_enabled() and (src.requires_grad or dst.requires_grad)):
+        return hard
+    soft = -2 * torch.matmul(src, dst.permute(0, 2, 1))
+    soft = soft + torch.sum(src ** 2, -1).unsqueeze(2) + torch.sum(dst ** 2, -1).unsqueeze(1)
+    return soft + (hard - soft).detach()
 
 
 def _csr(idx: torch.Tensor, n: int):

@@ -353,3 +353,20 @@ def test_pointconv_agg_grad_matches_fp64(B, S, Kn, C):
     w2 = wn.detach().clone().requires_grad_(True)
     KF.pointconv_agg(grouped.detach(), w2).backward(go)
     assert torch.equal(w2.grad, wn.grad)
+
+
+@pytest.mark.gpu
+def test_square_distance_is_differentiable_like_the_reference():
+    from kd_pointcloud_b200 import functional as KF
+    torch.manual_seed(3)
+    src = (torch.rand(2, 50, 3, device="cuda:0") * 10).requires_grad_(True)
+    dst = (torch.rand(2, 70, 3, device="cuda:0") * 10).requires_grad_(True)
+    d = KF.square_distance(src, dst)
+    assert torch.equal(d.detach(), KF.square_distance(src.detach(), dst.detach()))      # the kernel's values
+    w = torch.randn_like(d)
+    (d * w).sum().backward()
+    s2, d2 = src.detach().double().requires_grad_(True), dst.detach().double().requires_grad_(True)
+    ref = ((s2.unsqueeze(2) - d2.unsqueeze(1)) ** 2).sum(-1)
+    (ref * w.double()).sum().backward()
+    assert ((src.grad.double() - s2.grad).abs().max() / s2.grad.abs().max()).item() < 1e-4
+    assert ((dst.grad.double() - d2.grad).abs().max() / d2.grad.abs().max()).item() < 1e-4
