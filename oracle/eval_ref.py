@@ -9,26 +9,28 @@ unmodified reference functions (run with the alias restored) by tests/make_golde
 import numpy as np
 
 
+def _fraction(mask) -> float:
+    return mask.astype(np.float64).mean()
+
+
+def _errors(pred, gt, eps):
+    """per-point error norm and error relative to the ground-truth norm (+eps), float32 like the reference"""
+    err = np.linalg.norm(gt - pred, axis=-1)
+    return err, err / (np.linalg.norm(gt, axis=-1) + eps)
+
+
 def evaluate_3d(sf_pred, sf_gt):
-    """evaluation_utils.py:17-33.  sf_pred, sf_gt: (..., 3) float32 -> EPE3D, Acc3DS, Acc3DR, Outliers3D."""
-    l2_norm = np.linalg.norm(sf_gt - sf_pred, axis=-1)
-    EPE3D = l2_norm.mean()
-    sf_norm = np.linalg.norm(sf_gt, axis=-1)
-    relative_err = l2_norm / (sf_norm + 1e-4)
-    acc3d_strict = (np.logical_or(l2_norm < 0.05, relative_err < 0.05)).astype(np.float64).mean()
-    acc3d_relax = (np.logical_or(l2_norm < 0.1, relative_err < 0.1)).astype(np.float64).mean()
-    outlier = (np.logical_or(l2_norm > 0.3, relative_err > 0.1)).astype(np.float64).mean()
-    return EPE3D, acc3d_strict, acc3d_relax, outlier
+    """evaluation_utils.py:17-33.  (..., 3) float32 -> EPE3D, Acc3DS (5 cm or 5 %), Acc3DR (10 cm or 10 %),
+    Outliers3D (> 30 cm or > 10 %)."""
+    err, rel = _errors(sf_pred, sf_gt, 1e-4)
+    return (err.mean(), _fraction((err < 0.05) | (rel < 0.05)), _fraction((err < 0.1) | (rel < 0.1)),
+            _fraction((err > 0.3) | (rel > 0.1)))
 
 
 def evaluate_2d(flow_pred, flow_gt):
-    """evaluation_utils.py:36-50.  (..., 2) float32 -> EPE2D, Acc2D."""
-    epe2d = np.linalg.norm(flow_gt - flow_pred, axis=-1)
-    epe2d_mean = epe2d.mean()
-    flow_gt_norm = np.linalg.norm(flow_gt, axis=-1)
-    relative_err = epe2d / (flow_gt_norm + 1e-5)
-    acc2d = (np.logical_or(epe2d < 3., relative_err < 0.05)).astype(np.float64).mean()
-    return epe2d_mean, acc2d
+    """evaluation_utils.py:36-50.  (..., 2) float32 -> EPE2D, Acc2D (3 px or 5 %)."""
+    err, rel = _errors(flow_pred, flow_gt, 1e-5)
+    return err.mean(), _fraction((err < 3.) | (rel < 0.05))
 
 
 def project_3d_to_2d(pc, f=-1050., cx=479.5, cy=269.5, constx=0, consty=0, constz=0):

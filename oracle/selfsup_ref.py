@@ -9,52 +9,50 @@ import torch
 from .layers_ref import index_points_group, square_distance
 
 
+def _pm(x):
+    return x.permute(0, 2, 1)
+
+
+def _nearest(query_pm, cand_pm, k):
+    """the reference's neighbour search: full square_distance matrix + unsorted topk -> (dist, idx) [B,S,k]"""
+    return torch.topk(square_distance(query_pm, cand_pm), k, dim=-1, largest=False, sorted=False)
+
+
+def _laplacian(neigh_of_pm, values_pm):
+    """sum over the 10 nearest neighbours (found in ``neigh_of_pm``) of (value_j - value_i), / 9  (:565-572, :592-599)"""
+    _, kidx = _nearest(neigh_of_pm, neigh_of_pm, 10)
+    return torch.sum(index_points_group(values_pm, kidx) - values_pm.unsqueeze(2), dim=2) / 9.0
+
+
 def curvature(pc):
     """:565-572.  pc [B,3,N] -> [B,N,3]"""
-    pc = pc.permute(0, 2, 1)
-    sqrdist = square_distance(pc, pc)
-    _, kidx = torch.topk(sqrdist, 10, dim=-1, largest=False, sorted=False)
-    grouped_pc = index_points_group(pc, kidx)
-    return torch.sum(grouped_pc - pc.unsqueeze(2), dim=2) / 9.0
+    return _laplacian(_pm(pc), _pm(pc))
+
+
+def curvature_warp(pc, warped_pc):
+    """:592-599: neighbourhoods of pc, coordinates of warped_pc"""
+    return _laplacian(_pm(pc), _pm(warped_pc))
 
 
 def compute_chamfer(pc1, pc2):
-    """:574-590.  pc1 [B,3,N], pc2 [B,3,M] -> dist1 [B,N], dist2 [B,M]"""
-    pc1 = pc1.permute(0, 2, 1)
-    pc2 = pc2.permute(0, 2, 1)
-    sqrdist12 = square_distance(pc1, pc2)
+    """:574-590.  pc1 [B,3,N], pc2 [B,3,M] -> dist1 [B,N], dist2 [B,M]: row / column minima of ONE distance matrix"""
+    sqrdist12 = square_distance(_pm(pc1), _pm(pc2))
     dist1, _ = torch.topk(sqrdist12, 1, dim=-1, largest=False, sorted=False)
     dist2, _ = torch.topk(sqrdist12, 1, dim=1, largest=False, sorted=False)
     return dist1.squeeze(2), dist2.squeeze(1)
 
 
-def curvature_warp(pc, warped_pc):
-    """:592-599"""
-    warped_pc = warped_pc.permute(0, 2, 1)
-    pc = pc.permute(0, 2, 1)
-    sqrdist = square_distance(pc, pc)
-    _, kidx = torch.topk(sqrdist, 10, dim=-1, largest=False, sorted=False)
-    grouped_pc = index_points_group(warped_pc, kidx)
-    return torch.sum(grouped_pc - warped_pc.unsqueeze(2), dim=2) / 9.0
-
-
 def compute_smooth(pc1, pred_flow):
-    """:601-616"""
-    pc1 = pc1.permute(0, 2, 1)
-    pred_flow = pred_flow.permute(0, 2, 1)
-    sqrdist = square_distance(pc1, pc1)
-    _, kidx = torch.topk(sqrdist, 9, dim=-1, largest=False, sorted=False)
-    grouped_flow = index_points_group(pred_flow, kidx)
-    return torch.norm(grouped_flow - pred_flow.unsqueeze(2), dim=3).sum(dim=2) / 8.0
+    """:601-616 -> [B,N]: mean distance of a point's flow to the flows of its 9 nearest neighbours (self included), / 8"""
+    flow = _pm(pred_flow)
+    _, kidx = _nearest(_pm(pc1), _pm(pc1), 9)
+    return torch.norm(index_points_group(flow, kidx) - flow.unsqueeze(2), dim=3).sum(dim=2) / 8.0
 
 
 def interpolate_curvature(pc1, pc2, pc2_curvature):
-    """:618-638.  pc2_curvature [B,M,3] (point-major, as `curvature` returns it)"""
+    """:618-638.  pc2_curvature [B,M,3] (point-major, as `curvature` returns it): inverse squared-distance weights over 5"""
     B, _, N = pc1.shape
-    pc1 = pc1.permute(0, 2, 1)
-    pc2 = pc2.permute(0, 2, 1)
-    sqrdist12 = square_distance(pc1, pc2)
-    dist, knn_idx = torch.topk(sqrdist12, 5, dim=-1, largest=False, sorted=False)
+    dist, knn_idx = _nearest(_pm(pc1), _pm(pc2), 5)
     grouped = index_points_group(pc2_curvature, knn_idx)
     norm = torch.sum(1.0 / (dist + 1e-8), dim=2, keepdim=True)
     weight = (1.0 / (dist + 1e-8)) / norm
