@@ -78,27 +78,31 @@ def interpolateCurvature(pc1: torch.Tensor, pc2: torch.Tensor, pc2_curvature: to
     return (weight.unsqueeze(-1) * KF.gather_rows(pc2_curvature.contiguous(), idx)).sum(dim=2)
 
 
+SCALE_WEIGHTS = (0.02, 0.04, 0.08, 0.16)       # alpha per pyramid level, finest first (:649)
+TERM_WEIGHTS = {"chamfer": 1.0, "curvature": 0.3, "smoothness": 1.0}     # f_chamfer, f_curvature, f_smoothness (:641-643)
+
+
+def _scale_terms(p1: torch.Tensor, p2: torch.Tensor, flow: torch.Tensor):
+    """chamfer, curvature and smoothness terms of ONE pyramid level (:657-673), each a 0-dim tensor (batch mean of
+    per-cloud sums)."""
+    warped = p1 + flow
+    d12, d21 = computeChamfer(warped, p2)
+    chamfer = d12.sum(dim=1).mean() + d21.sum(dim=1).mean()
+    smooth = computeSmooth(p1, flow).sum(dim=1).mean()
+    target = interpolateCurvature(warped, p2, curvature(p2))
+    curv = ((target - curvatureWarp(p1, warped)) ** 2).sum(dim=2).sum(dim=1).mean()
+    return chamfer, curv, smooth
+
+
 def multiScaleChamferSmoothCurvature(pc1: Sequence[torch.Tensor], pc2: Sequence[torch.Tensor],
                                      pred_flows: Sequence[torch.Tensor]):
-    """:640-677.  Lists of [B,3,N_i] tensors -> (total, chamfer, curvature, smoothness), each of shape [1]."""
-    f_curvature, f_smoothness, f_chamfer = 0.3, 1.0, 1.0
-    alpha = [0.02, 0.04, 0.08, 0.16]
+    """:640-677.  Lists of [B,3,N_i] tensors (finest first) -> (total, chamfer, curvature, smoothness), each of shape [1]."""
     dev = pred_flows[0].device
-    chamfer_loss = torch.zeros(1, device=dev)
-    smoothness_loss = torch.zeros(1, device=dev)
-    curvature_loss = torch.zeros(1, device=dev)
-    for i in range(len(pred_flows)):
-        cur_pc1, cur_pc2, cur_flow = pc1[i], pc2[i], pred_flows[i]
-        cur_pc2_curvature = curvature(cur_pc2)
-        cur_pc1_warp = cur_pc1 + cur_flow
-        dist1, dist2 = computeChamfer(cur_pc1_warp, cur_pc2)
-        moved_pc1_curvature = curvatureWarp(cur_pc1, cur_pc1_warp)
-        chamferLoss = dist1.sum(dim=1).mean() + dist2.sum(dim=1).mean()
-        smoothnessLoss = computeSmooth(cur_pc1, cur_flow).sum(dim=1).mean()
-        inter_pc2_curvature = interpolateCurvature(cur_pc1_warp, cur_pc2, cur_pc2_curvature)
-        curvatureLoss = torch.sum((inter_pc2_curvature - moved_pc1_curvature) ** 2, dim=2).sum(dim=1).mean()
-        chamfer_loss = chamfer_loss + alpha[i] * chamferLoss
-        smoothness_loss = smoothness_loss + alpha[i] * smoothnessLoss
-        curvature_loss = curvature_loss + alpha[i] * curvatureLoss
-    total_loss = f_chamfer * chamfer_loss + f_curvature * curvature_loss + f_smoothness * smoothness_loss
-    return total_loss, chamfer_loss, curvature_loss, smoothness_loss
+    sums = [torch.zeros(1, device=dev) for _ in range(3)]
+    for level, flow in enumerate(pred_flows):
+        for acc_i, term in enumerate(_scale_terms(pc1[level], pc2[level], flow)):
+            sums[acc_i] = sums[acc_i] + SCALE_WEIGHTS[level] * term
+    chamfer_loss, curvature_loss, smoothness_loss = sums
+    total = (TERM_WEIGHTS["chamfer"] * chamfer_loss + TERM_WEIGHTS["curvature"] * curvature_loss
+             + TERM_WEIGHTS["smoothness"] * smoothness_loss)
+    return total, chamfer_loss, curvature_loss, smoothness_loss
