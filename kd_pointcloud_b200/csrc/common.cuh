@@ -29,7 +29,20 @@ static inline long long div_up_ll(long long a, long long b) { return (a + b - 1)
 
 namespace kdpc {
 
-constexpr int kNumSMs = 148;   // B200
+// SM count of the CURRENT device, queried once per device (148 on a B200): grids of the persistent kernels and the
+// split-K / queries-per-warp plans are sized from it.
+static inline int num_sms() {
+    static int cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 
 // ---- exact-rounding fp32 helpers: never contracted or re-associated by nvcc ----------------
 __device__ __forceinline__ float sq_norm3(float x, float y, float z) {

@@ -357,7 +357,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
             const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
             auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
             KDPC_ENSURE_SMEM(kern, SMEM_BUDGET + 1024);
-            const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+            const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
             kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
             KDPC_RETURN_LAST();
         }
@@ -367,7 +367,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
     const size_t smem = smem_bytes(g.n_pad, g.stages);
     auto kern = tc_gemm_kernel<CostVolProducer, MaxKEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
-    const unsigned grid = (unsigned)(g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs);
+    const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
     kern<<<grid, num_threads<CostVolProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
     KDPC_RETURN_LAST();
 }

@@ -214,7 +214,7 @@ KDPC_API int kdpc_group(int b, int c, int n, int s, int k, const float *f, const
         KDPC_ENSURE_SMEM((group_cm_smem_kernel<CPB>), 200 * 1024);
         const int cgroups = (c + CPB - 1) / CPB;
         // enough CTAs to cover the 148 SMs, but each one must amortise staging its channel rows
-        int split = (2 * kNumSMs + cgroups * b - 1) / (cgroups * b);
+        int split = (2 * num_sms() + cgroups * b - 1) / (cgroups * b);
         split = max(1, min(split, (sk + 8191) / 8192));
         const int chunk = (sk + split - 1) / split;
         dim3 grid(split, cgroups, b);

@@ -151,7 +151,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
             KDPC_ENSURE_SMEM(kern_a, SMEM_BUDGET + 1024);
             P::Args pa{x, ldx, k};
             StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
-            const unsigned grid = (unsigned)(ga.num_tiles < kNumSMs ? ga.num_tiles : kNumSMs);
+            const unsigned grid = (unsigned)(ga.num_tiles < num_sms() ? ga.num_tiles : num_sms());
             kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
             KDPC_RETURN_LAST();
         }
@@ -162,7 +162,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
     PlainProducer::Args pa{x, ldx, k};
     StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, reinterpret_cast<float *>(ws)};
     const long long work = g.num_tiles * g.splits;
-    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
+    const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
     kern<<<grid, num_threads<PlainProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
     if (g.splits > 1) return launch_splitk_reduce(g, ea, to_stream(stream));
     KDPC_RETURN_LAST();

@@ -16,7 +16,8 @@
 namespace kdpc {
 
 constexpr int LOSS_THREADS = 256;
-constexpr int LOSS_BLOCKS = 148;
+constexpr int LOSS_BLOCKS = 256;       // workspace capacity (partials); the grid is min(SM count, LOSS_BLOCKS)
+static inline int loss_grid() { int n = num_sms(); return n < LOSS_BLOCKS ? n : LOSS_BLOCKS; }
 constexpr int LOSS_MAX_SCALES = 4;
 constexpr int LOSS_MAX_TARGETS = 2;
 
@@ -144,7 +145,7 @@ KDPC_API int kdpc_flow_loss(int b, int nscales, int point_major, const int *n, c
     }
     float *partials = reinterpret_cast<float *>(ws);
     unsigned *counter = reinterpret_cast<unsigned *>(ws) + LOSS_BLOCKS;
-    flow_loss_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, to_stream(stream)>>>(a, partials, counter, loss);
+    flow_loss_kernel<<<loss_grid(), LOSS_THREADS, 0, to_stream(stream)>>>(a, partials, counter, loss);
     KDPC_RETURN_LAST();
 }
 
@@ -153,6 +154,6 @@ KDPC_API int kdpc_hint_loss(long long n, const float *fs, const float *ft, float
     KDPC_CHECK_ARGS(fs && ft && ws && loss && n > 0);
     float *partials = reinterpret_cast<float *>(ws);
     unsigned *counter = reinterpret_cast<unsigned *>(ws) + LOSS_BLOCKS;
-    hint_loss_kernel<<<LOSS_BLOCKS, LOSS_THREADS, 0, to_stream(stream)>>>(n, fs, ft, weight, grad_fs, partials, counter, loss);
+    hint_loss_kernel<<<loss_grid(), LOSS_THREADS, 0, to_stream(stream)>>>(n, fs, ft, weight, grad_fs, partials, counter, loss);
     KDPC_RETURN_LAST();
 }

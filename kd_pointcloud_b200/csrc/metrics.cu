@@ -16,7 +16,8 @@
 namespace kdpc {
 
 constexpr int MET_THREADS = 256;
-constexpr int MET_BLOCKS = 148;
+constexpr int MET_BLOCKS = 256;        // workspace capacity (partials); the grid is min(SM count, MET_BLOCKS)
+static inline int met_grid() { int n = num_sms(); return n < MET_BLOCKS ? n : MET_BLOCKS; }
 
 struct MetricPartial {
     double l2, epe2d;
@@ -130,7 +131,7 @@ KDPC_API int kdpc_flow_metrics(int b, int n, int point_major, const float *pred,
     if ((reinterpret_cast<uintptr_t>(ws) % 8) != 0) return KDPC_EINVAL;
     MetricPartial *partials = reinterpret_cast<MetricPartial *>(ws);
     unsigned *counter = reinterpret_cast<unsigned *>(partials + MET_BLOCKS);
-    flow_metrics_kernel<<<MET_BLOCKS, MET_THREADS, 0, to_stream(stream)>>>(b, n, point_major ? 1 : 0, pred, gt, pc1, calib,
+    flow_metrics_kernel<<<met_grid(), MET_THREADS, 0, to_stream(stream)>>>(b, n, point_major ? 1 : 0, pred, gt, pc1, calib,
                                                                          partials, counter, out);
     KDPC_RETURN_LAST();
 }

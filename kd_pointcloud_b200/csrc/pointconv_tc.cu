@@ -354,7 +354,7 @@ static int launch_pointconv(long long m, int n_out, const typename PointConvProd
     auto kern = tc_gemm_kernel<P, StoreEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
     const long long work = g.num_tiles * g.splits;
-    const unsigned grid = (unsigned)(work < kNumSMs ? work : kNumSMs);
+    const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
     kern<<<grid, num_threads<P>(), smem, st>>>(g, pa, ea);
     if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
     return (int)cudaGetLastError();

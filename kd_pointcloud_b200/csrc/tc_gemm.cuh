@@ -116,8 +116,9 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
 static inline void plan_split_k(GemmShape &g) {
     g.splits = 1;
     g.chunks_per_split = g.num_chunks;
-    if (g.num_tiles * 2 > 148 || g.num_chunks < 4) return;
-    int want = (int)(148 / g.num_tiles);
+    const int sms = num_sms();
+    if (g.num_tiles * 2 > sms || g.num_chunks < 4) return;
+    int want = (int)(sms / g.num_tiles);
     if (want > g.num_chunks / 2) want = g.num_chunks / 2;       // >= 2 chunks per work item
     if (want > 16) want = 16;
     if (want < 2) return;

@@ -31,6 +31,33 @@ def _tkey(t: torch.Tensor):
     return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index)
 
 
+# Weights can change WITHOUT their ``_version`` moving: a CUDA-graph replay of a training step (training.GraphedKDStep)
+# updates parameters and BatchNorm statistics on the device only.  Everything derived from weights (packed bf16 images,
+# folded BN affines, WeightNet host parameters) is therefore also keyed by this epoch, which graph owners bump after
+# every replay (bump_weight_epoch): a later eager / eval forward re-derives instead of hitting a stale entry.
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch() -> int:
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+    return _WEIGHT_EPOCH
+
+
+def _wkey(t: torch.Tensor):
+    return _tkey(t) + (_WEIGHT_EPOCH,)
+
+
+def weight_cache_tensors():
+    """Every device tensor the weight-derived caches currently own (graph owners keep these alive: a captured graph
+    bakes in the addresses of cache hits, and an LRU eviction or clear_caches(weights=True) must not free them)."""
+    out = []
+    for cache in (_PACK_CACHE, _AFFINE_CACHE):
+        for v in cache.d.values():
+            out.extend(t for t in v if isinstance(t, torch.Tensor))
+    return out
+
+
 class _LRU:
     def __init__(self, cap: int):
         self.cap = cap
@@ -353,9 +380,9 @@ _PACK_CACHE = _LRU(512)
 _AFFINE_CACHE = _LRU(512)
 
 
-def _packed_weight(w2d: torch.Tensor, mode: int = 0, d: int = 0, wn: int = 0) -> torch.Tensor:
+def _packed_weight_cached(w2d: torch.Tensor, mode: int = 0, d: int = 0, wn: int = 0) -> torch.Tensor:
     """bf16 hi/lo chunk images of a [N,K] weight, cached per (storage, version)."""
-    key = (mode, d, wn, _tkey(w2d))
+    key = (mode, d, wn, _wkey(w2d))
     hit = _PACK_CACHE.get(key)
     if hit is not None:
         return hit[0]
@@ -364,13 +391,16 @@ def _packed_weight(w2d: torch.Tensor, mode: int = 0, d: int = 0, wn: int = 0) ->
     return packed
 
 
+_packed_weight = _packed_weight_cached
+
+
 def _fold_affine(bias: Optional[torch.Tensor], bn: Optional[torch.nn.Module]):
     """(scale, shift) of the epilogue: Linear bias and eval-mode BatchNorm folded together,
     y = (x W^T + b - mean) * gamma / sqrt(var + eps) + beta."""
     if bn is None:
         return None, (None if bias is None else bias.detach())
     parts = (bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    key = tuple(None if t is None else _tkey(t) for t in parts) + (bn.eps,)
+    key = tuple(None if t is None else _wkey(t) for t in parts) + (bn.eps,)
     hit = _AFFINE_CACHE.get(key)
     if hit is not None:
         return hit[0], hit[1]
@@ -402,7 +432,7 @@ def fused_linear_available(x: torch.Tensor, weight: torch.Tensor, bias, bn) -> b
 
 def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
                  bn: Optional[torch.nn.Module] = None, slope: float = 1.0, clamp=None,
-                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 residual: Optional[torch.Tensor] = None, cache_weight: bool = True) -> torch.Tensor:
     """y[..., N] = clamp(leaky(bn(x[..., K] W^T + b), slope)) + residual in ONE kernel.
     weight [N,K] (nn.Linear) or [N,K,1(,1)] (1x1 conv)."""
     w2d = weight.reshape(weight.shape[0], -1)
@@ -411,6 +441,7 @@ def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     scale, shift = _fold_affine(bias, bn)
     lo, hi = (1.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
     res = None if residual is None else residual.contiguous()
+    _packed_weight = _packed_weight_cached if cache_weight else (lambda w: K.pack_weight(w.detach().contiguous(), 0, 0, 0))
     if k < 16 or n < 16 or k % 4 != 0:
         return K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
     if n <= 256:
@@ -448,7 +479,7 @@ class _LinearTC(torch.autograd.Function):
         gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = fused_linear(gy, w2d.detach().t().contiguous(), None)
+            gx = fused_linear(gy, w2d.detach().t().contiguous(), None, cache_weight=False)   # a one-shot tensor: never cached
         g2 = gy.reshape(-1, gy.shape[-1])
         if ctx.needs_input_grad[1]:
             gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
@@ -479,7 +510,7 @@ def _weightnet_host_params(convs):
     (w1 b1 w2 b2 w3 b3); one device->host copy per weight version (the fused kernel takes them as
     launch parameters so that every FFMA reads its weight from the constant bank)."""
     ts = [t for c in convs for t in (c.weight, c.bias)]
-    key = tuple(_tkey(t) for t in ts)
+    key = tuple(_wkey(t) for t in ts)
     hit = _WN_CACHE.get(key)
     if hit is not None:
         return hit[0]

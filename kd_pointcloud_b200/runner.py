@@ -63,6 +63,10 @@ class FlowRunner:
             with torch.cuda.graph(g):
                 self._forward()
             self.graph = g
+            # the graph bakes in the addresses of the cached packed weights / folded BN affines it hit: keep them alive
+            # past LRU evictions and clear_caches(weights=True).  Weights re-loaded in place after capture are NOT seen
+            # by the graph (no pack kernel is recorded for cache hits): call warmup_and_capture() again.
+            self._keepalive = KF.weight_cache_tensors()
         except Exception as e:                             # eager still works; report it
             print(f"[kdpc] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}")
             self.graph = None

@@ -33,14 +33,48 @@ def shard_batch(batch: dict, rank: int, world: int) -> dict:
     return {k: v[a:b] for k, v in batch.items()}
 
 
-class FlatGradAllReduce:
-    """Average gradients across ranks with one all-reduce over a persistent flat buffer."""
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Make every rank start from rank ``src``'s parameters AND buffers (BatchNorm statistics): replicas that load
+    different checkpoints, or a ``--pretrain`` given to one rank only, would otherwise diverge silently.  One flat
+    broadcast per dtype."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, ts in by_dtype.items():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        torch._foreach_copy_(ts, [c.view_as(t) for c, t in zip(flat.split([t.numel() for t in ts]), ts)])
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None):
+
+class FlatGradAllReduce:
+    """Average gradients across ranks with one all-reduce over a persistent flat buffer.
+
+    ``module``: when given, its parameters and buffers are broadcast from rank 0 at construction (see
+    ``broadcast_parameters``).  ``local_batch``: the number of pairs this rank contributes per step; the result is the
+    GLOBAL-batch mean ``sum_r n_r g_r / sum_r n_r`` (for equal shards this is the plain average; a rank may pass 0 and
+    contribute nothing).  Losses here are per-rank batch means (loss_functions.py:22 ``.mean()`` over B), which is what
+    makes this weighting the concatenated-batch gradient."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 module: Optional[torch.nn.Module] = None, local_batch: Optional[int] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.flat: Optional[torch.Tensor] = None
         self.active: Optional[List[int]] = None
+        self.weight = 1.0                                  # this rank's share of the global batch times world
+        if module is not None:
+            broadcast_parameters(module, 0, group)
+        if local_batch is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dev = self.params[0].device if dist.get_backend(group) == "nccl" else "cpu"
+            n = torch.tensor([float(local_batch)], dtype=torch.float64, device=dev)
+            total = n.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+            if total.item() <= 0:
+                raise RuntimeError("FlatGradAllReduce: the global batch is empty")
+            self.weight = float(local_batch) * dist.get_world_size(group) / total.item()
 
     def _plan(self):
         self.active = [i for i, p in enumerate(self.params) if p.grad is not None]
@@ -70,6 +104,8 @@ class FlatGradAllReduce:
         if any(g is None for g in grads):
             raise RuntimeError("FlatGradAllReduce: a parameter lost its gradient after planning")
         torch._foreach_copy_(list(self.flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        if self.weight != 1.0:
+            self.flat.mul_(self.weight)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(world)
         torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g for g in grads],

@@ -10,6 +10,7 @@ device scalar and leaves the read to the caller.
 """
 from __future__ import annotations
 
+import copy
 from typing import Callable, Dict, Optional
 
 import torch
@@ -18,9 +19,7 @@ from . import functional as KF
 from . import losses
 
 
-def kd_step(teacher: torch.nn.Module, student: torch.nn.Module, batch: Dict[str, torch.Tensor],
-            optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None,
-            gamma: float = 0.3, beta: float = 0.8, layers=(2, 3), hint_mode: str = "first") -> torch.Tensor:
+def _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode) -> torch.Tensor:
     KF.clear_caches()
     p1, p2, c1, c2, flow = batch["pos1"], batch["pos2"], batch["color1"], batch["color2"], batch["flow"]
     teacher.eval()
@@ -32,11 +31,18 @@ def kd_step(teacher: torch.nn.Module, student: torch.nn.Module, batch: Dict[str,
                                             t_out[6], t_out[1], t_out[2], gamma, beta, layer=layers, hint_mode=hint_mode)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
+    KF.clear_caches()
+    return loss.detach()
+
+
+def kd_step(teacher: torch.nn.Module, student: torch.nn.Module, batch: Dict[str, torch.Tensor],
+            optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None,
+            gamma: float = 0.3, beta: float = 0.8, layers=(2, 3), hint_mode: str = "first") -> torch.Tensor:
+    loss = _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode)
     if reducer is not None:
         reducer()
     optimizer.step()
-    KF.clear_caches()
-    return loss.detach()
+    return loss
 
 
 def supervised_step(model: torch.nn.Module, batch: Dict[str, torch.Tensor], optimizer: torch.optim.Optimizer,
@@ -55,45 +61,129 @@ def supervised_step(model: torch.nn.Module, batch: Dict[str, torch.Tensor], opti
     return loss.detach()
 
 
-class GraphedKDStep:
-    """``kd_step`` captured once in a CUDA graph (teacher forward, student forward + backward, fused loss, optional
-    gradient all-reduce, Adam) and replayed per batch: the eager step issues ~1600 kernel launches plus the autograd
-    bookkeeping from Python and is bound by the host (71 ms of CPU per 73 ms of GPU time, tools/prof_train.py).
+def make_capturable_adam(params, lr: float = 1e-3, **kw) -> torch.optim.Adam:
+    """Adam for ``GraphedKDStep``: ``capturable=True`` and the learning rate as a DEVICE tensor, so that the reference's
+    schedule (StepLR + the LEARNING_RATE_CLIP rewrite of ``param_group['lr']``, distilTrain.py:130-140) keeps working
+    after capture: ``set_lr`` / an in-place scheduler update changes what the captured kernels read."""
+    params = list(params)
+    dev = params[0].device
+    return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=dev), capturable=True, **kw)
 
-    The optimizer must be created with ``capturable=True``; batches are copied into static input buffers.
-    Falls back to the eager step (``self.graph is None``) when the capture fails, and ALWAYS runs eagerly when a gradient
-    ``reducer`` is given: capturing the NCCL all-reduce hung the 2-GPU run (round 1), so multi-GPU training stays eager
-    until that is understood."""
+
+def set_lr(optimizer: torch.optim.Optimizer, lr: float) -> None:
+    """``for g in optimizer.param_groups: g['lr'] = lr`` (distilTrain.py:139-140) that also reaches a captured graph."""
+    for g in optimizer.param_groups:
+        if isinstance(g["lr"], torch.Tensor):
+            g["lr"].fill_(float(lr))
+        else:
+            g["lr"] = float(lr)
+
+
+class GraphedKDStep:
+    """``kd_step`` captured in CUDA graphs and replayed per batch: the eager step issues ~1600 kernel launches plus the
+    autograd bookkeeping from Python and is bound by the host (71 ms of CPU per 73 ms of GPU time, tools/prof_train.py).
+
+    * Without a gradient ``reducer``: ONE graph (teacher forward, student forward + backward, fused loss, Adam).
+    * With a ``reducer`` (multi-GPU): TWO graphs — forward + backward into static ``.grad`` buffers, then the optimizer —
+      with the NCCL all-reduce issued EAGERLY between them (capturing the collective hung the 2-GPU run in round 1; one
+      31.8 MB all-reduce per step costs one launch from the host, the ~1600 other launches are replayed).
+
+    Contract:
+      * the optimizer must be ``capturable``; its lr is baked in unless it is a device tensor — use
+        ``make_capturable_adam`` / ``set_lr`` so that LR schedules keep working after capture;
+      * construction runs warm-up steps on ``example_batch``; student weights, BatchNorm statistics and optimizer state
+        are RESTORED afterwards (``restore_after_warmup=True``), so building the stepper does not train;
+      * ``step`` returns a CLONE of the static loss; a batch whose shapes differ from the captured ones (a short last
+        batch) runs the eager step;
+      * replays change weights without moving tensor versions: every replay bumps ``functional``'s weight epoch, so a
+        later ``student.eval()`` forward re-derives packed weights / folded BN affines instead of using stale ones;
+      * the graphs bake in the addresses of cached weight-derived tensors (teacher packs, folded affines): they are kept
+        alive in ``self._keepalive``.  Weights must not be re-loaded in place after capture — call ``recapture()``.
+    """
 
     def __init__(self, teacher: torch.nn.Module, student: torch.nn.Module, example_batch: Dict[str, torch.Tensor],
-                 optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None, warmup: int = 3, **kw):
-        self.teacher, self.student, self.optimizer, self.reducer, self.kw = teacher, student, optimizer, reducer, kw
+                 optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None, warmup: int = 3,
+                 restore_after_warmup: bool = True, **kw):
+        self.teacher, self.student, self.optimizer, self.reducer = teacher, student, optimizer, reducer
+        self.kw = {"gamma": kw.get("gamma", 0.3), "beta": kw.get("beta", 0.8), "layers": kw.get("layers", (2, 3)),
+                   "hint_mode": kw.get("hint_mode", "first")}
         self.static = {k: v.clone() for k, v in example_batch.items()}
         self.loss: Optional[torch.Tensor] = None
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
-        if reducer is not None:
-            return
-        dev = next(student.parameters()).device
+        self.graph: Optional[torch.cuda.CUDAGraph] = None          # forward + backward (+ optimizer when no reducer)
+        self.graph_opt: Optional[torch.cuda.CUDAGraph] = None      # optimizer (only with a reducer)
+        self._keepalive = []
+        self._warmup = max(3, warmup)
+        self._restore = restore_after_warmup
+        self.recapture()
+
+    def _eager(self, batch) -> torch.Tensor:
+        return kd_step(self.teacher, self.student, batch, self.optimizer, self.reducer, **self.kw)
+
+    def recapture(self) -> None:
+        """(Re)build the graphs from the CURRENT weights (call after load_state_dict or any in-place weight change)."""
+        self.graph = self.graph_opt = None
+        dev = next(self.student.parameters()).device
+        saved = None
+        if self._restore:
+            saved = (copy.deepcopy(self.student.state_dict()), copy.deepcopy(self.optimizer.state_dict()))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(3, warmup)):                 # allocator, caches and Adam state reach their steady state
-                kd_step(teacher, student, self.static, optimizer, reducer, **kw)
+            for _ in range(self._warmup):                   # allocator, caches and Adam state reach their steady state
+                self._eager(self.static)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.loss = kd_step(teacher, student, self.static, optimizer, reducer, **kw)
-            self.graph = g
+            if self.reducer is None:
+                with torch.cuda.graph(g):
+                    self.loss = self._eager(self.static)
+                self.graph = g
+            else:
+                with torch.cuda.graph(g):
+                    self.loss = _forward_backward(self.teacher, self.student, self.static, self.optimizer, **self.kw)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self.optimizer.step()
+                self.graph, self.graph_opt = g, g2
+            self._keepalive = KF.weight_cache_tensors()
         except Exception as e:                             # eager still works; report it
             print(f"[kdpc] CUDA graph capture of the KD step failed, running eagerly: {type(e).__name__}: {e}")
+            self.graph = self.graph_opt = None
             torch.cuda.synchronize(dev)
+        if saved is not None:                              # building the stepper must not train the student
+            with torch.no_grad():
+                self.student.load_state_dict(saved[0])     # in place: the captured addresses stay valid
+                cur = self.optimizer.state_dict()
+                for k, st in saved[1]["state"].items():
+                    for name, v in st.items():
+                        if isinstance(v, torch.Tensor) and k in cur["state"]:
+                            cur["state"][k][name].copy_(v)
+                missing = [k for k in cur["state"] if k not in saved[1]["state"]]
+                for k in missing:                          # optimizer state created by the warm-up: back to its initial value
+                    for name, v in cur["state"][k].items():
+                        if isinstance(v, torch.Tensor):
+                            v.zero_()
+            KF.bump_weight_epoch()
+
+    def _shapes_match(self, batch) -> bool:
+        return all(k in batch and batch[k].shape == v.shape for k, v in self.static.items())
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        if self.graph is None:
-            return kd_step(self.teacher, self.student, batch, self.optimizer, self.reducer, **self.kw)
+        if self.graph is None or not self._shapes_match(batch):
+            params = [p for g in self.optimizer.param_groups for p in g["params"]]
+            static_grads = [p.grad for p in params]        # the graphs write / read THESE buffers: keep them bound
+            loss = self._eager(batch)
+            if self.graph is not None:
+                for p, g in zip(params, static_grads):
+                    p.grad = g
+            KF.bump_weight_epoch()
+            return loss
         for k, v in self.static.items():
             v.copy_(batch[k], non_blocking=True)
         self.graph.replay()
-        return self.loss
+        if self.graph_opt is not None:
+            self.reducer()                                 # eager NCCL all-reduce over the static .grad buffers
+            self.graph_opt.replay()
+        KF.bump_weight_epoch()                             # weights moved on the device; tensor versions did not
+        return self.loss.clone()

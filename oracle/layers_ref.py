@@ -368,3 +368,33 @@ def multi_scale_loss(pred_flows: Sequence[torch.Tensor], gt_flow, fps_idxs, alph
         diff = pred_flows[i].permute(0, 2, 1) - gts[i + offset]
         total += alpha[i] * torch.norm(diff, dim=2).sum(dim=1).mean()
     return total
+
+
+def loss_fn_kd_2(outputs, fps_idxs, gt_flow, teacher_flow0, gamma):
+    """loss_functions.py:27-36: gamma * MS(student, teacher flow0) + (1-gamma) * MS(student, gt).
+    ``teacher_flow0`` is the teacher's finest flow [B,3,N] (the reference indexes teacher_outputs[0])."""
+    t0 = teacher_flow0.permute(0, 2, 1)
+    return gamma * multi_scale_loss(outputs, t0, fps_idxs) + (1 - gamma) * multi_scale_loss(outputs, gt_flow, fps_idxs)
+
+
+def bidirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, gt_flow, teacher_flow0, t_feat1s, t_feat2s, gamma, beta, layer=0):
+    """biDirection_loss_ht, loss_functions.py:83-96."""
+    t0 = teacher_flow0.permute(0, 2, 1)
+    loss1 = multi_scale_loss(outputs, t0, fps_idxs1)
+    loss2 = multi_scale_loss(outputs, gt_flow, fps_idxs1)
+    src = ((feat1s[layer] - t_feat1s[layer]) ** 2) / 2
+    tgt = ((feat2s[layer] - t_feat2s[layer]) ** 2) / 2
+    return beta * (gamma * loss1 + (1 - gamma) * loss2) + (1 - beta) * (0.5 * src.sum() + 0.5 * tgt.sum())
+
+
+def cross_bidirection_loss_ht(outputs, feat1s, fps_idxs1, gt_flow, teacher_flow0, t_feat1s, t_feat2s, gamma, beta, layer=(2, 3)):
+    """cross_biDirection_loss_ht, loss_functions.py:201-219 (student feature against cat(teacher feat1, feat2):
+    raises unless the student's hint features have twice the teacher's channels, like the reference)."""
+    t0 = teacher_flow0.permute(0, 2, 1)
+    loss1 = multi_scale_loss(outputs, t0, fps_idxs1)
+    loss2 = multi_scale_loss(outputs, gt_flow, fps_idxs1)
+    hint = torch.zeros(1)
+    for each in layer:
+        t_feats = torch.cat([t_feat1s[each], t_feat2s[each]], dim=1)
+        hint = hint + ((feat1s[each] - t_feats) ** 2).sum() / 2
+    return beta * (gamma * loss1 + (1 - gamma) * loss2) + (1 - beta) * hint

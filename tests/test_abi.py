@@ -50,7 +50,7 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.lower() or f == "synth.py", f"{f} mentions the oracle"
+                assert "oracle" not in text.lower() and "baseline/_ref" not in text, f"{f} mentions the oracle / reference install"
 
 
 def test_compat_names_resolve_to_kdpc(monkeypatch):

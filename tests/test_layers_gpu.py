@@ -127,6 +127,30 @@ def test_whole_model_against_reference_golden(golden):
     assert rel(loss, g["loss"]) < 1e-4
 
 
+def test_whole_model_against_reference_golden_at_benchmark_shape(golden):
+    """N = 8192 (the BASELINE shape): pair 0 of bench.py's first batch, bench.py's weights.  The golden is the unmodified
+    reference's forward on CPU (tests/make_golden_kd.py).  Run single AND as element 0 of the B=8 batch bench.py times."""
+    g = golden("model_teacher_n8192")
+    model, sd = load(PointConvBidirection(), 7)
+    d8 = make_pairs(8, 8192, seed=1234, device=DEV)
+    for B in (1, 8):
+        d = {k: v[:B].contiguous() for k, v in d8.items()}
+        KF.clear_caches()
+        with torch.no_grad():
+            flows, fps1, fps2, pc1, pc2, feat1s, feat2s, crosses = model(d["pos1"], d["pos2"], d["color1"], d["color2"])
+        for i in range(3):
+            assert np.array_equal(fps1[i][:1].cpu().numpy(), g[f"fps1_{i}"]) and np.array_equal(fps2[i][:1].cpu().numpy(), g[f"fps2_{i}"])
+        assert frac_bad(crosses[3][:1], g["cross3"]) < 5e-3
+        assert frac_bad(crosses[0][:1, :, :512], g["cross0_head"]) < 5e-3
+        for i in (3, 2, 1, 0):
+            assert frac_bad(flows[i][:1], g[f"flow{i}"]) < 5e-3, f"flow{i} (B={B})"
+        epe = L.epe3d(flows[0][:1], d["flow"][:1]).item()
+        assert abs(epe - float(g["epe3d"])) < 1e-4, (B, epe, float(g["epe3d"]))      # north star: EPE3D within 1e-4 m
+        loss = L.multiScaleLoss([f[:1] for f in flows], d["flow"][:1], [f[:1] for f in fps1])
+        assert rel(loss, g["loss"]) < 1e-4
+    KF.clear_caches()
+
+
 def test_batched_model_equals_oracle_and_single_runs():
     """B=2 through the 2B-batched encoder equals the oracle run pair by pair."""
     model, sd = load(PointConvBidirection(), 7)

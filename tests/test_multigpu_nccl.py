@@ -1,0 +1,150 @@
+"""NCCL, 2 ranks on 2 GPUs (SURVEY 8(e), configs[4]): batch-sharded KD training.
+
+  * the all-reduced gradients of the sharded step equal the single-GPU gradients over the concatenated batch
+    (BatchNorm in eval mode, so that batch statistics do not depend on the shard);
+  * the two-graph step (forward+backward graph, EAGER NCCL all-reduce, optimizer graph) equals the eager sharded step
+    loss for loss and weight for weight, and keeps the replicas identical.
+
+Skipped with fewer than 2 devices (run with ``gpurun --gpus 2``).
+"""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _setup(rank, world, port):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return dev
+
+
+def _models(dev):
+    from kd_pointcloud_b200 import flownet
+    from kd_pointcloud_b200.synth import synthetic_state_dict
+    teacher = flownet.teacher()
+    teacher.load_state_dict(synthetic_state_dict(teacher.state_dict(), 0))
+    student = flownet.student()
+    student.load_state_dict(synthetic_state_dict(student.state_dict(), 1))
+    return teacher.to(dev), student.to(dev)
+
+
+def _loss(teacher, student, batch):
+    from kd_pointcloud_b200 import functional as KF
+    from kd_pointcloud_b200 import losses
+    KF.clear_caches()
+    with torch.no_grad():
+        t = teacher(batch["pos1"], batch["pos2"], batch["color1"], batch["color2"])
+    s = student(batch["pos1"], batch["pos2"], batch["color1"], batch["color2"])
+    return losses.cross_biDirection_loss_ht(s[0], s[5], s[6], s[1], s[2], batch["flow"], t[0], t[5], t[6], t[1], t[2], 0.3, 0.8,
+                                            layer=(2, 3), hint_mode="first")
+
+
+def _worker_grad_parity(rank, world, port, q):
+    import torch.distributed as dist
+    from kd_pointcloud_b200.sharding import FlatGradAllReduce, shard_batch
+    from kd_pointcloud_b200.synth import make_pairs
+    dev = _setup(rank, world, port)
+    teacher, student = _models(dev)
+    teacher.eval(), student.eval()                           # BatchNorm on running statistics: shard-independent
+    full = make_pairs(4, 2048, seed=31, device=dev)
+    mine = shard_batch(full, rank, world)
+    red = FlatGradAllReduce(student.parameters(), module=student, local_batch=mine["pos1"].shape[0])
+    _loss(teacher, student, mine).backward()
+    red()
+    sharded = {k: p.grad.clone() for k, p in student.named_parameters() if p.grad is not None}
+    student.zero_grad(set_to_none=True)
+    _loss(teacher, student, full).backward()                 # every rank also computes the single-GPU reference itself
+    worst, bad = 0.0, []
+    for k, p in student.named_parameters():
+        if p.grad is None:
+            assert k not in sharded
+            continue
+        err = (sharded[k] - p.grad).abs().max().item() / max(p.grad.abs().max().item(), 1e-30)
+        worst = max(worst, err)
+        if err > 1e-4:
+            bad.append((k, err))
+    q.put((rank, worst, bad[:5], len(sharded), red.numel))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _worker_two_graph_step(rank, world, port, q):
+    import torch.distributed as dist
+    from kd_pointcloud_b200 import training
+    from kd_pointcloud_b200.sharding import FlatGradAllReduce
+    from kd_pointcloud_b200.synth import make_pairs
+    dev = _setup(rank, world, port)
+    teacher, student = _models(dev)
+    batches = [make_pairs(1, 2048, seed=200 + 10 * rank + i, device=dev) for i in range(3)]
+    init = copy.deepcopy(student.state_dict())
+    out = {}
+    for graphed in (False, True):
+        student.load_state_dict(init)
+        opt = training.make_capturable_adam(student.parameters(), lr=1e-4)
+        red = FlatGradAllReduce(student.parameters(), module=student, local_batch=1)
+        if graphed:
+            stepper = training.GraphedKDStep(teacher, student, batches[0], opt, red)
+            assert stepper.graph is not None and stepper.graph_opt is not None
+            step = stepper.step
+        else:
+            step = lambda b: training.kd_step(teacher, student, b, opt, red)
+        losses = [step(b).reshape(1) for b in batches]
+        torch.cuda.synchronize(dev)
+        out[graphed] = (torch.cat(losses).cpu(), {k: v.detach().cpu().clone() for k, v in student.state_dict().items()})
+    same_loss = torch.equal(out[False][0], out[True][0])
+    diff = [k for k in out[False][1] if not torch.equal(out[False][1][k], out[True][1][k])]
+    # replicas stay identical: compare a checksum of all parameters across ranks
+    chk = torch.stack([p.detach().double().sum() for p in student.parameters()]).sum().reshape(1)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    q.put((rank, same_loss, diff[:5], out[False][0].tolist(), out[True][0].tolist(), float(both[0]) == float(both[1])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _spawn(fn):
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=fn, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+def test_allreduced_gradients_equal_single_gpu_gradients_over_the_concatenated_batch():
+    for rank, worst, bad, n_tensors, numel in _spawn(_worker_grad_parity):
+        assert n_tensors == 226 and numel == 7956876
+        assert not bad and worst < 1e-4, (rank, worst, bad)
+
+
+def test_two_graph_step_with_eager_allreduce_equals_the_eager_sharded_step():
+    for rank, same_loss, diff, l_eager, l_graph, replicas_equal in _spawn(_worker_two_graph_step):
+        assert same_loss, (rank, l_eager, l_graph)
+        assert not diff, (rank, diff)
+        assert replicas_equal

@@ -120,3 +120,34 @@ def test_state_dict_keys_match_reference():
     assert list(mine) == list(ref)
     assert mine == ref
     assert sum(int(np.prod(v)) for k, v in mine.items() if "running" not in k and "tracked" not in k) == 7958604
+
+
+def test_kd_loss_oracles_match_reference_golden(golden):
+    """loss_fn_kd_2 / biDirection_loss_ht / cross_biDirection_loss_ht restatements against values AND gradients the
+    unmodified loss_functions.py produced (tests/make_golden_kd.py)."""
+    g = golden("kd_losses")
+    fps = [T(g[f"fps{i}"]) for i in range(3)]
+    gt, t0 = T(g["gt"]), T(g["t_flow0"])
+    t1, t2 = [T(g[f"t1_{i}"]) for i in range(4)], [T(g[f"t2_{i}"]) for i in range(4)]
+
+    def leaves(prefix):
+        return [T(g[f"{prefix}{i}"]).clone().requires_grad_(True) for i in range(4)]
+
+    preds, s1, s2, s1w = leaves("pred"), leaves("s1_"), leaves("s2_"), leaves("s1w_")
+    cases = [("kd2", lambda: O.loss_fn_kd_2(preds, fps, gt, t0, 0.3), {}),
+             ("bidir", lambda: O.bidirection_loss_ht(preds, s1, s2, fps, gt, t0, t1, t2, 0.3, 0.8, layer=1), {"s1_1": s1[1], "s2_1": s2[1]}),
+             ("cross", lambda: O.cross_bidirection_loss_ht(preds, s1w, fps, gt, t0, t1, t2, 0.3, 0.8, layer=[2, 3]),
+              {"s1w_2": s1w[2], "s1w_3": s1w[3]})]
+    for name, fn, extra in cases:
+        for t in preds + s1 + s2 + s1w:
+            t.grad = None
+        loss = fn()
+        loss.backward()
+        assert _rel(loss.detach(), g[f"{name}_loss"]) < 1e-6
+        for i in range(4):
+            assert _rel(preds[i].grad, g[f"{name}_g_pred{i}"]) < 1e-5
+        for k, t in extra.items():
+            assert _rel(t.grad, g[f"{name}_g_{k}"]) < 1e-6
+    with pytest.raises(RuntimeError):                      # equal student/teacher widths: the reference raises (SURVEY 9)
+        O.cross_bidirection_loss_ht(preds, s1, fps, gt, t0, t1, t2, 0.3, 0.8, layer=[2, 3])
+    assert int(g["cross_equal_width_raises"]) == 1

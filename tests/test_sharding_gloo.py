@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kd_pointcloud_b200.sharding import FlatGradAllReduce, shard_batch, shard_range
+from kd_pointcloud_b200.sharding import FlatGradAllReduce, broadcast_parameters, shard_batch, shard_range
 
 
 def test_shard_range_covers_everything_once():
@@ -71,3 +71,64 @@ def test_flat_grad_allreduce_matches_single_process():
             assert (a is None) == (b is None)
             if a is not None:
                 assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), rank
+
+
+def _worker_uneven(rank, world, port, q):
+    """Uneven shards (5 + 3 of 8) with per-rank MEAN losses, ranks seeded differently: the broadcast makes the replicas
+    identical, the batch-size weighting makes the result the gradient of the global-batch mean."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    batch = {"x": torch.randn(8, 6, generator=g), "y": torch.randn(8, 3, generator=g)}
+    a, b = (0, 5) if rank == 0 else (5, 8)
+    mine = {k: v[a:b] for k, v in batch.items()}
+    torch.manual_seed(100 + rank)                            # replicas start DIFFERENT ...
+    m = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.BatchNorm1d(16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    m[1].running_mean.fill_(float(rank))
+    red = FlatGradAllReduce(m.parameters(), module=m, local_batch=b - a)      # ... and are made equal here
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.eval()
+    loss = ((m(mine["x"]) - mine["y"]) ** 2).sum(dim=1).mean()                # per-rank batch MEAN (loss_functions.py:22)
+    loss.backward()
+    red()
+    # numpy: pickled by value (tensors travel as shared-memory fds, which die with this process)
+    q.put((rank, {k: v.numpy() for k, v in sd.items()}, [p.grad.numpy().copy() for p in m.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_uneven_shards_give_the_global_batch_mean_gradient():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_uneven, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, sd0, g0), (_, sd1, g1) = res
+    sd0, sd1 = ({k: torch.from_numpy(v) for k, v in sd.items()} for sd in (sd0, sd1))
+    g0, g1 = ([torch.from_numpy(v) for v in gs] for gs in (g0, g1))
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k                # parameters AND buffers (running_mean) came from rank 0
+    assert float(sd1["1.running_mean"][0]) == 0.0
+    g = torch.Generator().manual_seed(5)
+    batch = {"x": torch.randn(8, 6, generator=g), "y": torch.randn(8, 3, generator=g)}
+    m = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.BatchNorm1d(16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    m.load_state_dict(sd0)
+    m.eval()
+    ((m(batch["x"]) - batch["y"]) ** 2).sum(dim=1).mean().backward()
+    for a, b, ref in zip(g0, g1, [p.grad for p in m.parameters()]):
+        assert torch.allclose(a, ref, rtol=1e-5, atol=1e-6) and torch.equal(a, b)
+
+
+def test_broadcast_parameters_is_a_noop_without_a_process_group():
+    m = _model()
+    before = [p.clone() for p in m.parameters()]
+    broadcast_parameters(m)
+    assert all(torch.equal(a, b) for a, b in zip(before, m.parameters()))
