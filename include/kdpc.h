@@ -46,6 +46,10 @@ int kdpc_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, kdpc_
 /* Clouds of 2048..16384 points run on a cluster of 8 CTAs per cloud (distributed-shared-memory arg-max);
  * kdpc_fps_set_cluster(0) forces the one-CTA-per-cloud kernel (same results; for A/B measurements). */
 void kdpc_fps_set_cluster(int on);
+/* Measurement hooks (tools/bench_fps.py): kdpc_fps_set_cluster(spread * 1000000 + ctas * 10000 + threads_per_cloud)
+ * forces one cluster shape (ctas in {2,4,8}, threads_per_cloud in {1024,2048}; spread = 1 asks for
+ * cudaClusterSchedulingPolicySpread); kdpc_fps_cluster_capacity = clusters of that shape that fit on the device at once. */
+int kdpc_fps_cluster_capacity(int ctas, int threads_per_cloud, int n);
 
 /* gather_points_kernel_launcher_fast, sampling_gpu.h:12-13.  f [B,C,N], idx [B,M] -> out [B,C,M] */
 int kdpc_gather(int b, int c, int n, int m, const float *f, const int *idx, float *out, kdpc_stream_t stream);

@@ -143,6 +143,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_loss_workspace_bytes.argtypes = []
         L.kdpc_fps_set_cluster.restype = None
         L.kdpc_fps_set_cluster.argtypes = [c_int]
+        L.kdpc_fps_cluster_capacity.restype = c_int
+        L.kdpc_fps_cluster_capacity.argtypes = [c_int, c_int, c_int]
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -160,8 +162,8 @@ def lib() -> ctypes.CDLL:
             L.kdpc_pointconv_set_precompute(0)
         if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
             L.kdpc_tc_set_async(0)
-        if os.environ.get("KDPC_FPS_CLUSTER", "1") == "0":       # A/B switch for measurements
-            L.kdpc_fps_set_cluster(0)
+        if os.environ.get("KDPC_FPS_CLUSTER", "1") != "1":       # A/B switch for measurements (0 = off, or a forced shape)
+            L.kdpc_fps_set_cluster(int(os.environ["KDPC_FPS_CLUSTER"]))
         _lib = L
     return _lib
 
@@ -169,7 +171,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
-            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
+            "kdpc_loss_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)
 
 

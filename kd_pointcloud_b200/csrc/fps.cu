@@ -145,8 +145,7 @@ fps_generic_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, 
 // redundantly.  No barrier of any kind inside the loop.
 // Ownership keeps the reference's tie rule exact: the 2048 threads are (part, reference thread t = gtid % bs);
 // a thread owns k = t + i*bs for a contiguous range of i, scanned in ascending i with a strict '>'.
-constexpr int FPSC_TOTAL = 2048;                               // threads per cloud, over 8 x 256 or 4 x 512
-constexpr int FPSC_WARPS = FPSC_TOTAL / 32;                    // 64 warp results per iteration
+constexpr int FPSC_TOTAL = 2048;                               // default threads per cloud, over 8 x 256 or 4 x 512
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
@@ -171,23 +170,24 @@ __device__ __forceinline__ uint2 ld_volatile_v2(uint32_t addr) {
     return v;
 }
 
-template <int PPT, int FPSC_CTAS>
-__global__ void __launch_bounds__(FPSC_TOTAL / FPSC_CTAS)
+template <int PPT, int FPSC_CTAS, int TOTAL>
+__global__ void __launch_bounds__(TOTAL / FPSC_CTAS)
 fps_cluster_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, float *__restrict__ temp,
                    int *__restrict__ idx_out) {
+    constexpr int NWARPS = TOTAL / 32;                         // warp results per iteration: 64 (two per lane) or 32
     extern __shared__ float cloud[];          // x[n] | y[n] | z[n]
-    __shared__ __align__(8) uint2 slots[2][FPSC_WARPS];
+    __shared__ __align__(8) uint2 slots[2][NWARPS];
     float *sx = cloud, *sy = cloud + n, *sz = cloud + 2 * n;
-    constexpr int FPSC_THREADS = FPSC_TOTAL / FPSC_CTAS;
+    constexpr int FPSC_THREADS = TOTAL / FPSC_CTAS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = cluster_ctarank();
     const int cloud_id = blockIdx.x / FPSC_CTAS;
-    const int gtid = (int)rank * FPSC_THREADS + tid;           // 0 .. 2047
+    const int gtid = (int)rank * FPSC_THREADS + tid;           // 0 .. TOTAL-1
     const float *p = xyz + (size_t)cloud_id * n * 3;
     idx_out += (size_t)cloud_id * m;
 
-    if (tid < 2 * FPSC_WARPS) (&slots[0][0])[tid] = make_uint2(0u, 0u);      // tag 0 = "nothing yet"
+    for (int i = tid; i < 2 * NWARPS; i += FPSC_THREADS) (&slots[0][0])[i] = make_uint2(0u, 0u);      // tag 0 = "nothing yet"
     for (int i = tid; i < 3 * n; i += FPSC_THREADS) {
         int k = i / 3, c = i - 3 * k;
         cloud[c * n + k] = p[i];
@@ -208,7 +208,7 @@ fps_cluster_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, 
         md[i] = v ? 1e10f : -1.f;
     }
     const unsigned rt = __brev((unsigned)t) >> (32 - lg);
-    // lanes 0..7 forward this warp's result to CTA `lane`: remote slot addresses (per buffer)
+    // lanes 0..CTAS-1 forward this warp's result to CTA `lane`: remote slot addresses (per buffer)
     uint32_t rslot[2] = {0, 0};
     if (lane < FPSC_CTAS) {
 #pragma unroll
@@ -240,8 +240,9 @@ fps_cluster_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, 
         // iteration's result from the one written two iterations ago into the same (double-buffered) slot
         const unsigned tag = ((((unsigned)(j - 1) >> 1) + 1u) & 1u) << 31;
         if (lane < FPSC_CTAS) st_remote_v2(rslot[par], wh | tag, wl);
-        uint2 s0, s1;
-        {
+        unsigned mh, ml;
+        if constexpr (NWARPS == 64) {
+            uint2 s0, s1;
             const uint32_t a0 = smem_u32(&slots[par][lane]), a1 = smem_u32(&slots[par][lane + 32]);
             unsigned spins = 0;
             for (;;) {                                         // poll local shared memory until both slots are fresh
@@ -252,9 +253,22 @@ fps_cluster_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, 
             }
             s0.x &= 0x7fffffffu;
             s1.x &= 0x7fffffffu;
+            const bool second = s1.x > s0.x || (s1.x == s0.x && s1.y > s0.y);
+            mh = second ? s1.x : s0.x;
+            ml = second ? s1.y : s0.y;
+        } else {
+            static_assert(NWARPS == 32 || NWARPS == 64, "one or two warp results per lane");
+            uint2 s0;
+            const uint32_t a0 = smem_u32(&slots[par][lane]);
+            unsigned spins = 0;
+            for (;;) {
+                s0 = ld_volatile_v2(a0);
+                if ((s0.x ^ tag) >> 31 == 0u) break;
+                if (++spins > (1u << 22)) __trap();
+            }
+            mh = s0.x & 0x7fffffffu;
+            ml = s0.y;
         }
-        const bool second = s1.x > s0.x || (s1.x == s0.x && s1.y > s0.y);
-        const unsigned mh = second ? s1.x : s0.x, ml = second ? s1.y : s0.y;
         const unsigned gh = __reduce_max_sync(0xffffffffu, mh);
         const unsigned gl = __reduce_max_sync(0xffffffffu, mh == gh ? ml : 0u);
         const unsigned key = ~gl;
@@ -272,7 +286,9 @@ fps_cluster_kernel(int n, int m, int bs, int lg, const float *__restrict__ xyz, 
     cluster_sync_all();                                        // nobody exits while a peer may still write to it
 }
 
-template <int PPT, int CTAS>
+static int fps_cluster_spread = 0;                             // A/B: cudaClusterSchedulingPolicySpread
+
+template <int PPT, int CTAS, int TOTAL>
 static int launch_cluster_c(int b, int n, int m, int bs, int lg, const float *xyz, float *temp, int *idx, cudaStream_t st,
                             bool probe_only) {
     // > half of the SM's shared memory: ONE CTA per SM, so that co-resident clusters never share an SM (their
@@ -280,20 +296,22 @@ static int launch_cluster_c(int b, int n, int m, int bs, int lg, const float *xy
     // counts exclusive placements
     size_t smem = (size_t)3 * n * sizeof(float);
     if (smem < 120 * 1024) smem = 120 * 1024;
-    auto kern = fps_cluster_kernel<PPT, CTAS>;
+    auto kern = fps_cluster_kernel<PPT, CTAS, TOTAL>;
     KDPC_ENSURE_SMEM(kern, 3 * 16384 * (int)sizeof(float));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b * CTAS);
-    cfg.blockDim = dim3(FPSC_TOTAL / CTAS);
+    cfg.blockDim = dim3(TOTAL / CTAS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CTAS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+    attr[1].val.clusterSchedulingPolicyPreference = cudaClusterSchedulingPolicySpread;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = fps_cluster_spread ? 2 : 1;
     if (probe_only) {                                          // how many clusters of this shape fit at once?
         int clusters = 0;
         if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -312,13 +330,25 @@ static int launch_cluster(int b, int n, int m, int bs, int lg, const float *xyz,
     const int slot = PPT == 1 ? 0 : (PPT == 2 ? 1 : (PPT == 4 ? 2 : 3));
     if (dev < 0 || dev >= 64) return -100;
     if (fit8[slot][dev] == 0) {
-        fit8[slot][dev] = 1 + launch_cluster_c<PPT, 8>(1, n, m, bs, lg, xyz, temp, idx, st, true);
-        fit4[slot][dev] = 1 + launch_cluster_c<PPT, 4>(1, n, m, bs, lg, xyz, temp, idx, st, true);
+        fit8[slot][dev] = 1 + launch_cluster_c<PPT, 8, FPSC_TOTAL>(1, n, m, bs, lg, xyz, temp, idx, st, true);
+        fit4[slot][dev] = 1 + launch_cluster_c<PPT, 4, FPSC_TOTAL>(1, n, m, bs, lg, xyz, temp, idx, st, true);
     }
-    if (b <= fit8[slot][dev] - 1) return launch_cluster_c<PPT, 8>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    if (b <= fit8[slot][dev] - 1) return launch_cluster_c<PPT, 8, FPSC_TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
     if (b <= fit4[slot][dev] - 1 && b <= 24)                   // (measured: beyond ~24 clouds the one-CTA kernel wins)
-        return launch_cluster_c<PPT, 4>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+        return launch_cluster_c<PPT, 4, FPSC_TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
     return -100;                                               // caller falls back to the one-CTA kernel
+}
+
+// Forced variant (measurements: tools/bench_fps.py): ctas in {2,4,8}, total threads per cloud in {1024, 2048}.
+// Returns -100 when the shape does not divide.
+template <int CTAS, int TOTAL>
+static int launch_cluster_forced(int per, int b, int n, int m, int bs, int lg, const float *xyz, float *temp, int *idx, cudaStream_t st) {
+    if (per == 1) return launch_cluster_c<1, CTAS, TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    if (per == 2) return launch_cluster_c<2, CTAS, TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    if (per == 4) return launch_cluster_c<4, CTAS, TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    if (per == 8) return launch_cluster_c<8, CTAS, TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    if (per == 16) return launch_cluster_c<16, CTAS, TOTAL>(b, n, m, bs, lg, xyz, temp, idx, st, false);
+    return -100;
 }
 
 template <int PPT>
@@ -333,8 +363,22 @@ static int launch_smem(int b, int n, int m, int bs, int lg, const float *xyz, fl
 }  // namespace kdpc
 
 static int kdpc_fps_use_cluster = 1;
-/* test hook: 0 = always the single-CTA kernel */
+/* test / measurement hook: 0 = always the single-CTA kernel, 1 = automatic (default);
+   otherwise a forced cluster variant: on = spread * 1000000 + ctas * 10000 + threads_per_cloud (e.g. 82048, 41024, 1082048) */
 KDPC_API void kdpc_fps_set_cluster(int on) { kdpc_fps_use_cluster = on; }
+/* how many clusters of (ctas, threads per cloud) fit on the device at once for an n-point cloud (0: none / bad shape) */
+KDPC_API int kdpc_fps_cluster_capacity(int ctas, int total, int n) {
+    using namespace kdpc;
+    const int bs = ref_block_size(n);
+    int lg = 0;
+    while ((1 << lg) < bs) ++lg;
+    if (ctas == 8 && total == 2048) return launch_cluster_c<4, 8, 2048>(1, n, 1, bs, lg, nullptr, nullptr, nullptr, 0, true);
+    if (ctas == 4 && total == 2048) return launch_cluster_c<4, 4, 2048>(1, n, 1, bs, lg, nullptr, nullptr, nullptr, 0, true);
+    if (ctas == 8 && total == 1024) return launch_cluster_c<8, 8, 1024>(1, n, 1, bs, lg, nullptr, nullptr, nullptr, 0, true);
+    if (ctas == 4 && total == 1024) return launch_cluster_c<8, 4, 1024>(1, n, 1, bs, lg, nullptr, nullptr, nullptr, 0, true);
+    if (ctas == 2 && total == 1024) return launch_cluster_c<8, 2, 1024>(1, n, 1, bs, lg, nullptr, nullptr, nullptr, 0, true);
+    return 0;
+}
 
 KDPC_API int kdpc_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(xyz && idx && b > 0 && n > 0);
@@ -346,6 +390,23 @@ KDPC_API int kdpc_fps(int b, int n, int m, const float *xyz, float *temp, int *i
     while ((1 << lg) < bs) ++lg;
     const int ppt = (n + bs - 1) / bs;
     // clouds of >= 2048 points: a cluster of 8 CTAs per cloud (2048 threads = 2048/bs threads per reference thread)
+    if (kdpc_fps_use_cluster > 1) {                   // forced variant (measurements)
+        const int spread = kdpc_fps_use_cluster / 1000000, ctas = (kdpc_fps_use_cluster / 10000) % 100,
+                  tot = kdpc_fps_use_cluster % 10000;
+        fps_cluster_spread = spread;
+        int rc = -100;
+        if (n <= 16384 && tot >= bs && (ppt * bs) % tot == 0) {
+            const int per = ppt * bs / tot;
+            if (ctas == 8 && tot == 2048) rc = launch_cluster_forced<8, 2048>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+            if (ctas == 4 && tot == 2048) rc = launch_cluster_forced<4, 2048>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+            if (ctas == 2 && tot == 2048) rc = launch_cluster_forced<2, 2048>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+            if (ctas == 8 && tot == 1024) rc = launch_cluster_forced<8, 1024>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+            if (ctas == 4 && tot == 1024) rc = launch_cluster_forced<4, 1024>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+            if (ctas == 2 && tot == 1024) rc = launch_cluster_forced<2, 1024>(per, b, n, m, bs, lg, xyz, temp, idx, st);
+        }
+        fps_cluster_spread = 0;
+        if (rc != -100) return rc;
+    }
     const int total = FPSC_TOTAL;
     if (kdpc_fps_use_cluster && n >= 2 * total && n <= 16384 && (ppt * bs) % total == 0) {    // (n = 2048: one CTA is faster)
         const int per = ppt * bs / total;

@@ -131,7 +131,8 @@ def load(stack: str) -> Dict[str, types.ModuleType]:
         import pointconv_util
         out = {"models_bid_pointconv": models_bid_pointconv, "models_bid_lighttoken_res": models_bid_lighttoken_res,
                "loss_functions": loss_functions, "pointconv_util": pointconv_util,
-               "pointnet2_utils": sys.modules.get("pointnet2.pointnet2_utils")}
+               "pointnet2_utils": sys.modules.get("pointnet2.pointnet2_utils"),
+               "pointconv_util3": sys.modules.get("pointconv_util3")}
         src = os.path.abspath(models_bid_pointconv.__file__)
         assert src.startswith(REF_INSTALL), f"models_bid_pointconv came from {src}, not from the reference install"
         return out

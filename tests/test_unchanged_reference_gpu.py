@@ -162,3 +162,28 @@ def test_distil_train_step_on_both_stacks(compat, stock):
     for k in w_ref:
         if k.endswith("running_mean") and "bn_linear" in k:
             assert frac_bad(w_my[k], w_ref[k], 1e-3) < 2e-2, k
+
+
+def test_bottleneck_and_plain_convs_against_the_reference_modules(stock):
+    """a17: BottleNeck / ConvBNReLU (pointconv_util3.py:51-79) and Conv1d / Conv2d (pointconv_util.py:20-54) run on the
+    GPU against the reference's own modules with the same weights."""
+    from kd_pointcloud_b200 import pointconv_util as P
+    R, R3 = stock["pointconv_util"], stock["pointconv_util3"]
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 32, 1024, generator=g).to(DEV)
+    for mine, ref in ((P.BottleNeck(32, 16, 32), R3.BottleNeck(32, 16, 32)), (P.ConvBNReLU(32, 32), R3.ConvBNReLU(32, 32)),
+                      (P.Conv1d(32, 48), R.Conv1d(32, 48)), (P.Conv1d(32, 48, use_leaky=False, bn=True), R.Conv1d(32, 48, use_leaky=False, bn=True))):
+        assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+        sd = synthetic_state_dict(ref.state_dict(), 9)
+        mine.load_state_dict(sd), ref.load_state_dict(sd)
+        mine, ref = mine.to(DEV).eval(), ref.to(DEV).eval()
+        with torch.no_grad():
+            a, b = mine(x), ref(x.clone())
+        assert a.shape == b.shape and ((a - b).abs().max() / b.abs().max()).item() < 1e-4, type(mine).__name__
+    x4 = torch.randn(2, 16, 8, 256, generator=g).to(DEV)
+    mine, ref = P.Conv2d(16, 24), R.Conv2d(16, 24)
+    sd = synthetic_state_dict(ref.state_dict(), 10)
+    mine.load_state_dict(sd), ref.load_state_dict(sd)
+    with torch.no_grad():
+        a, b = mine.to(DEV).eval()(x4), ref.to(DEV).eval()(x4.clone())
+    assert ((a - b).abs().max() / b.abs().max()).item() < 1e-4

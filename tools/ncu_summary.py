@@ -11,11 +11,28 @@ want = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("launch__bloc
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("sm__inst_executed.avg.per_cycle_active", "IPC (per SM)"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
         ("sm__pipe_tensor_subunit_throughput.avg.pct_of_peak_sustained_active", "tensor pipe % (subunit)"),
-        ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe inst"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+        ("sm__inst_executed_pipe_tensor.sum", "tensor-pipe inst"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe cycles active %"),
+        ("sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active", "tensor subunit cycles active %"),
+        ("sm__inst_executed_pipe_tensor_subunit.sum", "tensor-subunit inst"),
+        ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe inst"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+        ("l1tex__data_bank_conflicts_pipe_lsu.sum", "L1/smem bank conflicts"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard / issue"),
         ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard / issue"),
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait / issue"),
-        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue")]
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
+        ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar / issue"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle / issue"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle / issue"),
+        ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle / issue"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving / issue"),
+        ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch / issue"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction / issue"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue"),
+        ("smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "stall sleeping / issue")]
 units = rows[1]
 for r in rows[2:]:
     print("-" * 100)
