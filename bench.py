@@ -206,6 +206,7 @@ def kernel_rooflines(torch, dev, B, hbm_peak, tc_peak):
         fn()
         ts = []
         for _ in range(iters):
+            torch.cuda._sleep(400000)                      # the host runs ahead of the GPU: events bracket GPU execution only
             flush.zero_()                                  # evict L2 (126 MB) between timed launches
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -263,6 +264,19 @@ def kernel_rooflines(torch, dev, B, hbm_peak, tc_peak):
     t = timeit(lambda: K.group_concat(xyz, xyz, feats, idx9))
     alg = B * (4 * N * Kn + 12 * (N + N) + 4 * N * D + 4 * N * Kn * (D + 3))
     out["group_concat"] = {"shape": f"B={B} S=N={N} K={Kn} D={D}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    # ---- point-major row gather (index_points_group, pointconv_util.py:122-133) and 3-NN interpolation (UpsampleFlow)
+    f64 = torch.randn(B, N, 64, device=dev)
+    idx16 = K.knn(xyz, xyz, 16)
+    t = timeit(lambda: K.gather_rows(f64, idx16))
+    alg = B * (4 * N * 16 + 4 * N * 64 + 4 * N * 16 * 64)
+    out["gather_rows"] = {"shape": f"B={B} N={N} K=16 C=64", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    fps_i = K.fps(xyz, 2048)
+    sparse = K.gather_rows(xyz, fps_i)
+    idx3 = K.knn(xyz, sparse, 3)
+    fs = torch.randn(B, 2048, 64, device=dev)
+    t = timeit(lambda: K.interp3(xyz, sparse, idx3, fs))
+    alg = B * (4 * 2048 * 64 + 36 * N + 12 * 2048 + 4 * N * 64)
+    out["interp3"] = {"shape": f"B={B} N={N} S=2048 C=64", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
     # ---- FPS: latency-bound (sequential arg-max)
     t = timeit(lambda: K.fps(xyz, 2048), iters=3)
     out["fps_8192_2048"] = {"shape": f"B={B} 8192->2048", "sec": t, "us_per_iter": t / 2047 * 1e6,

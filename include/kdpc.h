@@ -87,6 +87,12 @@ int kdpc_ball_query(int b, int n, int m, float radius, int nsample, const float 
 /* square_distance, pointconv_util.py:73-94: out[b,i,j] = rn(rn(-2*dot + |src_i|^2) + |dst_j|^2) */
 int kdpc_square_distance(int b, int s, int n, const float *src, const float *dst, float *out, kdpc_stream_t stream);
 
+/* kNN in a C-dimensional FEATURE space: square_distance + topk on [B,*,C] feature tensors, as CrossLayerLightFG uses them
+ * (pointconv_util.py:1905 knn_point(nsample//2, knn2, knn1); square_distance :73-94, topk :106).
+ * query [B,S,C], cand [B,N,C] -> idx int32 [B,S,k] ascending (distance, index); dist [B,S,k] or NULL.  k <= 32, C <= 512. */
+int kdpc_knn_feat(int b, int s, int n, int c, int k, const float *query, const float *cand, int *idx, float *dist,
+                  kdpc_stream_t stream);
+
 /* knn_point, pointconv_util.py:96-107, without materialising the [B,S,N] matrix.
  * query [B,S,3], cand [B,N,3] -> the k candidates with smallest square_distance, ordered
  * ascending by (distance, index).  idx32 / idx64 / dist may each be NULL.  k <= min(32, N).

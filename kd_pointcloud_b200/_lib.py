@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("KDPC_LIB") or os.path.join(_HERE, "libkdpc.so")   # KDPC_LIB: an experiment build (A/B measurements)
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu"]
+           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu", "knn_feat.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 LINK_FLAGS = ARCH_FLAGS + ["-shared"]
@@ -86,6 +86,7 @@ _SIGNATURES = {
     "kdpc_knn": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_knn_bruteforce": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_spatial_sort": [c_int, c_int, _P, _P, _P],
+    "kdpc_knn_feat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P],
     "kdpc_knn_sorted": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_gather_rows": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_group_concat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],

@@ -510,6 +510,46 @@ struct StoreEpilogue {
         const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0 &&
                          (e.residual == nullptr || partial || (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // this lane's row within a group of 4, and its 4 columns
+        // Fast path (every streaming layer of the model): whole 32-row block inside M, plain row order, 16-byte aligned
+        // rows, no residual.  Branch-free and fully unrolled: the generic path below carries a 64-bit division, eight
+        // predicated scalar scale/shift loads and ~10 branches per row group and cost ~2700 cycles per 32 x 32 block
+        // (tools/trace_linear.py: the epilogue, not HBM, paced the streaming layers at 26-34 % of the copy peak).
+        if (!partial && e.row_order == nullptr && e.residual == nullptr && vec && (g.n & 3) == 0 && row0 + 32 <= g.m &&
+            ((reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.shift)) & 15) == 0) {
+            const bool clampd = e.lo <= e.hi;
+            float *orow = e.out + (row0 + rsub) * (long long)ld + c4;
+            for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+                const int col = c0 + c4;
+                const bool live = col < g.n;                      // (n % 4 == 0: a lane's 4 columns are all in or all out)
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && e.scale) sc = __ldg(reinterpret_cast<const float4 *>(e.scale + col));   // in flight during the TMEM load
+                if (live && e.shift) sh = __ldg(reinterpret_cast<const float4 *>(e.shift + col));
+                float v[32];
+                tmem_ld_32x32(t_acc + (uint32_t)c0, v);           // warp-collective: no divergence around it
+                if (c0 >= g.n) continue;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(st + lane * TP + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = *reinterpret_cast<const float4 *>(st + (i * 4 + rsub) * TP + c4);
+                        float4 y;
+                        y.x = t.x * sc.x + sh.x; y.y = t.y * sc.y + sh.y; y.z = t.z * sc.z + sh.z; y.w = t.w * sc.w + sh.w;
+                        y.x = y.x > 0.f ? y.x : y.x * e.slope; y.y = y.y > 0.f ? y.y : y.y * e.slope;
+                        y.z = y.z > 0.f ? y.z : y.z * e.slope; y.w = y.w > 0.f ? y.w : y.w * e.slope;
+                        if (clampd) {
+                            y.x = fminf(fmaxf(y.x, e.lo), e.hi); y.y = fminf(fmaxf(y.y, e.lo), e.hi);
+                            y.z = fminf(fmaxf(y.z, e.lo), e.hi); y.w = fminf(fmaxf(y.w, e.lo), e.hi);
+                        }
+                        *reinterpret_cast<float4 *>(orow + (long long)(i * 4) * ld + c0) = y;
+                    }
+                }
+            }
+            return;
+        }
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
             tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // warp-collective: no divergence around it
@@ -677,7 +717,13 @@ struct PlainAsyncProducer {
     static constexpr bool kAsync = true;
     static constexpr int kIssuerWarps = 0;                   // dedicated issue warps: measured neutral for these streaming rows (4 tried)
     static constexpr int kIssueThreads = kIssuerWarps > 0 ? 32 * kIssuerWarps : 256;
-    static constexpr int kIssuers = kIssueThreads, kLookahead = 2;
+    // kBulkRows: every row's chunk slice (<= 256 contiguous bytes) travels as ONE 1-D bulk TMA copy (cp.async.bulk,
+    // completion by mbarrier transaction bytes) issued by thread r of the first 128 producer threads: 4 warp instructions
+    // per chunk instead of 64 LDGSTS requests (tools/trace_linear.py: ~1100 of a chunk's ~3500 producer cycles were
+    // the load/store unit working through those requests).  Needs 16-byte aligned rows (ldx % 4 == 0, checked by the
+    // launcher).  raw_full[] then counts ONE arrival (the expect_tx of producer thread 0).
+    static constexpr bool kBulkRows = true;
+    static constexpr int kIssuers = kBulkRows ? 1 : kIssueThreads, kLookahead = 2;
     static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
     static constexpr int kRawBytes = TILE_M * ROW_PITCH;
     using Args = PlainProducer::Args;
@@ -690,10 +736,20 @@ struct PlainAsyncProducer {
     // (t >> 4) + RSTEP j: a warp-level LDGSTS touches 4 lines.  (One thread per row-half copying its pieces one after the
     // other made every request touch 32 lines - the load/store unit then needs ~28 cycles per request, see costvol_tc.cu.)
     __device__ __forceinline__ void issue(int tile, int chunk, int /*next_tile*/, unsigned char *raw, uint64_t *bar, int ptid) {
-        const int q = ptid & 15, rb = ptid >> 4;
         const int k0 = chunk * CHUNK_K;
         const int pieces = max(0, min(CHUNK_K, a.k - k0)) >> 2;
         const long long row0 = (long long)tile * TILE_M;
+        if constexpr (kBulkRows) {
+            const uint32_t bytes = (uint32_t)pieces * 16u;
+            if (ptid == 0) mbar_expect_tx(bar, bytes * TILE_M);
+            if (ptid < TILE_M && bytes != 0) {
+                long long row = row0 + ptid;
+                if (row >= g.m) row = g.m - 1;               // padded rows repeat the last row; never stored
+                tma_load_1d(raw + ptid * ROW_PITCH, a.x + row * a.ldx + k0, bytes, bar);
+            }
+            return;
+        }
+        const int q = ptid & 15, rb = ptid >> 4;
         if (q < pieces) {
             constexpr int RSTEP = kIssueThreads / 16;        // rows covered by one pass of the issuing threads
 #pragma unroll

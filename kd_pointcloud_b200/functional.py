@@ -154,6 +154,8 @@ def _sorted_cloud(xyz_d: torch.Tensor) -> torch.Tensor:
 
 def _knn_compute(nsample: int, xyz_d: torch.Tensor, new_d: torch.Tensor) -> torch.Tensor:
     n, s = xyz_d.shape[1], new_d.shape[1]
+    if xyz_d.shape[2] != 3:                        # feature-space kNN (CrossLayerLightFG, pointconv_util.py:1905)
+        return K.knn_feat(new_d, xyz_d, nsample)[0]
     if ops.SORT_MIN_N <= n <= ops.SORT_MAX_N and s <= ops.SORT_MAX_N and xyz_d.shape[0] > 0:
         cs = _sorted_cloud(xyz_d)
         same = new_d.data_ptr() == xyz_d.data_ptr() and new_d.shape == xyz_d.shape

@@ -279,6 +279,29 @@ _register("knn_dist(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn
                            q.new_empty((q.shape[0], q.shape[1], k))))
 
 
+def _knn_feat(query: torch.Tensor, cand: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """query [B,S,C], cand [B,N,C] (any C <= 512) -> (idx int32 [B,S,k], dist [B,S,k]), ascending (distance, index)."""
+    _req(query, torch.float32, 3, "new_xyz")
+    _req(cand, torch.float32, 3, "xyz")
+    B, S, C = query.shape
+    N = cand.shape[1]
+    if cand.shape[0] != B or cand.shape[2] != C:
+        raise ValueError("kdpc: knn_feat query / candidate shapes do not match")
+    if k > N:
+        raise RuntimeError(f"kdpc: knn k={k} exceeds the number of candidates {N}")
+    with _guard(query):
+        idx = torch.empty((B, S, k), dtype=torch.int32, device=query.device)
+        dist = torch.empty((B, S, k), dtype=torch.float32, device=query.device)
+        if idx.numel():
+            _call("kdpc_knn_feat", B, S, N, C, k, _p(query), _p(cand), _p(idx), _p(dist), _stream())
+    return idx, dist
+
+
+_register("knn_feat(Tensor query, Tensor cand, int k) -> (Tensor, Tensor)", _knn_feat,
+          lambda q, c, k: (q.new_empty((q.shape[0], q.shape[1], k), dtype=torch.int32),
+                           q.new_empty((q.shape[0], q.shape[1], k))))
+
+
 def _knn_bruteforce(query: torch.Tensor, cand: torch.Tensor, k: int) -> torch.Tensor:
     _req(query, torch.float32, 3, "new_xyz")
     _req(cand, torch.float32, 3, "xyz")

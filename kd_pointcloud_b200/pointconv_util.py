@@ -268,6 +268,10 @@ class PointConvD(_PointConvBase):
         return cm(new_xyz), cm(feats), fps_idx
 
 
+class PointConvWeight(PointConvD):
+    """pointconv_util2.py:434-481: textually PointConvD under another name (models_bid_lighttoken_weight48.py)."""
+
+
 # ----------------------------------------------------------------------------------- a13
 class CrossLayerLight(nn.Module):
     """Bidirectional cost volume, pointconv_util.py:1791-1868."""
@@ -297,14 +301,16 @@ class CrossLayerLight(nn.Module):
                 self.mlp2.append(Conv2d(cin, cout, bn=bn, use_leaky=use_leaky))
         self.relu = _act(use_leaky)
 
-    def cross_pm(self, xyz1, xyz2, points1, points2, pos, mlp, bn) -> torch.Tensor:
+    def cross_pm(self, xyz1, xyz2, points1, points2, pos, mlp, bn, idx=None) -> torch.Tensor:
         """All point-major: xyz1 [B,N1,3] queries, xyz2 [B,N2,3], points1 [B,N1,D], points2 [B,N2,D]
-        -> [B,N1,D'].   relu(bn(p2[idx] + p1 + pos(xyz2[idx]-xyz1))) -> mlp -> max over K."""
-        idx = knn_idx(self.nsample, xyz2, xyz1)
+        -> [B,N1,D'].   relu(bn(p2[idx] + p1 + pos(xyz2[idx]-xyz1))) -> mlp -> max over K.
+        ``idx`` int32 [B,N1,K]: the neighbourhood when the caller builds it itself (CrossLayerLightFG)."""
+        if idx is None:
+            idx = knn_idx(self.nsample, xyz2, xyz1)
         D = points1.shape[2]
         needs_grad = torch.is_grad_enabled() and any(
             t.requires_grad for t in (xyz1, xyz2, points1, points2, pos.weight, pos.bias))
-        if (FUSED_COSTVOL and isinstance(bn, nn.Identity) and not needs_grad and self.nsample == 32 and D % 8 == 0 and D <= 256
+        if (FUSED_COSTVOL and isinstance(bn, nn.Identity) and not needs_grad and idx.shape[2] == 32 and D % 8 == 0 and D <= 256
                 and points2.shape[2] == D and len(mlp) == 1 and _is_pointwise(mlp[0].composed_module[0])
                 and isinstance(mlp[0].composed_module[1], nn.Identity) and mlp[0].out_channels <= 256
                 and KF.fused_linear_available(points1, mlp[0].composed_module[0].weight, mlp[0].composed_module[0].bias, None)):
@@ -351,6 +357,61 @@ class CrossLayerLight(nn.Module):
 
     def forward(self, pc1, pc2, feat1, feat2):
         return tuple(cm(t) for t in self.forward_pm(pm(pc1), pm(pc2), pm(feat1), pm(feat2)))
+
+
+class NoCrossLayerLight(CrossLayerLight):
+    """pointconv_util.py:1276-1331 (pointconv_util2.py:1197): ONE cost-volume direction, cross_t1/cross_t2 + pos + mlp.
+    ``bn`` is used by truthiness exactly like the reference (models_bid_no_cross.py:26 passes a list in its place)."""
+
+    def __init__(self, nsample, in_channel, mlp1, bn=use_bn, use_leaky=True, output_clue=False):
+        nn.Module.__init__(self)
+        self.nsample = nsample
+        self.output_clue = output_clue
+        self.mlp1_convs = nn.ModuleList()
+        if bn:
+            self.mlp1_bns = nn.ModuleList()
+        self.cross_t1 = nn.Conv1d(in_channel, mlp1[0], 1)
+        self.cross_t2 = nn.Conv1d(in_channel, mlp1[0], 1)
+        self.pos = nn.Conv2d(3, mlp1[0], 1)
+        self.bias = nn.Parameter(torch.randn((1, mlp1[0], 1, 1)), requires_grad=True)       # unused in cross()
+        self.bn = nn.BatchNorm2d(mlp1[0]) if bn else nn.Identity()
+        self.mlp = nn.ModuleList()
+        for cin, cout in zip(mlp1[:-1], mlp1[1:]):
+            self.mlp.append(Conv2d(cin, cout, bn=bn, use_leaky=use_leaky))
+        self.relu = _act(use_leaky)
+
+    def forward_pm(self, pc1, pc2, feat1, feat2):
+        return self.cross_pm(pc1, pc2, _linear_pm(self.cross_t1, feat1), _linear_pm(self.cross_t2, feat2), self.pos, self.mlp, self.bn)
+
+    def forward(self, pc1, pc2, feat1, feat2):
+        return cm(self.forward_pm(pm(pc1), pm(pc2), pm(feat1), pm(feat2)))
+
+
+class CrossLayerLightFG(CrossLayerLight):
+    """pointconv_util.py:1871-1957: the cost volume over a neighbourhood made of nsample/2 nearest neighbours in a
+    FEATURE space (knn1 / knn2, any channel count: csrc/knn_feat.cu) followed by nsample/2 nearest in xyz; all three
+    cross() calls are followed by cross_t1 / cross_t2 as in the reference's forward (:1944-1957)."""
+
+    def cross_fg_pm(self, xyz1, xyz2, points1, points2, knn1, knn2, pos, mlp, bn, nsample=None):
+        half = (self.nsample if nsample is None else nsample) // 2
+        idx = torch.cat([knn_idx(half, knn2, knn1), knn_idx(half, xyz2, xyz1)], dim=2).contiguous()
+        return self.cross_pm(xyz1, xyz2, points1, points2, pos, mlp, bn, idx=idx)
+
+    def cross(self, xyz1, xyz2, points1, points2, knn1, knn2, pos, mlp, bn, nsample=None):
+        return cm(self.cross_fg_pm(pm(xyz1), pm(xyz2), pm(points1), pm(points2), pm(knn1), pm(knn2), pos, mlp, bn, nsample))
+
+    def forward_pm(self, pc1, pc2, feat1, feat2, knn1, knn2):
+        a = self.cross_fg_pm(pc1, pc2, _linear_pm(self.cross_t11, feat1), _linear_pm(self.cross_t22, feat2), knn1, knn2,
+                             self.pos1, self.mlp1, self.bn1)
+        a = _linear_pm(self.cross_t1, a)
+        b = self.cross_fg_pm(pc2, pc1, _linear_pm(self.cross_t11, feat2), _linear_pm(self.cross_t22, feat1), knn2, knn1,
+                             self.pos1, self.mlp1, self.bn1)
+        b = _linear_pm(self.cross_t2, b)
+        c = self.cross_fg_pm(pc1, pc2, a, b, knn1, knn2, self.pos2, self.mlp2, self.bn2)
+        return a, b, c
+
+    def forward(self, pc1, pc2, feat1, feat2, knn1, knn2):
+        return tuple(cm(t) for t in self.forward_pm(pm(pc1), pm(pc2), pm(feat1), pm(feat2), pm(knn1), pm(knn2)))
 
 
 # ------------------------------------------------------------------------------ a14, a15
@@ -425,5 +486,5 @@ class SceneFlowEstimatorResidual(nn.Module):
 __all__: List[str] = [
     "LEAKY_RATE", "use_bn", "Conv1d", "Conv2d", "ConvBNReLU", "BottleNeck", "square_distance", "knn_point",
     "index_points_gather", "index_points_group", "group", "group_query", "WeightNet", "PointConv", "PointConvD",
-    "CrossLayerLight", "PointWarping", "UpsampleFlow", "SceneFlowEstimatorResidual", "pointnet2_utils",
+    "CrossLayerLight", "CrossLayerLightFG", "NoCrossLayerLight", "PointConvWeight", "PointWarping", "UpsampleFlow", "SceneFlowEstimatorResidual", "pointnet2_utils",
 ]

@@ -228,13 +228,22 @@ def pointconvd(sd, prefix, npoint, nsample, xyz, points, knn_impl="c"):
     return new_xyz.permute(0, 2, 1), _pointconv_tail(sd, prefix, new_points, rel, B, npoint, False, False), fps_idx
 
 
-def cross(sd, nsample, xyz1, xyz2, points1, points2, pos_prefix, mlp_prefix, knn_impl="c"):
-    """CrossLayerLight.cross, pointconv_util.py:1826-1850 (bn = Identity)."""
+def knn_point_feat(nsample: int, feats: torch.Tensor, new_feats: torch.Tensor) -> torch.Tensor:
+    """knn_point on C-dimensional FEATURES (CrossLayerLightFG, pointconv_util.py:1905): the reference's matmul
+    expansion, selected by ascending (distance, index) (stable sort) instead of topk's unspecified order."""
+    sq = square_distance(new_feats, feats)
+    return torch.sort(sq, dim=-1, stable=True)[1][..., :nsample]
+
+
+def cross(sd, nsample, xyz1, xyz2, points1, points2, pos_prefix, mlp_prefix, knn_impl="c", idx=None):
+    """CrossLayerLight.cross, pointconv_util.py:1826-1850 (bn = Identity).  ``idx``: a neighbourhood built by the caller."""
     B, C, N1 = xyz1.shape
     D1 = points1.shape[1]
     x1, x2 = xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1)
     p1, p2 = points1.permute(0, 2, 1), points2.permute(0, 2, 1)
-    idx = knn_point(nsample, x2, x1, knn_impl)
+    if idx is None:
+        idx = knn_point(nsample, x2, x1, knn_impl)
+    nsample = idx.shape[2]
     direction = index_points_group(x2, idx) - x1.view(B, N1, 1, C)
     g2 = index_points_group(p2, idx).permute(0, 3, 2, 1)
     g1 = p1.view(B, N1, 1, D1).repeat(1, 1, nsample, 1).permute(0, 3, 2, 1)
@@ -256,6 +265,31 @@ def cross_layer_light(sd, prefix, nsample, pc1, pc2, feat1, feat2, knn_impl="c")
     f1 = conv1d(sd, prefix + ".cross_t1", f1, act=False)
     f2 = conv1d(sd, prefix + ".cross_t2", f2, act=False)
     f3 = cross(sd, nsample, pc1, pc2, f1, f2, prefix + ".pos2", prefix + ".mlp2", knn_impl)
+    return f1, f2, f3
+
+
+def no_cross_layer_light(sd, prefix, nsample, pc1, pc2, feat1, feat2, knn_impl="c"):
+    """NoCrossLayerLight.forward, pointconv_util.py:1276-1331 (bn = Identity)."""
+    t1 = conv1d(sd, prefix + ".cross_t1", feat1, act=False)
+    t2 = conv1d(sd, prefix + ".cross_t2", feat2, act=False)
+    return cross(sd, nsample, pc1, pc2, t1, t2, prefix + ".pos", prefix + ".mlp", knn_impl)
+
+
+def cross_layer_light_fg(sd, prefix, nsample, pc1, pc2, feat1, feat2, knn1, knn2, knn_impl="c"):
+    """CrossLayerLightFG.forward, pointconv_util.py:1871-1957: neighbourhood = nsample/2 nearest in the feature space
+    knn1/knn2 followed by nsample/2 nearest in xyz."""
+    half = nsample // 2
+
+    def fg(xa, xb, pa, pb, ka, kb, pos, mlp):
+        idx = torch.cat([knn_point_feat(half, kb.permute(0, 2, 1), ka.permute(0, 2, 1)),
+                         knn_point(half, xb.permute(0, 2, 1), xa.permute(0, 2, 1), knn_impl)], dim=-1)
+        return cross(sd, nsample, xa, xb, pa, pb, prefix + pos, prefix + mlp, knn_impl, idx=idx)
+
+    t11 = lambda x: conv1d(sd, prefix + ".cross_t11", x, act=False)
+    t22 = lambda x: conv1d(sd, prefix + ".cross_t22", x, act=False)
+    f1 = conv1d(sd, prefix + ".cross_t1", fg(pc1, pc2, t11(feat1), t22(feat2), knn1, knn2, ".pos1", ".mlp1"), act=False)
+    f2 = conv1d(sd, prefix + ".cross_t2", fg(pc2, pc1, t11(feat2), t22(feat1), knn2, knn1, ".pos1", ".mlp1"), act=False)
+    f3 = fg(pc1, pc2, f1, f2, knn1, knn2, ".pos2", ".mlp2")
     return f1, f2, f3
 
 

@@ -98,6 +98,39 @@ def test_cross_layer_warp_upsample_estimator(golden):
         assert rel(f, g["out_feat"]) < TOL and rel(fl, g["out_flow"]) < TOL
 
 
+def test_layer_variants_against_reference_golden(golden):
+    """NoCrossLayerLight, CrossLayerLightFG (feature-space kNN kernel + fused cost volume) and
+    PointConvWeight against the unmodified reference's outputs."""
+    g = golden("variants")
+    pc1, pc2, f1, f2, k1, k2 = (T(g[k]) for k in ("pc1", "pc2", "feat1", "feat2", "knn1", "knn2"))
+    with torch.no_grad():
+        idx, dist = torch.ops.kdpc.knn_feat(k1.permute(0, 2, 1).contiguous(), k2.permute(0, 2, 1).contiguous(), 16)
+        assert (dist[..., 1:] >= dist[..., :-1]).all()
+        assert np.array_equal(torch.sort(idx, dim=-1)[0].cpu().numpy(), g["knn_feat16"])
+        # brute-force check of the feature-space kNN at a larger, ragged shape (C = 37, K = 9, 300 queries, 1000 candidates)
+        gen = torch.Generator().manual_seed(2)
+        q, c = torch.randn(3, 300, 37, generator=gen), torch.randn(3, 1000, 37, generator=gen)
+        i2, d2 = torch.ops.kdpc.knn_feat(q.to(DEV), c.to(DEV), 9)
+        ref = torch.cdist(q.double(), c.double()).pow(2).topk(9, largest=False)
+        assert torch.equal(torch.sort(i2.cpu().long(), -1)[0], torch.sort(ref[1], -1)[0])
+        assert torch.allclose(d2.cpu().double(), ref[0], rtol=1e-4, atol=1e-4)
+
+        nc, _ = load(P.NoCrossLayerLight(32, 24, [16, 16]), 11)
+        assert rel(nc(pc1, pc2, f1, f2), g["nocross"]) < TOL
+        fg, _ = load(P.CrossLayerLightFG(32, 24, [16, 16], [16, 16]), 12)
+        for fused in (True, False):
+            P.FUSED_COSTVOL = fused
+            try:
+                a, b, c3 = fg(pc1, pc2, f1, f2, k1, k2)
+            finally:
+                P.FUSED_COSTVOL = True
+            assert rel(a, g["fg1"]) < TOL and rel(b, g["fg2"]) < TOL and rel(c3, g["fg3"]) < TOL, fused
+        pw, _ = load(P.PointConvWeight(64, 16, 29 + 3, 40), 13)
+        nx, ny, fi = pw(pc1, T(g["pcw_points"]))
+        assert np.array_equal(fi.cpu().numpy(), g["pcw_fps"]) and rel(ny, g["pcw_out"]) < TOL
+        assert np.array_equal(nx.cpu().numpy(), g["pcw_new_xyz"])
+
+
 def test_multiscale_loss(golden):
     g = golden("multiscale_loss")
     loss = L.multiScaleLoss([T(g["p0"]), T(g["p1"]), T(g["p2"])], T(g["gt"]), [T(g["fps1"]), T(g["fps2"])])

@@ -151,3 +151,22 @@ def test_kd_loss_oracles_match_reference_golden(golden):
     with pytest.raises(RuntimeError):                      # equal student/teacher widths: the reference raises
         O.cross_bidirection_loss_ht(preds, s1, fps, gt, t0, t1, t2, 0.3, 0.8, layer=[2, 3])
     assert int(g["cross_equal_width_raises"]) == 1
+
+
+def test_layer_variant_oracles_match_reference_golden(golden):
+    """NoCrossLayerLight / CrossLayerLightFG / PointConvWeight restatements against the unmodified
+    reference's outputs (tests/make_golden_variants.py)."""
+    from kd_pointcloud_b200 import pointconv_util as P
+    g = golden("variants")
+    pc1, pc2, f1, f2, k1, k2 = (T(g[k]) for k in ("pc1", "pc2", "feat1", "feat2", "knn1", "knn2"))
+    sd = _sd(_shapes(P.NoCrossLayerLight(32, 24, [16, 16])), 11, "n.")
+    assert _rel(O.no_cross_layer_light(sd, "n", 32, pc1, pc2, f1, f2), g["nocross"]) < 1e-5
+    sd = _sd(_shapes(P.CrossLayerLightFG(32, 24, [16, 16], [16, 16])), 12, "c.")
+    outs = O.cross_layer_light_fg(sd, "c", 32, pc1, pc2, f1, f2, k1, k2)
+    for o, name in zip(outs, ("fg1", "fg2", "fg3")):
+        assert _rel(o, g[name]) < 1e-5
+    idx = torch.sort(O.knn_point_feat(16, k2.permute(0, 2, 1), k1.permute(0, 2, 1)), dim=-1)[0]
+    assert np.array_equal(idx.numpy(), g["knn_feat16"])
+    sd = _sd(_shapes(P.PointConvWeight(64, 16, 32, 40)), 13, "p.")
+    nx, ny, fi = O.pointconvd(sd, "p", 64, 16, pc1, T(g["pcw_points"]))
+    assert np.array_equal(fi.numpy(), g["pcw_fps"]) and _rel(ny, g["pcw_out"]) < 1e-5

@@ -56,7 +56,8 @@ def main():
         torch.cuda.synchronize()
         ts = []
         for _ in range(iters):
-            flush.zero_()
+            torch.cuda._sleep(400000)                      # ~0.2 ms of GPU spin: the host runs ahead, so the events bracket
+            flush.zero_()                                  # GPU execution only (no Python / dispatcher launch latency)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
