@@ -36,6 +36,21 @@ typedef struct CUstream_st *kdpc_stream_t;
 int kdpc_abi_version(void);
 const char *kdpc_error_string(int code);
 
+/* ---- input pipeline (transforms/transforms.py:137-316: ProcessData, Augmentation) ---------------------------------
+ * A batch of padded raw clouds pc*_raw [B,nmax,stride>=3] with n_raw[B] valid points each.
+ * kdpc_dataprep_mask: optional augmentation (affine[b] = m1[9] t1[3] m2[9] t2[3] as the reference builds them,
+ *   jitter1 / jitter2 [B,nmax,3] or NULL), flow = pc2' - pc1', depth mask (pc1.z < T && pc2.z < T; T <= 0: all),
+ *   stable compaction (np.where) into the workspace; count[b] = number of survivors.
+ * kdpc_dataprep_select: out[b,j] = survivors[sel[b,j]] for caller-supplied draws sel1 / sel2 (positions in the
+ *   survivor list, exactly what np.random.choice(indices, n, replace) draws); status[b] bit 0 = draw out of range. */
+long long kdpc_dataprep_workspace_bytes(int b, int nmax);
+int kdpc_dataprep_mask(int b, int nmax, int stride, float depth_threshold, int augment, const int *n_raw,
+                       const float *pc1_raw, const float *pc2_raw, const float *affine, const float *jitter1,
+                       const float *jitter2, void *ws, int *count, kdpc_stream_t stream);
+int kdpc_dataprep_select(int b, int nmax, int num_points, const void *ws, const int *count, const int *sel1,
+                         const int *sel2, float *out_pc1, float *out_pc2, float *out_sf, int *status,
+                         kdpc_stream_t stream);
+
 /* ---- pointnet2 ops (channel-major API of pointnet2/pointnet2_utils.py) ----------------- */
 
 /* furthest_point_sampling_kernel_launcher, sampling_gpu.h:26-27 / sampling_gpu.cu:93-253.
@@ -195,6 +210,13 @@ int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, const voi
 int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const float *w,
                      const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
                      const float *residual, float *out, int ldo, kdpc_stream_t stream);
+
+/* Weight gradient of y = x W^T (nn.Linear / 1x1 conv; reference: autograd of pointconv_util.py:20-54, 223, 250):
+ * dw[n,k] = sum_m dy[m,n] * x[m,k] on tcgen05 with MN-major operand tiles (bf16 hi/lo, fp32 accumulation), the row range
+ * split over CTAs and reduced in split order (deterministic).  ws: kdpc_linear_dw_ws_bytes(m, n, k) bytes. */
+long long kdpc_linear_dw_ws_bytes(long long m, int n, int k);
+int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy, const float *x, int ldx, void *ws,
+                   float *dw, int lddw, kdpc_stream_t stream);
 
 /* PointConv (pointconv_util.py:231-258) fused end to end for inference: neighbour gather + relative xyz +
  * WeightNet(3->8->8->16, ReLU) + sum over K + Linear(16(d+3) -> n_out) + scale/shift (bias, eval BatchNorm) +

@@ -1,0 +1,291 @@
+// Weight gradient of every Linear / 1x1 convolution of the training path on tcgen05 (sm_100a):
+//
+//        dW[n, k] = sum_m dY[m, n] * X[m, k]          (what autograd computes for nn.Linear / nn.Conv1d(k=1):
+//                                                       reference pointconv_util.py:20-54, 223, 250 via loss.backward(),
+//                                                       distilTrain.py:180)
+//
+// The reduction runs over the ROWS m (65 536 .. 262 144 points), the output is small (N <= 256 by K <= 2096), so both
+// operands are "MN-major" for the tensor core: dY[m, :] and X[m, :] are contiguous along the NON-reduced index.  No
+// transposition anywhere: producers read 8 consecutive floats of a row, split them into bf16 hi / lo and store ONE
+// 16-byte unit into the canonical MN-major SWIZZLE_128B tile (atom = 64 MN elements x 8 reduction rows, 16-byte units
+// XOR-swizzled by the row, atoms LBO apart along MN and SBO apart along the reduction), and tcgen05.mma is issued with
+// a_major = b_major = MN.  fp32 accuracy from three bf16 MMAs per step (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM.
+// (torch's fp32 mm for this product runs on the CUDA cores - cutlass_80_simt_sgemm - and was 28 % of the KD step.)
+//
+// Work decomposition: output tiles of 128 (n) x KT <= 256 (k); the row range is split over CTAs so that ~all SMs work
+// (few output tiles, very long reduction); every CTA leaves its partial tile in a workspace and dw_reduce_kernel adds
+// the partials in split order: deterministic.
+#include "tc_common.cuh"
+
+namespace kdpc {
+namespace tc {
+
+constexpr int DW_MCHUNK = 64;                       // reduction rows per pipeline stage (4 UMMA K-steps)
+constexpr int DW_TN = 128;                          // n rows of an output tile (UMMA M)
+constexpr int DW_KT = 256;                          // k columns of an output tile (UMMA N), multiple of 64 in smem
+constexpr int DW_SBO = 1024;                        // bytes between 8-row reduction groups (one swizzle atom)
+constexpr int DW_LBO = DW_MCHUNK / 8 * DW_SBO;      // bytes between 64-element MN groups: 8 atoms = 8192
+constexpr int DW_A_PART = DW_TN / 64 * DW_LBO;      // one bf16 part (hi or lo) of the dY tile: 16 KB
+constexpr int DW_PRODUCERS = 256;
+constexpr int DW_THREADS = DW_PRODUCERS + 32 + 128; // producers + MMA warp + 4 epilogue warps
+
+// Shared-memory matrix descriptor, MN-major SWIZZLE_128B (cute UMMA::make_umma_desc<Major::MN>):
+//   [0,14) addr >> 4 | [16,30) LBO >> 4 (between 64-element MN groups) | [32,46) SBO >> 4 (between 8-row K groups)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor: bf16 x bf16 -> fp32, BOTH operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n) {
+    return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
+}
+// byte offset of the 16-byte unit holding MN elements [8c, 8c+8) of reduction row r inside an MN-major tile
+__device__ __forceinline__ uint32_t mn_offset(int mn_unit, int r) {
+    const int g = mn_unit >> 3, c = mn_unit & 7;                 // 64-element group, unit inside it
+    return (uint32_t)(g * DW_LBO + (r >> 3) * DW_SBO + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+struct DwArgs {
+    const float *dy;      // [M, ldy]
+    const float *x;       // [M, ldx]
+    long long m;
+    int n, k, ldy, ldx;
+    int n_tiles, k_tiles, splits;
+    long long rows_per_split;        // multiple of DW_MCHUNK
+    float *partial;                  // [splits][n_tiles * 128][k_tiles * 256]
+};
+
+// unit = 8 consecutive floats of one source row -> (hi, lo) 16-byte units; `width` valid floats from `col0`
+__device__ __forceinline__ void dw_load_unit(const float *rowp, bool row_ok, int col0, int width, bool vec, float (&v)[8]) {
+    if (row_ok && vec && col0 + 8 <= width) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(rowp + col0));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(rowp + col0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (row_ok && col0 + j < width) ? __ldg(rowp + col0 + j) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw_tc_kernel(const DwArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[2], empty[2], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    // work item -> (n tile, k tile, split)
+    const int tiles = a.n_tiles * a.k_tiles;
+    const int split = blockIdx.x / tiles;
+    const int tile = blockIdx.x - split * tiles;
+    const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
+    const int n0 = nt * DW_TN, k0 = kt * DW_KT;
+    const int kw = min(DW_KT, a.k - k0);                         // valid k columns of this tile
+    const int kgroups = (kw + 63) >> 6;                          // 64-column groups staged in shared memory
+    const int umma_n = (kw + 15) & ~15;                          // UMMA N (multiple of 16)
+    const int b_part = kgroups * DW_LBO;                         // one bf16 part of the X tile
+    const int stage_bytes = 2 * DW_A_PART + 2 * b_part;
+    const long long m_begin = (long long)split * a.rows_per_split;
+    const long long m_end = min(a.m, m_begin + a.rows_per_split);
+    const int chunks = m_end > m_begin ? (int)((m_end - m_begin + DW_MCHUNK - 1) / DW_MCHUNK) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&full[s], DW_PRODUCERS / 32); mbar_init(&empty[s], 1); }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == DW_PRODUCERS / 32) tmem_alloc(&tmem_base_smem, 256u);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < DW_PRODUCERS / 32) {
+        // ================= producers: fp32 rows -> bf16 hi/lo, MN-major SW128 tiles =================
+        const bool vec_y = (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 && (n0 & 3) == 0;
+        const bool vec_x = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+        const int a_units = DW_MCHUNK * (DW_TN / 8);             // 1024: (row r, unit u) = (i / 16, i % 16)
+        const int b_upr = kgroups * 8;                           // units per row of the X tile
+        const int b_units = DW_MCHUNK * b_upr;
+        for (int c = 0; c < chunks; ++c) {
+            const int s = c & 1;
+            mbar_wait(&empty[s], ((c >> 1) & 1) ^ 1);
+            unsigned char *st = smem + (size_t)s * stage_bytes;
+            unsigned char *a_hi = st, *a_lo = st + DW_A_PART, *b_hi = st + 2 * DW_A_PART, *b_lo = b_hi + b_part;
+            const long long row0 = m_begin + (long long)c * DW_MCHUNK;
+            // dY tile: 64 rows x 128 columns (n0 ..)
+            for (int i0 = tid; i0 < a_units; i0 += 4 * DW_PRODUCERS) {
+                float v[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * DW_PRODUCERS;
+                    const int r = i >> 4, u = i & 15;
+                    const long long row = row0 + r;
+                    dw_load_unit(a.dy + row * a.ldy + n0, i < a_units && row < m_end, u * 8, a.n - n0, vec_y, v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * DW_PRODUCERS;
+                    if (i < a_units) {
+                        uint4 hi, lo;
+                        split8(v[j], hi, lo);
+                        const uint32_t off = mn_offset(i & 15, i >> 4);
+                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    }
+                }
+            }
+            // X tile: 64 rows x (kgroups * 64) columns (k0 ..)
+            for (int i0 = tid; i0 < b_units; i0 += 4 * DW_PRODUCERS) {
+                float v[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * DW_PRODUCERS;
+                    const int r = i / b_upr, u = i - r * b_upr;
+                    const long long row = row0 + r;
+                    dw_load_unit(a.x + row * a.ldx + k0, i < b_units && row < m_end, u * 8, a.k - k0, vec_x && (k0 & 3) == 0, v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * DW_PRODUCERS;
+                    if (i < b_units) {
+                        const int r = i / b_upr, u = i - r * b_upr;
+                        uint4 hi, lo;
+                        split8(v[j], hi, lo);
+                        const uint32_t off = mn_offset(u, r);
+                        *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                        *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+    } else if (warp == DW_PRODUCERS / 32) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_bf16_mn(DW_TN, umma_n);
+        const uint32_t base = smem_u32(smem);
+        for (int c = 0; c < chunks; ++c) {
+            const int s = c & 1;
+            mbar_wait(&full[s], (c >> 1) & 1);
+            fence_after_sync();
+            const uint32_t a_hi = base + (uint32_t)s * (uint32_t)stage_bytes, a_lo = a_hi + DW_A_PART;
+            const uint32_t b_hi = a_hi + 2 * DW_A_PART, b_lo = b_hi + (uint32_t)b_part;
+            const bool leader = elect_one();
+#pragma unroll
+            for (int kk = 0; kk < DW_MCHUNK / UMMA_K; ++kk) {
+                const uint32_t off = (uint32_t)kk * 2u * DW_SBO;              // 16 reduction rows = two 8-row groups
+                const uint64_t dah = make_smem_desc_mn_sw128(a_hi + off, DW_LBO, DW_SBO), dal = make_smem_desc_mn_sw128(a_lo + off, DW_LBO, DW_SBO);
+                const uint64_t dbh = make_smem_desc_mn_sw128(b_hi + off, DW_LBO, DW_SBO), dbl = make_smem_desc_mn_sw128(b_lo + off, DW_LBO, DW_SBO);
+                if (leader) {
+                    umma_bf16(tmem_base, dah, dbh, idesc, (c != 0) || (kk != 0));
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dal, dbh, idesc, 1);
+                }
+            }
+            if (leader) {
+                umma_commit(&empty[s]);
+                if (c == chunks - 1) umma_commit(&done_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue: partial tile -> workspace =================
+        const int quarter = warp & 3;
+        float *prow = a.partial + ((size_t)split * a.n_tiles * DW_TN + (size_t)n0 + quarter * 32 + lane) * ((size_t)a.k_tiles * DW_KT) + k0;
+        if (chunks > 0) {
+            mbar_wait(&done_bar, 0);
+            fence_after_sync();
+        }
+        for (int c0 = 0; c0 < umma_n; c0 += 32) {
+            float v[32];
+            if (chunks > 0) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (c0 + j < umma_n)
+                    *reinterpret_cast<float4 *>(prow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == DW_PRODUCERS / 32) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 256u);
+    }
+}
+
+// dW[n, k] = sum over splits, in split order
+__global__ void __launch_bounds__(256)
+dw_reduce_kernel(int n, int k, int splits, long long split_stride, int ldp, const float *__restrict__ partial,
+                 float *__restrict__ dw, int lddw) {
+    const int kq = (k + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * kq) return;
+    const int row = (int)(t / kq), c0 = (int)(t - (long long)row * kq) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *p = partial + (size_t)row * ldp + c0;
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4 *>(p + (size_t)s * split_stride);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (c0 + j < k) dw[(size_t)row * lddw + c0 + j] = o[j];
+}
+
+static inline void dw_plan(long long m, int n, int k, DwArgs &a) {
+    a.n_tiles = (n + DW_TN - 1) / DW_TN;
+    a.k_tiles = (k + DW_KT - 1) / DW_KT;
+    const int tiles = a.n_tiles * a.k_tiles;
+    const long long mchunks = (m + DW_MCHUNK - 1) / DW_MCHUNK;
+    long long want = (2LL * num_sms() + tiles - 1) / tiles;          // ~2 waves of CTAs
+    if (want > mchunks) want = mchunks;
+    if (want < 1) want = 1;
+    const long long cps = (mchunks + want - 1) / want;               // chunks per split
+    a.rows_per_split = cps * DW_MCHUNK;
+    a.splits = (int)((mchunks + cps - 1) / cps);
+}
+
+}  // namespace tc
+}  // namespace kdpc
+
+using namespace kdpc;
+using namespace kdpc::tc;
+
+KDPC_API long long kdpc_linear_dw_ws_bytes(long long m, int n, int k) {
+    if (m <= 0 || n <= 0 || k <= 0) return 0;
+    DwArgs a{};
+    dw_plan(m, n, k, a);
+    return (long long)a.splits * a.n_tiles * DW_TN * a.k_tiles * DW_KT * (long long)sizeof(float);
+}
+
+/* dW[n,k] = sum_m dY[m,n] X[m,k]  (weight gradient of y = x W^T).  dy [M,ldy], x [M,ldx], dw [N,lddw]; ws: kdpc_linear_dw_ws_bytes. */
+KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy, const float *x, int ldx, void *ws,
+                            float *dw, int lddw, kdpc_stream_t stream) {
+    KDPC_CHECK_ARGS(dy && x && ws && dw && m > 0 && n > 0 && k > 0 && ldy >= n && ldx >= k && lddw >= k);
+    if ((reinterpret_cast<uintptr_t>(ws) % 16) != 0) return KDPC_EINVAL;
+    DwArgs a{};
+    a.dy = dy; a.x = x; a.m = m; a.n = n; a.k = k; a.ldy = ldy; a.ldx = ldx;
+    dw_plan(m, n, k, a);
+    a.partial = reinterpret_cast<float *>(ws);
+    const size_t smem = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)(DW_KT / 64) * DW_LBO) + 1024;
+    KDPC_ENSURE_SMEM(dw_tc_kernel, (int)smem);
+    cudaStream_t st = to_stream(stream);
+    const unsigned grid = (unsigned)(a.n_tiles * a.k_tiles * a.splits);
+    dw_tc_kernel<<<grid, DW_THREADS, smem, st>>>(a);
+    const int ldp = a.k_tiles * DW_KT;
+    const long long split_stride = (long long)a.n_tiles * DW_TN * ldp;
+    const long long total = (long long)n * ((k + 3) / 4);
+    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.splits, split_stride, ldp, a.partial, dw, lddw);
+    KDPC_RETURN_LAST();
+}

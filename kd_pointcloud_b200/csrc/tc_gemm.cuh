@@ -722,7 +722,10 @@ struct PlainAsyncProducer {
     // per chunk instead of 64 LDGSTS requests (tools/trace_linear.py: ~1100 of a chunk's ~3500 producer cycles were
     // the load/store unit working through those requests).  Needs 16-byte aligned rows (ldx % 4 == 0, checked by the
     // launcher).  raw_full[] then counts ONE arrival (the expect_tx of producer thread 0).
-    static constexpr bool kBulkRows = true;
+    // MEASURED AND OFF (round 2): 128 per-row bulk copies take ~2300 cycles to issue (the TMA unit accepts roughly
+    // one request per 17 cycles whichever warp sends it) against ~1100 for the 64 LDGSTS requests: 25.2 us instead of
+    // 23.2 us at M = 65536, K = N = 128.  One request per chunk needs a 2-D tensor map (UTMALDG), not per-row copies.
+    static constexpr bool kBulkRows = false;
     static constexpr int kIssuers = kBulkRows ? 1 : kIssueThreads, kLookahead = 2;
     static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
     static constexpr int kRawBytes = TILE_M * ROW_PITCH;

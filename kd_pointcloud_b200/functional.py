@@ -466,8 +466,9 @@ def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
 
 class _LinearTC(torch.autograd.Function):
     """y = x W^T + b for the TRAINING path: forward and the input gradient dX = dY W run on tcgen05 (bf16 hi/lo split,
-    fp32-level accuracy - the same kernel as inference); dW = dY^T X and db are reductions over all rows and stay
-    torch ops.  (torch's own fp32 matmul runs on the CUDA cores: 48 % of the KD training step before this.)"""
+    fp32-level accuracy - the same kernel as inference); dW = dY^T X on tcgen05 with MN-major operand tiles and a
+    deterministic split over the rows (csrc/dw_tc.cu); db = column sums stays a torch reduction.  (torch's own fp32
+    matmul runs on the CUDA cores: cutlass_80_simt_sgemm was 28 % of the KD training step.)"""
 
     @staticmethod
     def forward(ctx, x, w2d, bias):
@@ -484,7 +485,10 @@ class _LinearTC(torch.autograd.Function):
             gx = fused_linear(gy, w2d.detach().t().contiguous(), None, cache_weight=False)   # a one-shot tensor: never cached
         g2 = gy.reshape(-1, gy.shape[-1])
         if ctx.needs_input_grad[1]:
-            gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
+            if USE_TC_DW:
+                gw = K.linear_dw(g2, x.detach().reshape(-1, x.shape[-1]).contiguous())       # tcgen05, MN-major operands
+            else:
+                gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2.sum(0)
         return gx, gw, gb
@@ -501,6 +505,7 @@ def linear_tc_autograd(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.
 
 
 USE_TC_TRAINING = os.environ.get("KDPC_TC_TRAINING", "1") != "0"
+USE_TC_DW = os.environ.get("KDPC_TC_DW", "1") != "0"           # A/B: dW = dY^T X on tcgen05 (csrc/dw_tc.cu) or torch.mm
 
 
 # ------------------------------------------------------------------- fused PointConv / cost volume

@@ -562,6 +562,26 @@ def linear_tc_into(x: torch.Tensor, wpacked: torch.Tensor, n: int, out: torch.Te
                   float(hi), None, _p(ws), out.data_ptr() + 4 * col0, ntot, _stream())
 
 
+def _linear_dw(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [N,K] = dY^T X for dy [..., N], x [..., K] (same leading shape): the weight gradient of y = x W^T, on tcgen05."""
+    _req(dy, torch.float32, None, "grad_out")
+    _req(x, torch.float32, None, "x")
+    n, k = dy.shape[-1], x.shape[-1]
+    m = dy.numel() // max(n, 1)
+    if x.numel() // max(k, 1) != m:
+        raise ValueError("kdpc: linear_dw row counts differ")
+    with _guard(x):
+        dw = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        if m == 0:
+            return dw.zero_()
+        ws = torch.empty((_lib.lib().kdpc_linear_dw_ws_bytes(m, n, k),), dtype=torch.uint8, device=x.device)
+        _call("kdpc_linear_dw", m, n, k, _p(dy), n, _p(x), k, _p(ws), _p(dw), k, _stream())
+    return dw
+
+
+_register("linear_dw(Tensor dy, Tensor x) -> Tensor", _linear_dw, lambda dy, x: dy.new_empty((dy.shape[-1], x.shape[-1])))
+
+
 def _linear_simt(x, w, scale, shift, slope: float, lo: float, hi: float, residual) -> torch.Tensor:
     _req(w, torch.float32, 2, "weight")
     n = w.shape[0]

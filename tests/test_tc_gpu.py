@@ -227,3 +227,41 @@ def test_wide_linear_blocks_written_in_place():
         lo = KF.fused_linear(x, lin.weight[:256], lin.bias[:256], None, 0.1)
     assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
     assert torch.equal(y[..., :256], lo)
+
+
+@pytest.mark.parametrize("m,n,k", [(65536, 128, 128), (4096, 64, 2096), (1000, 32, 35), (128 * 3 + 5, 256, 256), (50, 16, 16),
+                                   (8192, 128, 1072), (300, 200, 520)])
+def test_linear_dw_matches_fp64(m, n, k):
+    """dW = dY^T X on tcgen05 with MN-major operand tiles (csrc/dw_tc.cu) against an fp64 product: ragged row counts,
+    N < 128 (zero-padded tile rows), K tails that are not multiples of 16 / 64 / 256, several split counts."""
+    g = torch.Generator().manual_seed(m + n + k)
+    dy = torch.randn(m, n, generator=g).to(DEV)
+    x = (torch.randn(m, k, generator=g) + 0.5).to(DEV)
+    dw = torch.ops.kdpc.linear_dw(dy, x)
+    ref = dy.double().t() @ x.double()
+    err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
+    assert dw.shape == (n, k) and err < 2e-5, err
+    assert torch.equal(dw, torch.ops.kdpc.linear_dw(dy, x))                 # deterministic
+
+
+def test_linear_tc_autograd_uses_the_tcgen05_weight_gradient():
+    from kd_pointcloud_b200 import functional as KF
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 700, 96, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(48, 96, generator=g) * 0.1).to(DEV).requires_grad_(True)
+    b = torch.randn(48, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(2, 700, 48, generator=g).to(DEV)
+    outs = {}
+    for tc_dw in (True, False):
+        KF.USE_TC_DW = tc_dw
+        try:
+            for t in (x, w, b):
+                t.grad = None
+            KF.linear_tc_autograd(x, w, b).backward(go)
+            outs[tc_dw] = (x.grad.clone(), w.grad.clone(), b.grad.clone())
+        finally:
+            KF.USE_TC_DW = True
+    ref_w = go.double().reshape(-1, 48).t() @ x.detach().double().reshape(-1, 96)
+    for tc_dw in (True, False):
+        assert ((outs[tc_dw][1].double() - ref_w).abs().max() / ref_w.abs().max()).item() < 2e-5
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][2], outs[False][2])
