@@ -151,6 +151,16 @@ int kdpc_weightnet(long long rows, const float *in, int in_stride, int h1, int h
                    const float *w1, const float *b1, const float *w2, const float *b2,
                    const float *w3, const float *b3, float *out, kdpc_stream_t stream);
 
+/* Backward of WeightNet(3 -> 8 -> 8 -> wout), wout in {8, 16} (pointconv_util.py:184-215 under autograd): one kernel
+ * recomputes the forward per row, back-propagates g_out [rows,wout] and reduces the six parameter gradients
+ * deterministically (per-warp partials in ws, kdpc_weightnet_grad_ws_bytes).  g_in [rows,3] (optional): gradient w.r.t.
+ * the localized coordinates. */
+long long kdpc_weightnet_grad_ws_bytes(long long rows);
+int kdpc_weightnet_grad(long long rows, const float *in, int in_stride, int wout, const float *g_out,
+                        const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                        const float *b3, void *ws, float *gw1, float *gb1, float *gw2, float *gb2, float *gw3,
+                        float *gb3, float *g_in, kdpc_stream_t stream);
+
 /* PointConv aggregation, pointconv_util.py:249 / :437: out[r, c*wout + w] =
  * sum_k grouped[r,k,c] * wn[r,k,w].  grouped [R,K,C], wn [R,K,wout] -> out [R, C*wout]. */
 int kdpc_pointconv_agg(long long rows, int k, int c, int wout, const float *grouped, const float *wn,
@@ -216,7 +226,7 @@ int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const f
  * split over CTAs and reduced in split order (deterministic).  ws: kdpc_linear_dw_ws_bytes(m, n, k) bytes. */
 long long kdpc_linear_dw_ws_bytes(long long m, int n, int k);
 int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy, const float *x, int ldx, void *ws,
-                   float *dw, int lddw, kdpc_stream_t stream);
+                   float *dw, int lddw, float *db /* [N] bias gradient = column sums of dy, or NULL */, kdpc_stream_t stream);
 
 /* PointConv (pointconv_util.py:231-258) fused end to end for inference: neighbour gather + relative xyz +
  * WeightNet(3->8->8->16, ReLU) + sum over K + Linear(16(d+3) -> n_out) + scale/shift (bias, eval BatchNorm) +

@@ -51,6 +51,7 @@ struct DwArgs {
     const float *x;       // [M, ldx]
     long long m;
     int n, k, ldy, ldx;
+    int k_eff;                       // k + 1 when the bias gradient rides along as an extra all-ones column of X
     int n_tiles, k_tiles, splits;
     long long rows_per_split;        // multiple of DW_MCHUNK
     float *partial;                  // [splits][n_tiles * 128][k_tiles * 256]
@@ -83,7 +84,7 @@ dw_tc_kernel(const DwArgs a) {
     const int tile = blockIdx.x - split * tiles;
     const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
     const int n0 = nt * DW_TN, k0 = kt * DW_KT;
-    const int kw = min(DW_KT, a.k - k0);                         // valid k columns of this tile
+    const int kw = min(DW_KT, a.k_eff - k0);                     // valid k columns of this tile (incl. the ones column)
     const int kgroups = (kw + 63) >> 6;                          // 64-column groups staged in shared memory
     const int umma_n = (kw + 15) & ~15;                          // UMMA N (multiple of 16)
     const int b_part = kgroups * DW_LBO;                         // one bf16 part of the X tile
@@ -147,6 +148,13 @@ dw_tc_kernel(const DwArgs a) {
                     const int r = i / b_upr, u = i - r * b_upr;
                     const long long row = row0 + r;
                     dw_load_unit(a.x + row * a.ldx + k0, i < b_units && row < m_end, u * 8, a.k - k0, vec_x && (k0 & 3) == 0, v[j]);
+                    // db = sum_m dY[m, :] rides along as column k of X == 1 (valid rows only)
+                    const int oc = a.k - k0 - u * 8;                  // position of the ones column inside this unit
+                    if (a.k_eff != a.k && oc >= 0 && oc < 8 && i < b_units && row < m_end) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q == oc) v[j][q] = 1.f;
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -223,11 +231,11 @@ dw_tc_kernel(const DwArgs a) {
     }
 }
 
-// dW[n, k] = sum over splits, in split order
+// dW[n, k] = sum over splits, in split order; column k (when present) is the bias gradient db[n]
 __global__ void __launch_bounds__(256)
-dw_reduce_kernel(int n, int k, int splits, long long split_stride, int ldp, const float *__restrict__ partial,
-                 float *__restrict__ dw, int lddw) {
-    const int kq = (k + 3) >> 2;
+dw_reduce_kernel(int n, int k, int k_eff, int splits, long long split_stride, int ldp, const float *__restrict__ partial,
+                 float *__restrict__ dw, int lddw, float *__restrict__ db) {
+    const int kq = (k_eff + 3) >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * kq) return;
     const int row = (int)(t / kq), c0 = (int)(t - (long long)row * kq) * 4;
@@ -239,16 +247,22 @@ dw_reduce_kernel(int n, int k, int splits, long long split_stride, int ldp, cons
     }
     const float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
         if (c0 + j < k) dw[(size_t)row * lddw + c0 + j] = o[j];
+        else if (c0 + j == k && k_eff != k) db[row] = o[j];
+    }
 }
 
-static inline void dw_plan(long long m, int n, int k, DwArgs &a) {
+static inline void dw_plan(long long m, int n, int k, bool bias, DwArgs &a) {
+    a.k_eff = k + (bias ? 1 : 0);
     a.n_tiles = (n + DW_TN - 1) / DW_TN;
-    a.k_tiles = (k + DW_KT - 1) / DW_KT;
+    a.k_tiles = (a.k_eff + DW_KT - 1) / DW_KT;
     const int tiles = a.n_tiles * a.k_tiles;
     const long long mchunks = (m + DW_MCHUNK - 1) / DW_MCHUNK;
-    long long want = (2LL * num_sms() + tiles - 1) / tiles;          // ~2 waves of CTAs
+    // one wave of CTAs: every split leaves a [128 x 256] partial tile that dw_reduce_kernel has to read again, so more
+    // splits than SMs only add reduction traffic (2 waves: 296 partial tiles = 19 MB read back for a 64 KB gradient)
+    long long want = (num_sms() + tiles - 1) / tiles;
+    if (want > (mchunks + 3) / 4) want = (mchunks + 3) / 4;          // >= 4 chunks of 64 rows per CTA
     if (want > mchunks) want = mchunks;
     if (want < 1) want = 1;
     const long long cps = (mchunks + want - 1) / want;               // chunks per split
@@ -265,18 +279,19 @@ using namespace kdpc::tc;
 KDPC_API long long kdpc_linear_dw_ws_bytes(long long m, int n, int k) {
     if (m <= 0 || n <= 0 || k <= 0) return 0;
     DwArgs a{};
-    dw_plan(m, n, k, a);
+    dw_plan(m, n, k, true, a);                               // (sized for the variant with the bias column)
     return (long long)a.splits * a.n_tiles * DW_TN * a.k_tiles * DW_KT * (long long)sizeof(float);
 }
 
-/* dW[n,k] = sum_m dY[m,n] X[m,k]  (weight gradient of y = x W^T).  dy [M,ldy], x [M,ldx], dw [N,lddw]; ws: kdpc_linear_dw_ws_bytes. */
+/* dW[n,k] = sum_m dY[m,n] X[m,k]  (weight gradient of y = x W^T) and, when db != NULL, db[n] = sum_m dY[m,n] from the same
+ * launch.  dy [M,ldy], x [M,ldx], dw [N,lddw]; ws: kdpc_linear_dw_ws_bytes. */
 KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy, const float *x, int ldx, void *ws,
-                            float *dw, int lddw, kdpc_stream_t stream) {
+                            float *dw, int lddw, float *db, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(dy && x && ws && dw && m > 0 && n > 0 && k > 0 && ldy >= n && ldx >= k && lddw >= k);
     if ((reinterpret_cast<uintptr_t>(ws) % 16) != 0) return KDPC_EINVAL;
     DwArgs a{};
     a.dy = dy; a.x = x; a.m = m; a.n = n; a.k = k; a.ldy = ldy; a.ldx = ldx;
-    dw_plan(m, n, k, a);
+    dw_plan(m, n, k, db != nullptr, a);
     a.partial = reinterpret_cast<float *>(ws);
     const size_t smem = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)(DW_KT / 64) * DW_LBO) + 1024;
     KDPC_ENSURE_SMEM(dw_tc_kernel, (int)smem);
@@ -285,7 +300,7 @@ KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy,
     dw_tc_kernel<<<grid, DW_THREADS, smem, st>>>(a);
     const int ldp = a.k_tiles * DW_KT;
     const long long split_stride = (long long)a.n_tiles * DW_TN * ldp;
-    const long long total = (long long)n * ((k + 3) / 4);
-    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.splits, split_stride, ldp, a.partial, dw, lddw);
+    const long long total = (long long)n * ((a.k_eff + 3) / 4);
+    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
     KDPC_RETURN_LAST();
 }

@@ -12,24 +12,40 @@ namespace kdpc {
 
 constexpr int CSR_THREADS = 1024;
 
-// one CTA per batch element; counts / cursors live in shared memory.
+// CTA (part, b) inverts the candidates i in [i_lo, i_hi) of cloud b: it scans the WHOLE index list of the cloud (1 MB at
+// most, L2-resident) but counts / places only the entries that select its candidates, plus one scalar - how many
+// entries select a smaller candidate - which is its segments' base offset.  No communication between the parts, so a
+// cloud is spread over `parts` SMs; the per-candidate segments are then sorted ascending (deterministic order) with
+// one thread per segment.  (One CTA per cloud spent ~65 of its ~127 us insertion-sorting 8 segments per thread in global
+// memory while 130 SMs idled: 26 builds per KD step.)
 __global__ void __launch_bounds__(CSR_THREADS)
-build_csr_kernel(int n, int m, const int *__restrict__ idx, int *__restrict__ offsets, int *__restrict__ perm) {
-    extern __shared__ int cnt[];                          // [n]
+build_csr_kernel(int n, int m, int per_part, const int *__restrict__ idx, int *__restrict__ offsets, int *__restrict__ perm) {
+    extern __shared__ int cnt[];                          // [per_part]
     __shared__ int warp_sums[32];
+    __shared__ int below_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    idx += (size_t)blockIdx.x * m;
-    offsets += (size_t)blockIdx.x * (n + 1);
-    perm += (size_t)blockIdx.x * m;
+    const int i_lo = blockIdx.x * per_part, i_hi = min(n, i_lo + per_part), span = i_hi - i_lo;
+    idx += (size_t)blockIdx.y * m;
+    offsets += (size_t)blockIdx.y * (n + 1);
+    perm += (size_t)blockIdx.y * m;
 
-    for (int i = tid; i < n; i += CSR_THREADS) cnt[i] = 0;
+    for (int i = tid; i < span; i += CSR_THREADS) cnt[i] = 0;
+    if (tid == 0) below_s = 0;
     __syncthreads();
-    for (int j = tid; j < m; j += CSR_THREADS) atomicAdd(&cnt[idx[j]], 1);   // integer: order-free
+    int below = 0;
+    for (int j = tid; j < m; j += CSR_THREADS) {
+        const int v = idx[j];
+        if (v < i_lo) ++below;
+        else if (v < i_hi) atomicAdd(&cnt[v - i_lo], 1);  // integer: order-free
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0 && below) atomicAdd(&below_s, below);
     __syncthreads();
 
     // exclusive scan: contiguous chunk per thread, then warp + block scan of the chunk sums
-    const int chunk = (n + CSR_THREADS - 1) / CSR_THREADS;
-    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    const int chunk = (span + CSR_THREADS - 1) / CSR_THREADS;
+    const int lo = min(span, tid * chunk), hi = min(span, lo + chunk);
     int sum = 0;
     for (int i = lo; i < hi; ++i) sum += cnt[i];
     int incl = sum;
@@ -50,22 +66,25 @@ build_csr_kernel(int n, int m, const int *__restrict__ idx, int *__restrict__ of
         warp_sums[lane] = wi - w;                         // exclusive prefix of warp totals
     }
     __syncthreads();
-    int run = warp_sums[warp] + incl - sum;
+    int run = below_s + warp_sums[warp] + incl - sum;
     for (int i = lo; i < hi; ++i) {
         const int c = cnt[i];
-        offsets[i] = run;
+        offsets[i_lo + i] = run;
         cnt[i] = run;                                     // becomes the fill cursor
         run += c;
     }
-    if (tid == CSR_THREADS - 1) offsets[n] = m;
+    if (i_hi == n && tid == CSR_THREADS - 1) offsets[n] = m;
     __syncthreads();
 
-    for (int j = tid; j < m; j += CSR_THREADS) perm[atomicAdd(&cnt[idx[j]], 1)] = j;
+    for (int j = tid; j < m; j += CSR_THREADS) {
+        const int v = idx[j];
+        if (v >= i_lo && v < i_hi) perm[atomicAdd(&cnt[v - i_lo], 1)] = j;
+    }
     __syncthreads();
     // cursors now hold segment ends; sort each (short) segment ascending => deterministic order
-    for (int i = tid; i < n; i += CSR_THREADS) {
+    for (int i = tid; i < span; i += CSR_THREADS) {
         const int e = cnt[i];
-        const int s0 = (i == 0) ? 0 : cnt[i - 1];
+        const int s0 = offsets[i_lo + i];
         for (int a = s0 + 1; a < e; ++a) {
             const int v = perm[a];
             int p = a - 1;
@@ -138,10 +157,18 @@ scatter_cm_csr_kernel(int c, int n, int m, int gdiv, const float *__restrict__ g
 }
 
 static int build_csr(int b, int n, int m, const int *idx, int *offsets, int *perm, cudaStream_t st) {
-    const size_t smem = (size_t)n * sizeof(int);
+    if (b > 65535) return KDPC_EUNSUPPORTED;
+    // ~2 CTAs per SM over all clouds, at least 64 candidates per part (and one segment per thread when possible)
+    int parts = (2 * num_sms() + b - 1) / b;
+    if (parts > (n + 63) / 64) parts = (n + 63) / 64;
+    if (parts < 1) parts = 1;
+    const int per_part = (n + parts - 1) / parts;
+    parts = (n + per_part - 1) / per_part;
+    const size_t smem = (size_t)per_part * sizeof(int);
     if (smem > 200 * 1024) return KDPC_EUNSUPPORTED;
     KDPC_ENSURE_SMEM(build_csr_kernel, 200 * 1024);
-    build_csr_kernel<<<b, CSR_THREADS, smem, st>>>(n, m, idx, offsets, perm);
+    dim3 grid(parts, b);
+    build_csr_kernel<<<grid, CSR_THREADS, smem, st>>>(n, m, per_part, idx, offsets, perm);
     return (int)cudaGetLastError();
 }
 

@@ -73,6 +73,14 @@ class _SamplePyramid:
         return idx, xyz
 
 
+# The 2B-cloud batch and its sampling pyramid depend on the input coordinates only.  Teacher and student of a KD step
+# (training.kd_step) see the SAME clouds, so the second model reuses the first one's tensors - and with them every
+# coordinate-only kNN / spatial sort / CSR downstream, whose caches are keyed by tensor identity.  (The reference runs
+# FPS and all 45 kNNs in both models.)  Dropped with the other per-batch caches by functional.clear_caches().
+_GEOMETRY_CACHE = KF._LRU(4)
+KF.register_batch_cache(_GEOMETRY_CACHE)
+
+
 class PointConvBidirection(nn.Module):
     def __init__(self, weightnet: int = 16):
         super().__init__()
@@ -123,10 +131,18 @@ class PointConvBidirection(nn.Module):
         both = lambda a, b: torch.cat([a, b], dim=0)
 
         # ---- encoder: clouds 1 and 2 as one batch of 2B (weights are shared, no BN) --------------
-        pc_l0 = both(xyz1, xyz2).contiguous()
-        # The sampling pyramid depends on coordinates only and is a chain of latency-bound kernels on <= 64 SMs:
-        # it runs on a side stream while this stream does the level-0 convolutions and the level-0 self-kNN.
-        pyramid = self._sample_pyramid(pc_l0)
+        npts = (self.level1.npoint, self.level2.npoint, self.level3.npoint, self.level4.npoint)
+        gkey = (KF._tkey(xyz1), KF._tkey(xyz2), npts)
+        hit = _GEOMETRY_CACHE.get(gkey) if (KF._CACHE_ENABLED and not xyz1.requires_grad and not xyz2.requires_grad) else None
+        if hit is not None:
+            pc_l0, pyramid = hit[0], hit[1]
+        else:
+            pc_l0 = both(xyz1, xyz2).contiguous()
+            # The sampling pyramid depends on coordinates only and is a chain of latency-bound kernels on <= 64 SMs
+            # (optionally on a side stream while this stream does the level-0 convolutions and the level-0 self-kNN).
+            pyramid = self._sample_pyramid(pc_l0)
+            if KF._CACHE_ENABLED and not pyramid.overlapped:
+                _GEOMETRY_CACHE.put(gkey, (pc_l0, pyramid, xyz1, xyz2))
         f_l0 = self.level0_1.forward_pm(self.level0.forward_pm(both(color1, color2)))
         f_l0_1 = self.level0_2.forward_pm(f_l0)
         if pyramid.overlapped:

@@ -88,12 +88,21 @@ _CSR_CACHE = _LRU(48)
 _CACHE_ENABLED = True
 
 
+_EXTRA_CACHES = []          # per-batch caches owned by other modules (flownet's sampling pyramid): cleared with the rest
+
+
+def register_batch_cache(cache) -> None:
+    _EXTRA_CACHES.append(cache)
+
+
 def clear_caches(weights: bool = False) -> None:
     """Drop cached kNN results and inverse indices (call between independent batches);
     ``weights=True`` also drops the packed-weight / folded-affine caches."""
     _KNN_CACHE.clear()
     _CSR_CACHE.clear()
     _SORT_CACHE.clear()
+    for c in _EXTRA_CACHES:
+        c.clear()
     if weights:
         _PACK_CACHE.clear()
         _AFFINE_CACHE.clear()
@@ -484,14 +493,56 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = fused_linear(gy, w2d.detach().t().contiguous(), None, cache_weight=False)   # a one-shot tensor: never cached
         g2 = gy.reshape(-1, gy.shape[-1])
-        if ctx.needs_input_grad[1]:
-            if USE_TC_DW:
-                gw = K.linear_dw(g2, x.detach().reshape(-1, x.shape[-1]).contiguous())       # tcgen05, MN-major operands
-            else:
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] and USE_TC_DW:
+            # tcgen05, MN-major operands; the bias gradient comes out of the same launch as an extra all-ones column of
+            # X - unless that column would open a new 256-wide output tile (K % 256 == 0): then db is a torch reduction
+            fuse_b = want_b and x.shape[-1] % 256 != 0
+            gw, gb = K.linear_dw(g2, x.detach().reshape(-1, x.shape[-1]).contiguous(), fuse_b)
+            gb = gb if fuse_b else (g2.sum(0) if want_b else None)
+        else:
+            if ctx.needs_input_grad[1]:
                 gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            if want_b:
+                gb = g2.sum(0)
         return gx, gw, gb
+
+
+class _LinearSmall(torch.autograd.Function):
+    """y = x W^T + b for layers with a TINY channel count on one side (3 -> 32 positional encodings over B*N*K rows,
+    64 -> 3 flow heads): forward and dX on the CUDA-core kernel (kdpc_linear_simt), dW / db on the tcgen05 weight-gradient
+    kernel (zero-padded to its 128 x 16 minimum tile: the reduction over millions of rows is what costs).  torch's
+    addmm / mm for these shapes land on SIMT sgemm kernels at ~600 us per call."""
+
+    @staticmethod
+    def forward(ctx, x, w2d, bias):
+        ctx.save_for_backward(x, w2d)
+        ctx.has_bias = bias is not None
+        return K.linear_simt(x.detach().contiguous(), w2d.detach().contiguous(), None, None if bias is None else bias.detach(), 1.0, 1.0, 0.0, None)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w2d = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = K.linear_simt(gy, w2d.detach().t().contiguous(), None, None, 1.0, 1.0, 0.0, None)
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or want_b:
+            gw, gb = K.linear_dw(gy.reshape(-1, gy.shape[-1]), x.detach().reshape(-1, x.shape[-1]).contiguous(), want_b)
+            gb = gb if want_b else None
+            gw = gw if ctx.needs_input_grad[1] else None
+        return gx, gw, gb
+
+
+def linear_small_autograd_available(x: torch.Tensor, w2d: torch.Tensor) -> bool:
+    n, k = w2d.shape
+    return (USE_TC_TRAINING and USE_TC_DW and x.is_cuda and x.dtype == torch.float32 and min(n, k) < 16 and max(n, k) <= 256
+            and x.numel() // max(k, 1) >= 4096)
+
+
+def linear_small_autograd(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    return _LinearSmall.apply(x, w2d, bias)
 
 
 def linear_tc_autograd_available(x: torch.Tensor, w2d: torch.Tensor) -> bool:
@@ -585,6 +636,38 @@ def fused_costvol(xyz1, xyz2, p1, p2, idx, pos, slope_pre: float, conv, slope_po
                            pos.weight.detach().reshape(d, 3).contiguous(), pos.bias.detach(), slope_pre,
                            _packed_weight(w2d), w2d.shape[0], None if conv.bias is None else conv.bias.detach(),
                            slope_post)
+
+
+# ------------------------------------------------------------------- WeightNet (training path)
+class _WeightNetFn(torch.autograd.Function):
+    """relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3) on the first 3 columns of ``rel`` (pointconv_util.py:204-215, bn=False):
+    forward = the fused inference kernel, backward = ONE kernel that recomputes the forward per row and reduces the six
+    parameter gradients deterministically (csrc/weightnet_grad.cu).  Only ``rel`` is saved."""
+
+    @staticmethod
+    def forward(ctx, rel, w1, b1, w2, b2, w3, b3):
+        ctx.save_for_backward(rel, w1, b1, w2, b2, w3, b3)
+        return K.weightnet(rel, w1, b1, w2, b2, w3, b3)
+
+    @staticmethod
+    def backward(ctx, g):
+        rel, w1, b1, w2, b2, w3, b3 = ctx.saved_tensors
+        want_x = ctx.needs_input_grad[0]
+        gw1, gb1, gw2, gb2, gw3, gb3, gx3 = K.weightnet_grad(rel, g.contiguous(), w1, b1, w2, b2, w3, b3, want_x)
+        g_rel = None
+        if want_x:
+            g_rel = torch.zeros_like(rel)
+            g_rel[..., :3] = gx3
+        return g_rel, gw1, gb1, gw2, gb2, gw3, gb3
+
+
+def weightnet_autograd(rel: torch.Tensor, convs) -> torch.Tensor:
+    """Differentiable WeightNet(3 -> 8 -> 8 -> W in {8, 16}) on a point-major [..., C>=3] tensor."""
+    return _WeightNetFn.apply(rel.contiguous(), convs[0].weight.reshape(8, 3), convs[0].bias, convs[1].weight.reshape(8, 8),
+                              convs[1].bias, convs[2].weight.reshape(-1, 8), convs[2].bias)
+
+
+USE_FUSED_WEIGHTNET_GRAD = os.environ.get("KDPC_WN_GRAD", "1") != "0"
 
 
 # ------------------------------------------------------------------- PointConv pieces

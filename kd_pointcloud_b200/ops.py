@@ -408,6 +408,34 @@ def _weightnet(x: torch.Tensor, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
     return out
 
 
+def _weightnet_grad(x: torch.Tensor, g_out: torch.Tensor, w1, b1, w2, b2, w3, b3, want_input: bool):
+    """Backward of kdpc::weightnet: x [..., C>=3] (first 3 columns = localized xyz), g_out [..., W] ->
+    (gw1 [8,3], gb1 [8], gw2 [8,8], gb2 [8], gw3 [W,8], gb3 [W], g_x3 [..., 3] or empty)."""
+    _req(x, torch.float32, None, "localized_xyz")
+    _req(g_out, torch.float32, None, "grad_out")
+    wout = g_out.shape[-1]
+    rows = g_out.numel() // max(wout, 1)
+    if x.numel() // x.shape[-1] != rows:
+        raise ValueError("kdpc: weightnet_grad row counts differ")
+    ps = [t.detach().contiguous().float() for t in (w1, b1, w2, b2, w3, b3)]
+    dev = x.device
+    with _guard(x):
+        outs = [torch.empty_like(t) for t in ps]
+        gx = torch.empty(tuple(x.shape[:-1]) + (3,), dtype=torch.float32, device=dev) if want_input else torch.empty(0, device=dev)
+        if rows == 0:
+            return tuple(o.zero_() for o in outs) + (gx,)
+        ws = torch.empty((_lib.lib().kdpc_weightnet_grad_ws_bytes(rows),), dtype=torch.uint8, device=dev)
+        _call("kdpc_weightnet_grad", rows, _p(x), x.shape[-1], wout, _p(g_out), *[_p(t) for t in ps], _p(ws),
+              *[_p(o) for o in outs], _p(gx) if want_input else None, _stream())
+    return tuple(outs) + (gx,)
+
+
+_register("weightnet_grad(Tensor x, Tensor g_out, Tensor w1, Tensor b1, Tensor w2, Tensor b2, Tensor w3, Tensor b3, bool want_input)"
+          " -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)", _weightnet_grad,
+          lambda x, g, w1, b1, w2, b2, w3, b3, wi: (torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2),
+                                                    torch.empty_like(w3), torch.empty_like(b3), x.new_empty(tuple(x.shape[:-1]) + (3,)) if wi else x.new_empty(0)))
+
+
 def _pointconv_agg(grouped: torch.Tensor, wn: torch.Tensor) -> torch.Tensor:
     _req(grouped, torch.float32, 4, "grouped")
     _req(wn, torch.float32, 4, "weights")
@@ -562,8 +590,9 @@ def linear_tc_into(x: torch.Tensor, wpacked: torch.Tensor, n: int, out: torch.Te
                   float(hi), None, _p(ws), out.data_ptr() + 4 * col0, ntot, _stream())
 
 
-def _linear_dw(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW [N,K] = dY^T X for dy [..., N], x [..., K] (same leading shape): the weight gradient of y = x W^T, on tcgen05."""
+def _linear_dw(dy: torch.Tensor, x: torch.Tensor, want_bias: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dW [N,K], db [N]) = (dY^T X, column sums of dY) for dy [..., N], x [..., K] (same leading shape): the weight and
+    bias gradients of y = x W^T + b in ONE tcgen05 launch (db rides along as an all-ones column of X)."""
     _req(dy, torch.float32, None, "grad_out")
     _req(x, torch.float32, None, "x")
     n, k = dy.shape[-1], x.shape[-1]
@@ -572,14 +601,16 @@ def _linear_dw(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         raise ValueError("kdpc: linear_dw row counts differ")
     with _guard(x):
         dw = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        db = torch.empty((n if want_bias else 0,), dtype=torch.float32, device=x.device)
         if m == 0:
-            return dw.zero_()
+            return dw.zero_(), db.zero_()
         ws = torch.empty((_lib.lib().kdpc_linear_dw_ws_bytes(m, n, k),), dtype=torch.uint8, device=x.device)
-        _call("kdpc_linear_dw", m, n, k, _p(dy), n, _p(x), k, _p(ws), _p(dw), k, _stream())
-    return dw
+        _call("kdpc_linear_dw", m, n, k, _p(dy), n, _p(x), k, _p(ws), _p(dw), k, _p(db) if want_bias else None, _stream())
+    return dw, db
 
 
-_register("linear_dw(Tensor dy, Tensor x) -> Tensor", _linear_dw, lambda dy, x: dy.new_empty((dy.shape[-1], x.shape[-1])))
+_register("linear_dw(Tensor dy, Tensor x, bool want_bias) -> (Tensor, Tensor)", _linear_dw,
+          lambda dy, x, wb: (dy.new_empty((dy.shape[-1], x.shape[-1])), dy.new_empty((dy.shape[-1] if wb else 0,))))
 
 
 def _linear_simt(x, w, scale, shift, slope: float, lo: float, hi: float, residual) -> torch.Tensor:

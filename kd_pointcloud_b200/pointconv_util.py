@@ -56,6 +56,8 @@ def _linear_pm(conv: nn.Module, x: torch.Tensor, norm: Optional[nn.Module] = Non
     w2d = w.reshape(w.shape[0], -1)
     if KF.linear_tc_autograd_available(x, w2d):
         y = KF.linear_tc_autograd(x, w2d, conv.bias)        # tcgen05 forward + input gradient (training path)
+    elif KF.linear_small_autograd_available(x, w2d):
+        y = KF.linear_small_autograd(x, w2d, conv.bias)     # 3 -> D / D -> 3 layers: SIMT forward + dX, tcgen05 dW
     else:
         y = F.linear(x, w2d, conv.bias)
     if bn is not None:
@@ -186,12 +188,18 @@ class WeightNet(nn.Module):
                 and c[1].out_channels == 8 and c[2].out_channels in (4, 8, 16, 32, 48)
                 and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))))
 
-    def forward_pm(self, rel: torch.Tensor) -> torch.Tensor:
-        """rel [..., W>=3] whose first 3 channels are the localized xyz -> [..., out_channel]."""
+    def forward_pm(self, rel: torch.Tensor, coords_need_grad: bool = True) -> torch.Tensor:
+        """rel [..., W>=3] whose first 3 channels are the localized xyz -> [..., out_channel].
+        ``coords_need_grad=False`` (the coordinates are constants, as in every PointConv of the models): the training
+        path does not route a gradient back into ``rel`` through the WeightNet."""
         if self._fusable(rel):
             c = self.mlp_convs
             return K.weightnet(rel.contiguous(), c[0].weight.reshape(8, 3), c[0].bias, c[1].weight.reshape(8, 8),
                                c[1].bias, c[2].weight.reshape(-1, 8), c[2].bias)
+        c = self.mlp_convs
+        if (KF.USE_FUSED_WEIGHTNET_GRAD and not self.bn and rel.is_cuda and len(c) == 3 and c[0].in_channels == 3 and c[0].out_channels == 8
+                and c[1].out_channels == 8 and c[2].out_channels in (8, 16) and all(_is_pointwise(m) and m.bias is not None for m in c)):
+            return KF.weightnet_autograd(rel if coords_need_grad else rel.detach(), c)   # training: fused forward + one-kernel backward
         w = rel[..., :self.mlp_convs[0].in_channels]
         for i, conv in enumerate(self.mlp_convs):
             w = _linear_pm(conv, w)
@@ -223,7 +231,7 @@ class _PointConvBase(nn.Module):
         if KF.fused_pointconv_available(self.weightnet, self.linear, bn, idx.shape[2], s_points):
             return KF.fused_pointconv(s_xyz, q_xyz, s_points, idx, self.weightnet, self.linear, bn, _slope(self.relu))
         grouped = KF.group_concat(s_xyz, q_xyz, s_points, idx)            # [B,S,K,3+D]
-        wn = self.weightnet.forward_pm(grouped)                           # [B,S,K,W]
+        wn = self.weightnet.forward_pm(grouped, s_xyz.requires_grad or q_xyz.requires_grad)   # [B,S,K,W]
         agg = KF.pointconv_agg(grouped, wn)                               # [B,S,(3+D)*W]  (c-major)
         # Linear (+ BatchNorm1d over B and S) + activation
         return _linear_pm(self.linear, agg, self.bn_linear if self.bn else None, self.relu)

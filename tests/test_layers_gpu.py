@@ -131,6 +131,39 @@ def test_layer_variants_against_reference_golden(golden):
         assert np.array_equal(nx.cpu().numpy(), g["pcw_new_xyz"])
 
 
+def test_weightnet_fused_backward_matches_autograd_of_the_op_chain():
+    """csrc/weightnet_grad.cu against torch autograd through the three 1x1 convolutions (the unfused training path),
+    parameter gradients and the gradient w.r.t. the localized coordinates; ragged row count; W = 16 and 8."""
+    for wout, shape in ((16, (2, 300, 9, 3 + 20)), (8, (1, 77, 16, 3)), (16, (3, 1000, 9, 3 + 4))):
+        wn, _ = load(P.WeightNet(3, wout), 21)
+        wn.train()
+        gen = torch.Generator().manual_seed(wout)
+        rel0 = torch.randn(*shape, generator=gen).to(DEV)
+        go = torch.randn(*shape[:3], wout, generator=gen).to(DEV)
+        res = {}
+        for fused in (True, False):
+            KF.USE_FUSED_WEIGHTNET_GRAD = fused
+            try:
+                wn.zero_grad(set_to_none=True)
+                rin = rel0.clone().requires_grad_(True)
+                out = wn.forward_pm(rin)
+                out.backward(go)
+                res[fused] = (out.detach().clone(), rin.grad.clone(), [p.grad.clone() for p in wn.mlp_convs.parameters()])
+            finally:
+                KF.USE_FUSED_WEIGHTNET_GRAD = True
+        assert rel(res[True][0], res[False][0]) < 1e-5
+        assert rel(res[True][1], res[False][1]) < 1e-4 and torch.count_nonzero(res[True][1][..., 3:]) == 0
+        for a, b in zip(res[True][2], res[False][2]):
+            assert a.shape == b.shape and rel(a, b) < 1e-4
+        # constants as coordinates: no gradient reaches ``rel`` through the WeightNet, parameters unchanged
+        wn.zero_grad(set_to_none=True)
+        r2 = rel0.clone().requires_grad_(True)
+        (wn.forward_pm(r2, coords_need_grad=False) * go).sum().backward()
+        assert r2.grad is None
+        for a, p in zip(res[True][2], wn.mlp_convs.parameters()):
+            assert torch.equal(a, p.grad)
+
+
 def test_multiscale_loss(golden):
     g = golden("multiscale_loss")
     loss = L.multiScaleLoss([T(g["p0"]), T(g["p1"]), T(g["p2"])], T(g["gt"]), [T(g["fps1"]), T(g["fps2"])])

@@ -237,11 +237,16 @@ def test_linear_dw_matches_fp64(m, n, k):
     g = torch.Generator().manual_seed(m + n + k)
     dy = torch.randn(m, n, generator=g).to(DEV)
     x = (torch.randn(m, k, generator=g) + 0.5).to(DEV)
-    dw = torch.ops.kdpc.linear_dw(dy, x)
+    dw, db = torch.ops.kdpc.linear_dw(dy, x, True)
     ref = dy.double().t() @ x.double()
     err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
     assert dw.shape == (n, k) and err < 2e-5, err
-    assert torch.equal(dw, torch.ops.kdpc.linear_dw(dy, x))                 # deterministic
+    ref_b = dy.double().sum(0)
+    assert db.shape == (n,) and ((db.double() - ref_b).abs().max() / ref_b.abs().max()).item() < 2e-5
+    dw2, db2 = torch.ops.kdpc.linear_dw(dy, x, True)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)                     # deterministic
+    dw3, db3 = torch.ops.kdpc.linear_dw(dy, x, False)                        # without the bias column: same weight gradient
+    assert db3.numel() == 0 and ((dw3.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
 
 
 def test_linear_tc_autograd_uses_the_tcgen05_weight_gradient():
@@ -264,4 +269,28 @@ def test_linear_tc_autograd_uses_the_tcgen05_weight_gradient():
     ref_w = go.double().reshape(-1, 48).t() @ x.detach().double().reshape(-1, 96)
     for tc_dw in (True, False):
         assert ((outs[tc_dw][1].double() - ref_w).abs().max() / ref_w.abs().max()).item() < 2e-5
-    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][2], outs[False][2])
+    assert torch.equal(outs[True][0], outs[False][0])
+    ref_b = go.double().reshape(-1, 48).sum(0)
+    for tc_dw in (True, False):
+        assert ((outs[tc_dw][2].double() - ref_b).abs().max() / ref_b.abs().max()).item() < 2e-5
+
+
+def test_small_channel_linear_autograd_matches_torch():
+    """3 -> 32 (cost-volume positional encoding) and 64 -> 3 (flow head) layers of the training path: SIMT forward / dX,
+    tcgen05 dW / db (functional._LinearSmall) against torch autograd."""
+    from kd_pointcloud_b200 import functional as KF
+    g = torch.Generator().manual_seed(5)
+    for k, n, lead in ((3, 32, (2, 300, 32)), (64, 3, (2, 4099)), (3, 64, (1, 5000, 16))):
+        x0 = torch.randn(*lead, k, generator=g).to(DEV)
+        w0 = (torch.randn(n, k, generator=g) * 0.3).to(DEV)
+        b0 = torch.randn(n, generator=g).to(DEV)
+        go = torch.randn(*lead, n, generator=g).to(DEV)
+        res = []
+        for small in (True, False):
+            x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+            assert KF.linear_small_autograd_available(x, w)
+            y = KF.linear_small_autograd(x, w, b) if small else torch.nn.functional.linear(x, w, b)
+            y.backward(go)
+            res.append((y.detach(), x.grad, w.grad, b.grad))
+        for a, r in zip(res[0], res[1]):
+            assert a.shape == r.shape and ((a - r).abs().max() / r.abs().max()).item() < 2e-5
