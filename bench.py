@@ -522,7 +522,9 @@ def run_train(args):
     use_graph = not args.no_graph
     from kd_pointcloud_b200.training import make_capturable_adam
     opt = make_capturable_adam(s.parameters(), lr=1e-3) if use_graph else torch.optim.Adam(s.parameters(), lr=1e-3)
-    reducer = FlatGradAllReduce(s.parameters(), module=s, local_batch=B) if world > 1 else None
+    # mode='sum': the KD hint term is a SUM over the batch (loss_functions.py:213-214), so ranks add their gradients and the
+    # flow terms' batch means are taken over the global batch (tests/test_multigpu_nccl.py: == single-GPU gradients)
+    reducer = FlatGradAllReduce(s.parameters(), module=s, local_batch=B, mode="sum") if world > 1 else None
     kind = "kitti" if world > 1 else "ft3d"
     pool = [make_pairs(B, NPOINTS, seed=4321 + 1000 * rank + i, kind=kind, device=dev) for i in range(2)]
 

@@ -34,14 +34,16 @@ def _fusable(pred_flows, gt_flow, fps_idxs, hints=()) -> bool:
 
 
 def multiScaleLoss(pred_flows: Sequence[torch.Tensor], gt_flow: torch.Tensor, fps_idxs: Sequence[torch.Tensor],
-                   alpha: Sequence[float] = ALPHA) -> torch.Tensor:
+                   alpha: Sequence[float] = ALPHA, global_batch: int = None) -> torch.Tensor:
     """pred_flows: [B,3,N_i] per scale (finest first); gt_flow [B,N,3]; fps_idxs int32 [B,N_{i+1}].
     CUDA fp32 inputs with a constant target: ONE fused kernel (forward + gradient, functional.kd_loss);
-    otherwise (a target that needs a gradient) the reference op chain on kdpc gathers."""
+    otherwise (a target that needs a gradient) the reference op chain on kdpc gathers.
+    ``global_batch`` (batch-sharded training): the mean over B (loss_functions.py:22) is taken over the GLOBAL batch, so
+    that the SUM of the ranks' losses / gradients is the single-process loss / gradient over the concatenated batch."""
+    B = gt_flow.shape[0]
     if _fusable(pred_flows, gt_flow, fps_idxs):
-        B = gt_flow.shape[0]
-        return KF.kd_loss(pred_flows, fps_idxs, [gt_flow], [1.0 / B], alpha)
-    return multiScaleLoss_composed(pred_flows, gt_flow, fps_idxs, alpha)
+        return KF.kd_loss(pred_flows, fps_idxs, [gt_flow], [1.0 / (global_batch or B)], alpha)
+    return multiScaleLoss_composed(pred_flows, gt_flow, fps_idxs, alpha) * (B / float(global_batch or B))
 
 
 def multiScaleLoss_composed(pred_flows: Sequence[torch.Tensor], gt_flow: torch.Tensor, fps_idxs: Sequence[torch.Tensor],
@@ -64,27 +66,28 @@ def epe3d(pred_flow0: torch.Tensor, gt_flow: torch.Tensor) -> torch.Tensor:
     return torch.norm(pred_flow0.permute(0, 2, 1) - gt_flow, dim=2).mean()
 
 
-def _kd_fused(outputs, fps_idxs, gt_flow, t0, w_teacher, w_gt, hints, alpha):
-    B = gt_flow.shape[0]
+def _kd_fused(outputs, fps_idxs, gt_flow, t0, w_teacher, w_gt, hints, alpha, global_batch=None):
+    B = global_batch or gt_flow.shape[0]
     return KF.kd_loss(outputs, fps_idxs, [t0, gt_flow], [w_teacher / B, w_gt / B], alpha, hints)
 
 
-def loss_fn_kd_2(outputs, fps_idxs, gt_flow, teacher_outputs, teacher_fps_idxs, gamma, alpha=ALPHA):
+def loss_fn_kd_2(outputs, fps_idxs, gt_flow, teacher_outputs, teacher_fps_idxs, gamma, alpha=ALPHA, global_batch=None):
     t0 = teacher_outputs[0].permute(0, 2, 1)
     if _fusable(outputs, gt_flow, fps_idxs) and not t0.requires_grad:
-        return _kd_fused(outputs, fps_idxs, gt_flow, t0, gamma, 1 - gamma, (), alpha)
-    return gamma * multiScaleLoss(outputs, t0, fps_idxs, alpha) + (1 - gamma) * multiScaleLoss(outputs, gt_flow, fps_idxs, alpha)
+        return _kd_fused(outputs, fps_idxs, gt_flow, t0, gamma, 1 - gamma, (), alpha, global_batch)
+    return (gamma * multiScaleLoss(outputs, t0, fps_idxs, alpha, global_batch)
+            + (1 - gamma) * multiScaleLoss(outputs, gt_flow, fps_idxs, alpha, global_batch))
 
 
 def biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, teacher_outputs, t_feat1s, t_feat2s,
-                        t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=0, alpha=ALPHA):
+                        t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=0, alpha=ALPHA, global_batch=None):
     t0 = teacher_outputs[0].permute(0, 2, 1)
     if (_fusable(outputs, gt_flow, fps_idxs1, [(feat1s[layer], t_feat1s[layer]), (feat2s[layer], t_feat2s[layer])])
             and not t0.requires_grad):
         hints = [(feat1s[layer], t_feat1s[layer], 0.5 * (1 - beta)), (feat2s[layer], t_feat2s[layer], 0.5 * (1 - beta))]
-        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha)
-    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
-    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
+        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha, global_batch)
+    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha, global_batch)
+    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha, global_batch)
     src = ((feat1s[layer] - t_feat1s[layer]) ** 2) / 2
     tgt = ((feat2s[layer] - t_feat2s[layer]) ** 2) / 2
     return beta * (gamma * loss1 + (1 - gamma) * loss2) + (1 - beta) * (0.5 * src.sum() + 0.5 * tgt.sum())
@@ -92,18 +95,21 @@ def biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, 
 
 def cross_biDirection_loss_ht(outputs, feat1s, feat2s, fps_idxs1, fps_idxs2, gt_flow, teacher_outputs, t_feat1s,
                               t_feat2s, t_fps_idxs1, t_fps_idxs2, gamma, beta, layer=(2, 3), alpha=ALPHA,
-                              hint_mode: str = "cat"):
+                              hint_mode: str = "cat", global_batch=None):
     """``hint_mode='cat'`` is the reference formula verbatim (student feature vs cat(teacher feat1,
     teacher feat2) on channels — needs a student with twice the teacher's channels);
     ``hint_mode='first'`` compares against the teacher's feat1 only (shape-valid for the shipped
-    student, same structure: MS-vs-teacher + MS-vs-GT + half squared hint error)."""
+    student, same structure: MS-vs-teacher + MS-vs-GT + half squared hint error).
+    NOTE the reference's hint term is a SUM over the batch while the flow terms are batch MEANS: under batch sharding
+    the ranks' gradients must therefore be SUMMED with the means taken over ``global_batch`` (sharding.FlatGradAllReduce
+    mode='sum') - averaging per-rank gradients would halve the hint term's share at 2 ranks."""
     t0 = teacher_outputs[0].permute(0, 2, 1)
     pairs = [(feat1s[e], torch.cat([t_feat1s[e], t_feat2s[e]], dim=1) if hint_mode == "cat" else t_feat1s[e]) for e in layer]
     if _fusable(outputs, gt_flow, fps_idxs1, pairs) and not t0.requires_grad:
         hints = [(a, b, 1 - beta) for a, b in pairs]
-        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha)
-    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha)
-    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha)
+        return _kd_fused(outputs, fps_idxs1, gt_flow, t0, beta * gamma, beta * (1 - gamma), hints, alpha, global_batch)
+    loss1 = multiScaleLoss(outputs, t0, fps_idxs1, alpha, global_batch)
+    loss2 = multiScaleLoss(outputs, gt_flow, fps_idxs1, alpha, global_batch)
     hint = torch.zeros(1, device=gt_flow.device, dtype=gt_flow.dtype)
     for each in layer:
         t = torch.cat([t_feat1s[each], t_feat2s[each]], dim=1) if hint_mode == "cat" else t_feat1s[each]

@@ -59,9 +59,17 @@ class FlatGradAllReduce:
     makes this weighting the concatenated-batch gradient."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 module: Optional[torch.nn.Module] = None, local_batch: Optional[int] = None):
+                 module: Optional[torch.nn.Module] = None, local_batch: Optional[int] = None, mode: str = "mean"):
+        """mode='mean': per-rank losses are batch means; the result is the global-batch mean gradient.
+        mode='sum' : per-rank losses are already scaled for the global batch (``self.global_batch`` is what their means
+                     must divide by; losses with per-sample SUM terms, e.g. the KD hint loss, need this): gradients are
+                     added, nothing is divided."""
+        if mode not in ("mean", "sum"):
+            raise ValueError(mode)
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
+        self.mode = mode
+        self.global_batch: Optional[int] = local_batch
         self.flat: Optional[torch.Tensor] = None
         self.active: Optional[List[int]] = None
         self.weight = 1.0                                  # this rank's share of the global batch times world
@@ -74,7 +82,9 @@ class FlatGradAllReduce:
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
             if total.item() <= 0:
                 raise RuntimeError("FlatGradAllReduce: the global batch is empty")
-            self.weight = float(local_batch) * dist.get_world_size(group) / total.item()
+            self.global_batch = int(round(total.item()))
+            if mode == "mean":
+                self.weight = float(local_batch) * dist.get_world_size(group) / total.item()
 
     def _plan(self):
         self.active = [i for i, p in enumerate(self.params) if p.grad is not None]
@@ -107,7 +117,8 @@ class FlatGradAllReduce:
         if self.weight != 1.0:
             self.flat.mul_(self.weight)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(world)
+        if self.mode == "mean":
+            self.flat.div_(world)
         torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g for g in grads],
                              [c.view_as(g) if not g.is_contiguous() else c for c, g in
                               zip(self.flat.split([g.numel() for g in grads]), grads)])

@@ -19,7 +19,7 @@ from . import functional as KF
 from . import losses
 
 
-def _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode) -> torch.Tensor:
+def _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode, global_batch=None) -> torch.Tensor:
     KF.clear_caches()
     p1, p2, c1, c2, flow = batch["pos1"], batch["pos2"], batch["color1"], batch["color2"], batch["flow"]
     teacher.eval()
@@ -28,17 +28,23 @@ def _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, h
     student.train()
     s_out = student(p1, p2, c1, c2)
     loss = losses.cross_biDirection_loss_ht(s_out[0], s_out[5], s_out[6], s_out[1], s_out[2], flow, t_out[0], t_out[5],
-                                            t_out[6], t_out[1], t_out[2], gamma, beta, layer=layers, hint_mode=hint_mode)
+                                            t_out[6], t_out[1], t_out[2], gamma, beta, layer=layers, hint_mode=hint_mode,
+                                            global_batch=global_batch)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
     KF.clear_caches()
     return loss.detach()
 
 
+def _global_batch(reducer) -> Optional[int]:
+    """Batch-sharded training with a 'sum' reducer: batch means are taken over the global batch (see losses.py)."""
+    return getattr(reducer, "global_batch", None) if getattr(reducer, "mode", None) == "sum" else None
+
+
 def kd_step(teacher: torch.nn.Module, student: torch.nn.Module, batch: Dict[str, torch.Tensor],
             optimizer: torch.optim.Optimizer, reducer: Optional[Callable[[], None]] = None,
             gamma: float = 0.3, beta: float = 0.8, layers=(2, 3), hint_mode: str = "first") -> torch.Tensor:
-    loss = _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode)
+    loss = _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode, _global_batch(reducer))
     if reducer is not None:
         reducer()
     optimizer.step()
@@ -141,7 +147,8 @@ class GraphedKDStep:
                 self.graph = g
             else:
                 with torch.cuda.graph(g):
-                    self.loss = _forward_backward(self.teacher, self.student, self.static, self.optimizer, **self.kw)
+                    self.loss = _forward_backward(self.teacher, self.student, self.static, self.optimizer,
+                                                  global_batch=_global_batch(self.reducer), **self.kw)
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, pool=g.pool()):
                     self.optimizer.step()

@@ -1,7 +1,8 @@
 """NCCL, 2 ranks on 2 GPUs (SURVEY 8(e), configs[4]): batch-sharded KD training.
 
   * the all-reduced gradients of the sharded step equal the single-GPU gradients over the concatenated batch
-    (BatchNorm in eval mode, so that batch statistics do not depend on the shard);
+    (BatchNorm in eval mode, so that batch statistics do not depend on the shard).  The reference's KD loss mixes batch
+    MEANS (flow terms) with a batch SUM (hint term), so ranks ADD gradients and the means divide by the global batch;
   * the two-graph step (forward+backward graph, EAGER NCCL all-reduce, optimizer graph) equals the eager sharded step
     loss for loss and weight for weight, and keeps the replicas identical.
 
@@ -46,7 +47,7 @@ def _models(dev):
     return teacher.to(dev), student.to(dev)
 
 
-def _loss(teacher, student, batch):
+def _loss(teacher, student, batch, global_batch=None):
     from kd_pointcloud_b200 import functional as KF
     from kd_pointcloud_b200 import losses
     KF.clear_caches()
@@ -54,7 +55,7 @@ def _loss(teacher, student, batch):
         t = teacher(batch["pos1"], batch["pos2"], batch["color1"], batch["color2"])
     s = student(batch["pos1"], batch["pos2"], batch["color1"], batch["color2"])
     return losses.cross_biDirection_loss_ht(s[0], s[5], s[6], s[1], s[2], batch["flow"], t[0], t[5], t[6], t[1], t[2], 0.3, 0.8,
-                                            layer=(2, 3), hint_mode="first")
+                                            layer=(2, 3), hint_mode="first", global_batch=global_batch)
 
 
 def _worker_grad_parity(rank, world, port, q):
@@ -66,12 +67,20 @@ def _worker_grad_parity(rank, world, port, q):
     teacher.eval(), student.eval()                           # BatchNorm on running statistics: shard-independent
     full = make_pairs(4, 2048, seed=31, device=dev)
     mine = shard_batch(full, rank, world)
-    red = FlatGradAllReduce(student.parameters(), module=student, local_batch=mine["pos1"].shape[0])
-    _loss(teacher, student, mine).backward()
+    # the KD hint term is a SUM over the batch, the flow terms are batch MEANS (loss_functions.py:201-219): ranks add
+    # their gradients, the means divide by the global batch
+    red = FlatGradAllReduce(student.parameters(), module=student, local_batch=mine["pos1"].shape[0], mode="sum")
+    assert red.global_batch == 4
+    local = _loss(teacher, student, mine, red.global_batch)
+    local.backward()
     red()
+    total = local.detach().clone()
+    dist.all_reduce(total)
     sharded = {k: p.grad.clone() for k, p in student.named_parameters() if p.grad is not None}
     student.zero_grad(set_to_none=True)
-    _loss(teacher, student, full).backward()                 # every rank also computes the single-GPU reference itself
+    ref_loss = _loss(teacher, student, full)                 # every rank also computes the single-GPU reference itself
+    ref_loss.backward()
+    assert abs(total.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item()), (total.item(), ref_loss.item())
     worst, bad = 0.0, []
     for k, p in student.named_parameters():
         if p.grad is None:
@@ -99,7 +108,7 @@ def _worker_two_graph_step(rank, world, port, q):
     for graphed in (False, True):
         student.load_state_dict(init)
         opt = training.make_capturable_adam(student.parameters(), lr=1e-4)
-        red = FlatGradAllReduce(student.parameters(), module=student, local_batch=1)
+        red = FlatGradAllReduce(student.parameters(), module=student, local_batch=1, mode="sum")
         if graphed:
             stepper = training.GraphedKDStep(teacher, student, batches[0], opt, red)
             assert stepper.graph is not None and stepper.graph_opt is not None

@@ -41,7 +41,8 @@ def _worker(rank, world, port, q):
         loss = ((m(mine["x"]) - mine["y"]) ** 2).sum() / 8 * world      # per-rank mean-of-global * world -> average = global
         loss.backward()
         red()
-    q.put((rank, [None if p.grad is None else p.grad.clone() for p in m.parameters()], red.numel))
+    # numpy: pickled by value (tensors travel as shared-memory fds, which die with this process)
+    q.put((rank, [None if p.grad is None else p.grad.numpy().copy() for p in m.parameters()], red.numel))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,7 +71,7 @@ def test_flat_grad_allreduce_matches_single_process():
         for a, b in zip(grads, ref):
             assert (a is None) == (b is None)
             if a is not None:
-                assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), rank
+                assert torch.allclose(torch.from_numpy(a), b, rtol=1e-5, atol=1e-6), rank
 
 
 def _worker_uneven(rank, world, port, q):
@@ -132,3 +133,49 @@ def test_broadcast_parameters_is_a_noop_without_a_process_group():
     before = [p.clone() for p in m.parameters()]
     broadcast_parameters(m)
     assert all(torch.equal(a, b) for a, b in zip(before, m.parameters()))
+
+
+def _worker_sum_mode(rank, world, port, q):
+    """A loss that mixes a batch MEAN with a batch SUM (the KD hint term, loss_functions.py:213-214): ranks scale their
+    means by the global batch and ADD gradients (mode='sum')."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    batch = {"x": torch.randn(8, 6, generator=g), "y": torch.randn(8, 3, generator=g)}
+    a, b = (0, 5) if rank == 0 else (5, 8)
+    m = _model()
+    red = FlatGradAllReduce(m.parameters(), module=m, local_batch=b - a, mode="sum")
+    out = m(batch["x"][a:b])
+    loss = ((out - batch["y"][a:b]) ** 2).sum(dim=1).sum() / red.global_batch + 0.1 * (out ** 2).sum()
+    loss.backward()
+    red()
+    q.put((rank, red.global_batch, [None if p.grad is None else p.grad.numpy().copy() for p in m.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sum_mode_reproduces_a_loss_with_mean_and_sum_terms():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sum_mode, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    batch = {"x": torch.randn(8, 6, generator=g), "y": torch.randn(8, 3, generator=g)}
+    m = _model()
+    out = m(batch["x"])
+    (((out - batch["y"]) ** 2).sum(dim=1).mean() + 0.1 * (out ** 2).sum()).backward()
+    for rank, gb, grads in res:
+        assert gb == 8
+        for a, p in zip(grads, m.parameters()):
+            assert (a is None) == (p.grad is None)
+            if a is not None:
+                assert torch.allclose(torch.from_numpy(a), p.grad, rtol=1e-5, atol=1e-6), rank
