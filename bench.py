@@ -65,14 +65,14 @@ def ncu_capture_of_roofline_kernel():
         vals = {}
         with open(path) as f:
             for line in f:
-                m = re.match(r"(dram read|dram write|tensor pipe % \(subunit\)|tensor-pipe inst|duration)\s+([0-9.,]+)\s*(\S*)", line)
+                m = re.match(r"(dram read|dram write|tensor pipe cycles active %|duration)\s+([0-9.,]+)\s*(\S*)", line)
                 if m and m.group(1) not in vals:
                     v = float(m.group(2).replace(",", ""))
                     unit = m.group(3).lower()
                     mult = {"mbyte": 1e6, "gbyte": 1e9, "kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
                     vals[m.group(1)] = v * mult
         if "dram read" in vals and "dram write" in vals:
-            return {"traffic": vals["dram read"] + vals["dram write"], "tensor_pipe_pct": vals.get("tensor pipe % (subunit)"),
+            return {"traffic": vals["dram read"] + vals["dram write"], "tensor_pipe_pct": vals.get("tensor pipe cycles active %"),
                     "source": os.path.relpath(path, ROOT)}
     return {"traffic": None, "tensor_pipe_pct": None, "source": None}
 

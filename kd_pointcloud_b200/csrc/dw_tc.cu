@@ -139,11 +139,12 @@ dw_tc_kernel(const DwArgs a) {
                     }
                 }
             }
-            // X tile: 64 rows x (kgroups * 64) columns (k0 ..)
-            for (int i0 = tid; i0 < b_units; i0 += 4 * DW_PRODUCERS) {
-                float v[4][8];
+            // X tile: 64 rows x (kgroups * 64) columns (k0 ..).  Eight units (16 x 16-byte loads) per thread in flight:
+            // the whole 256-column tile is ONE round trip to memory (batches of four made a chunk three dependent trips)
+            for (int i0 = tid; i0 < b_units; i0 += 8 * DW_PRODUCERS) {
+                float v[8][8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const int i = i0 + j * DW_PRODUCERS;
                     const int r = i / b_upr, u = i - r * b_upr;
                     const long long row = row0 + r;
@@ -157,7 +158,7 @@ dw_tc_kernel(const DwArgs a) {
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const int i = i0 + j * DW_PRODUCERS;
                     if (i < b_units) {
                         const int r = i / b_upr, u = i - r * b_upr;

@@ -480,15 +480,25 @@ class _LinearTC(torch.autograd.Function):
     matmul runs on the CUDA cores: cutlass_80_simt_sgemm was 28 % of the KD training step.)"""
 
     @staticmethod
-    def forward(ctx, x, w2d, bias):
-        ctx.save_for_backward(x, w2d)
+    def forward(ctx, x, w2d, bias, slope=1.0):
+        # slope != 1: LeakyReLU / ReLU applied in the tcgen05 epilogue (no separate activation kernel, no pre-activation
+        # tensor); the backward masks the incoming gradient with the sign of the OUTPUT (same sign as the pre-activation
+        # for slope > 0; for ReLU the mask is y > 0 exactly like threshold_backward)
+        y = fused_linear(x.detach(), w2d.detach(), None if bias is None else bias.detach(), None, slope)
+        ctx.slope = float(slope)
+        if ctx.slope != 1.0:
+            ctx.save_for_backward(x, w2d, y)
+        else:
+            ctx.save_for_backward(x, w2d)
         ctx.has_bias = bias is not None
-        return fused_linear(x.detach(), w2d.detach(), None if bias is None else bias.detach())
+        return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w2d = ctx.saved_tensors
+        x, w2d = ctx.saved_tensors[0], ctx.saved_tensors[1]
         gy = gy.contiguous()
+        if ctx.slope != 1.0:
+            gy = torch.ops.aten.leaky_relu_backward(gy, ctx.saved_tensors[2], ctx.slope, True)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = fused_linear(gy, w2d.detach().t().contiguous(), None, cache_weight=False)   # a one-shot tensor: never cached
@@ -505,7 +515,7 @@ class _LinearTC(torch.autograd.Function):
                 gw = g2.t().mm(x.detach().reshape(-1, x.shape[-1]))
             if want_b:
                 gb = g2.sum(0)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 class _LinearSmall(torch.autograd.Function):
@@ -551,8 +561,8 @@ def linear_tc_autograd_available(x: torch.Tensor, w2d: torch.Tensor) -> bool:
             and x.numel() // max(k, 1) >= 128)
 
 
-def linear_tc_autograd(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    return _LinearTC.apply(x, w2d, bias)
+def linear_tc_autograd(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor], slope: float = 1.0) -> torch.Tensor:
+    return _LinearTC.apply(x, w2d, bias, slope)
 
 
 USE_TC_TRAINING = os.environ.get("KDPC_TC_TRAINING", "1") != "0"

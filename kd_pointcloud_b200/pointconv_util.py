@@ -55,7 +55,12 @@ def _linear_pm(conv: nn.Module, x: torch.Tensor, norm: Optional[nn.Module] = Non
         return KF.fused_linear(x, w, conv.bias, bn, slope, clamp, residual)
     w2d = w.reshape(w.shape[0], -1)
     if KF.linear_tc_autograd_available(x, w2d):
-        y = KF.linear_tc_autograd(x, w2d, conv.bias)        # tcgen05 forward + input gradient (training path)
+        if bn is None and act is not None and 0.0 <= slope < 1.0:
+            # tcgen05 forward with the activation in its epilogue + tcgen05 dX / dW (training path)
+            y = KF.linear_tc_autograd(x, w2d, conv.bias, slope)
+            act = None
+        else:
+            y = KF.linear_tc_autograd(x, w2d, conv.bias)
     elif KF.linear_small_autograd_available(x, w2d):
         y = KF.linear_small_autograd(x, w2d, conv.bias)     # 3 -> D / D -> 3 layers: SIMT forward + dX, tcgen05 dW
     else:
