@@ -108,65 +108,77 @@ dw_tc_kernel(const DwArgs a) {
         // ================= producers: fp32 rows -> bf16 hi/lo, MN-major SW128 tiles =================
         const bool vec_y = (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 && (n0 & 3) == 0;
         const bool vec_x = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
-        const int a_units = DW_MCHUNK * (DW_TN / 8);             // 1024: (row r, unit u) = (i / 16, i % 16)
         const int b_upr = kgroups * 8;                           // units per row of the X tile
-        const int b_units = DW_MCHUNK * b_upr;
         for (int c = 0; c < chunks; ++c) {
             const int s = c & 1;
             mbar_wait(&empty[s], ((c >> 1) & 1) ^ 1);
             unsigned char *st = smem + (size_t)s * stage_bytes;
             unsigned char *a_hi = st, *a_lo = st + DW_A_PART, *b_hi = st + 2 * DW_A_PART, *b_lo = b_hi + b_part;
             const long long row0 = m_begin + (long long)c * DW_MCHUNK;
+            // Units that lie entirely beyond the tile's valid columns (n >= N, k >= K_eff) are all-zero in EVERY chunk:
+            // they are written when a stage is filled for the first time (c < 2) and skipped afterwards (for a 32-wide
+            // layer three quarters of the dY tile are such padding).
+            const bool first_fill = c < 2;
+            const int a_live = min(DW_TN / 8, (a.n - n0 + 7) >> 3);   // live units per dY row
+            const int b_live = min(b_upr, (kw + 7) >> 3);              // live units per X row
             // dY tile: 64 rows x 128 columns (n0 ..)
-            for (int i0 = tid; i0 < a_units; i0 += 4 * DW_PRODUCERS) {
-                float v[4][8];
+            {
+                const int upr = first_fill ? DW_TN / 8 : a_live;
+                const int units = DW_MCHUNK * upr;
+                for (int i0 = tid; i0 < units; i0 += 4 * DW_PRODUCERS) {
+                    float v[4][8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + j * DW_PRODUCERS;
-                    const int r = i >> 4, u = i & 15;
-                    const long long row = row0 + r;
-                    dw_load_unit(a.dy + row * a.ldy + n0, i < a_units && row < m_end, u * 8, a.n - n0, vec_y, v[j]);
-                }
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * DW_PRODUCERS;
+                        const int r = i / upr, u = i - r * upr;
+                        const long long row = row0 + r;
+                        dw_load_unit(a.dy + row * a.ldy + n0, i < units && row < m_end, u * 8, a.n - n0, vec_y, v[j]);
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + j * DW_PRODUCERS;
-                    if (i < a_units) {
-                        uint4 hi, lo;
-                        split8(v[j], hi, lo);
-                        const uint32_t off = mn_offset(i & 15, i >> 4);
-                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * DW_PRODUCERS;
+                        if (i < units) {
+                            const int r = i / upr, u = i - r * upr;
+                            uint4 hi, lo;
+                            split8(v[j], hi, lo);
+                            const uint32_t off = mn_offset(u, r);
+                            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                        }
                     }
                 }
             }
-            // X tile: 64 rows x (kgroups * 64) columns (k0 ..).  Eight units (16 x 16-byte loads) per thread in flight:
-            // the whole 256-column tile is ONE round trip to memory (batches of four made a chunk three dependent trips)
-            for (int i0 = tid; i0 < b_units; i0 += 8 * DW_PRODUCERS) {
-                float v[8][8];
+            // X tile: 64 rows x (kgroups * 64) columns (k0 ..)
+            {
+                const int upr = first_fill ? b_upr : b_live;
+                const int units = DW_MCHUNK * upr;
+                for (int i0 = tid; i0 < units; i0 += 4 * DW_PRODUCERS) {
+                    float v[4][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = i0 + j * DW_PRODUCERS;
-                    const int r = i / b_upr, u = i - r * b_upr;
-                    const long long row = row0 + r;
-                    dw_load_unit(a.x + row * a.ldx + k0, i < b_units && row < m_end, u * 8, a.k - k0, vec_x && (k0 & 3) == 0, v[j]);
-                    // db = sum_m dY[m, :] rides along as column k of X == 1 (valid rows only)
-                    const int oc = a.k - k0 - u * 8;                  // position of the ones column inside this unit
-                    if (a.k_eff != a.k && oc >= 0 && oc < 8 && i < b_units && row < m_end) {
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * DW_PRODUCERS;
+                        const int r = i / upr, u = i - r * upr;
+                        const long long row = row0 + r;
+                        dw_load_unit(a.x + row * a.ldx + k0, i < units && row < m_end, u * 8, a.k - k0, vec_x && (k0 & 3) == 0, v[j]);
+                        // db = sum_m dY[m, :] rides along as column k of X == 1 (valid rows only)
+                        const int oc = a.k - k0 - u * 8;              // position of the ones column inside this unit
+                        if (a.k_eff != a.k && oc >= 0 && oc < 8 && i < units && row < m_end) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q == oc) v[j][q] = 1.f;
+                            for (int q = 0; q < 8; ++q)
+                                if (q == oc) v[j][q] = 1.f;
+                        }
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = i0 + j * DW_PRODUCERS;
-                    if (i < b_units) {
-                        const int r = i / b_upr, u = i - r * b_upr;
-                        uint4 hi, lo;
-                        split8(v[j], hi, lo);
-                        const uint32_t off = mn_offset(u, r);
-                        *reinterpret_cast<uint4 *>(b_hi + off) = hi;
-                        *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j * DW_PRODUCERS;
+                        if (i < units) {
+                            const int r = i / upr, u = i - r * upr;
+                            uint4 hi, lo;
+                            split8(v[j], hi, lo);
+                            const uint32_t off = mn_offset(u, r);
+                            *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                            *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+                        }
                     }
                 }
             }
