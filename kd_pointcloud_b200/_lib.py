@@ -37,8 +37,10 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every kernel for sm_100a with nvcc (cross-compiles without a GPU): one object per
     source (in parallel, rebuilt only when stale) under csrc/build/, then one link."""
+    force = force or os.environ.get("KDPC_FORCE_BUILD", "0") == "1"      # rebuild every object from clean
     if os.environ.get("KDPC_LIB") or (not force and not needs_build()):
         return LIB_PATH
+    log = []
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = os.path.join(CSRC, "build")
@@ -51,6 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
             cmd = [nvcc] + COMPILE_FLAGS + ["-c", src, "-o", obj]
+            log.append(" ".join(cmd))
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True, cwd=CSRC)
@@ -59,9 +62,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
     cmd = [nvcc] + LINK_FLAGS + ["-o", LIB_PATH] + objs
+    log.append(" ".join(cmd))
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)
+    with open(os.path.join(objdir, "build.log"), "w") as f:   # the nvcc command lines of the last (re)build
+        f.write("\n".join(log) + "\n")
     return LIB_PATH
 
 

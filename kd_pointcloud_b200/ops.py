@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -41,9 +43,19 @@ def _req(t: torch.Tensor, dtype, ndim=None, name="tensor"):
 TRACE = None          # set to a list to record (name, int args, start event, end event) per C-ABI call (tools/trace_model.py)
 
 
+NVTX = os.environ.get("KDPC_NVTX", "0") == "1"     # one NVTX range per C-ABI call (visible in nsys / ncu --nvtx)
+
+
 def _call(name: str, *args):
     global LAUNCHES
     LAUNCHES += 1
+    if NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(getattr(_lib.lib(), name)(*args), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if TRACE is not None:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

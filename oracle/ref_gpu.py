@@ -141,3 +141,30 @@ def load(stack: str) -> Dict[str, types.ModuleType]:
             sys.modules.pop(k, None)
         sys.modules.update(saved)
         sys.path[:] = saved_path
+
+
+def load_reference_pointnet2_utils(backend: str) -> types.ModuleType:
+    """The reference's OWN pointnet2/pointnet2_utils.py (unmodified, from baseline/_ref) on top of a ``pointnet2_cuda``
+    module: backend="stock" -> the reference's kernels (oracle/_ref), backend="kdpc" -> compat/pointnet2_cuda.py, the
+    ctypes binding of libkdpc.so with the pybind wrapper names (INTEGRATION.md route B)."""
+    import importlib.util
+    if backend == "stock":
+        cuda_mod = make_pointnet2_cuda()
+    elif backend == "kdpc":
+        spec = importlib.util.spec_from_file_location("pointnet2_cuda", os.path.join(COMPAT, "pointnet2_cuda.py"))
+        cuda_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cuda_mod)
+    else:
+        raise ValueError(backend)
+    saved = sys.modules.get("pointnet2_cuda")
+    sys.modules["pointnet2_cuda"] = cuda_mod
+    try:
+        spec = importlib.util.spec_from_file_location(f"_ref_pointnet2_utils_{backend}", os.path.join(REF_INSTALL, "pointnet2", "pointnet2_utils.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop("pointnet2_cuda", None)
+        else:
+            sys.modules["pointnet2_cuda"] = saved
+    return mod

@@ -198,3 +198,42 @@ def test_bottleneck_and_plain_convs_against_the_reference_modules(stock):
     with torch.no_grad():
         a, b = mine.to(DEV).eval()(x4), ref.to(DEV).eval()(x4.clone())
     assert ((a - b).abs().max() / b.abs().max()).item() < 1e-4
+
+
+def test_route_b_reference_pointnet2_utils_on_the_kdpc_extension_stub():
+    """INTEGRATION.md route B: the reference's OWN pointnet2/pointnet2_utils.py (autograd Functions, output allocation)
+    with only the native extension replaced - ``pointnet2_cuda`` = compat/pointnet2_cuda.py (ctypes over libkdpc.so with
+    the pybind wrapper names) - against the same file on the reference's own kernels.  Config-2 sizes."""
+    if not ref_gpu.stock_available():
+        pytest.skip("baseline/_ref or oracle/_ref missing")
+    mine = ref_gpu.load_reference_pointnet2_utils("kdpc")
+    ref = ref_gpu.load_reference_pointnet2_utils("stock")
+    B, n, m = 8, 8192, 2048
+    xyz = make_pairs(B, n, seed=3, device=DEV)["pos1"]
+    a, b = mine.furthest_point_sample(xyz, m), ref.furthest_point_sample(xyz, m)
+    assert a.dtype == torch.int32 and torch.equal(a, b)
+    g = torch.Generator().manual_seed(1)
+    f = torch.randn(B, 64, n, generator=g).to(DEV)
+    assert torch.equal(mine.gather_operation(f, a), ref.gather_operation(f, a))
+    new_xyz = mine.gather_operation(xyz.permute(0, 2, 1).contiguous(), a).permute(0, 2, 1).contiguous()
+    (d1, i1), (d2, i2) = mine.three_nn(xyz, new_xyz), ref.three_nn(xyz, new_xyz)
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)
+    w = torch.softmax(-d1, dim=2).contiguous()
+    fs = torch.randn(B, 64, m, generator=g).to(DEV)
+    assert torch.equal(mine.three_interpolate(fs, i1, w), ref.three_interpolate(fs, i1, w))
+    idx = torch.randint(0, n, (B, m, 16), generator=g).int().to(DEV)
+    assert torch.equal(mine.grouping_operation(f, idx), ref.grouping_operation(f, idx))
+    bq1, bq2 = mine.ball_query(2.0, 16, xyz, new_xyz), ref.ball_query(2.0, 16, xyz, new_xyz)
+    assert torch.equal(bq1, bq2)
+    # backward through the reference's autograd Functions: deterministic CSR scatter vs the reference's atomics
+    for fn, args in ((lambda M, t: M.gather_operation(t, a), f), (lambda M, t: M.grouping_operation(t, idx), f),
+                     (lambda M, t: M.three_interpolate(t, i1, w), fs)):
+        grads = []
+        for M in (mine, ref):
+            t = args.clone().requires_grad_(True)
+            out = fn(M, t)
+            out.backward(torch.ones_like(out) * 0.5)
+            grads.append(t.grad)
+        assert torch.allclose(grads[0], grads[1], rtol=1e-5, atol=1e-5)
+    q = mine.QueryAndGroup(2.0, 16)(xyz, new_xyz, f)
+    assert q.shape == (B, 3 + 64, m, 16) and torch.equal(q, ref.QueryAndGroup(2.0, 16)(xyz, new_xyz, f))
