@@ -35,6 +35,10 @@ typedef struct CUstream_st *kdpc_stream_t;
 #define KDPC_ABI_VERSION 1
 int kdpc_abi_version(void);
 const char *kdpc_error_string(int code);
+/* SM budget of the persistent (one CTA per SM) kernels and of the split plans: 0 = the whole device (default), n > 0 = at
+ * most n SMs, so that a concurrent stream keeps the rest (the runner overlaps the next batch's sampling pyramid). */
+void kdpc_set_sm_limit(int n);
+int kdpc_sm_limit(void);
 
 /* ---- input pipeline (transforms/transforms.py:137-316: ProcessData, Augmentation) ---------------------------------
  * A batch of padded raw clouds pc*_raw [B,nmax,stride>=3] with n_raw[B] valid points each.

@@ -158,6 +158,10 @@ def lib() -> ctypes.CDLL:
         L.kdpc_weightnet_grad_ws_bytes.argtypes = [c_longlong]
         L.kdpc_loss_workspace_bytes.restype = c_longlong
         L.kdpc_loss_workspace_bytes.argtypes = []
+        L.kdpc_set_sm_limit.restype = None
+        L.kdpc_set_sm_limit.argtypes = [c_int]
+        L.kdpc_sm_limit.restype = c_int
+        L.kdpc_sm_limit.argtypes = []
         L.kdpc_fps_set_cluster.restype = None
         L.kdpc_fps_set_cluster.argtypes = [c_int]
         L.kdpc_fps_cluster_capacity.restype = c_int
@@ -186,7 +190,7 @@ def lib() -> ctypes.CDLL:
 
 
 def exported_symbols():
-    return ["kdpc_abi_version", "kdpc_error_string", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
+    return ["kdpc_abi_version", "kdpc_error_string", "kdpc_set_sm_limit", "kdpc_sm_limit", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
             "kdpc_loss_workspace_bytes", "kdpc_linear_dw_ws_bytes", "kdpc_weightnet_grad_ws_bytes", "kdpc_dataprep_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
             "kdpc_tc_async_enabled"] + list(_SIGNATURES)

@@ -13,3 +13,8 @@ KDPC_API const char *kdpc_error_string(int code) {
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "kdpc: unknown error";
 }
+
+static int g_sm_limit = 0;
+/* 0 = all SMs (default).  n > 0: persistent kernels and split plans size themselves for at most n SMs. */
+KDPC_API void kdpc_set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+KDPC_API int kdpc_sm_limit(void) { return g_sm_limit; }

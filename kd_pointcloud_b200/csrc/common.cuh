@@ -31,7 +31,11 @@ namespace kdpc {
 
 // SM count of the CURRENT device, queried once per device (148 on a B200): grids of the persistent kernels and the
 // split-K / queries-per-warp plans are sized from it.
-static inline int num_sms() {
+// kdpc_set_sm_limit(n) caps it: persistent kernels then launch at most n CTAs, leaving the other SMs to kernels of a
+// concurrent stream (runner.FlowRunner pipelines the sampling pyramid of the next batch beside the current one).
+// Work PLANS (split-K, splits over rows, queries per warp) always use the real count, so results do not depend on the cap.
+extern "C" int kdpc_sm_limit(void);
+static inline int device_sms() {
     static int cached[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -42,6 +46,10 @@ static inline int num_sms() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+static inline int num_sms() {                    // grid size of the persistent kernels
+    const int n = device_sms(), lim = kdpc_sm_limit();
+    return (lim > 0 && lim < n) ? lim : n;
 }
 
 // ---- exact-rounding fp32 helpers: never contracted or re-associated by nvcc ----------------

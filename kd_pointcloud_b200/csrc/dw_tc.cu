@@ -274,7 +274,7 @@ static inline void dw_plan(long long m, int n, int k, bool bias, DwArgs &a) {
     const long long mchunks = (m + DW_MCHUNK - 1) / DW_MCHUNK;
     // one wave of CTAs: every split leaves a [128 x 256] partial tile that dw_reduce_kernel has to read again, so more
     // splits than SMs only add reduction traffic (2 waves: 296 partial tiles = 19 MB read back for a 64 KB gradient)
-    long long want = (num_sms() + tiles - 1) / tiles;
+    long long want = (device_sms() + tiles - 1) / tiles;
     if (want > (mchunks + 3) / 4) want = (mchunks + 3) / 4;          // >= 4 chunks of 64 rows per CTA
     if (want > mchunks) want = mchunks;
     if (want < 1) want = 1;

@@ -233,7 +233,7 @@ KDPC_API int kdpc_group(int b, int c, int n, int s, int k, const float *f, const
         KDPC_ENSURE_SMEM((group_cm_smem_kernel<CPB>), 72 * 1024);
         const int cgroups = (c + CPB - 1) / CPB;
         // ~2 waves of 3 CTAs per SM; every CTA must amortise staging its channel rows over >= n gathered entries
-        int split = (6 * num_sms() + cgroups * b - 1) / (cgroups * b);
+        int split = (6 * device_sms() + cgroups * b - 1) / (cgroups * b);
         split = max(1, min(split, (int)(skl / (long long)n)));
         split = max(split, 1);
         int chunk = (sk + split - 1) / split;

@@ -440,7 +440,7 @@ static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cw
                      float *dist, cudaStream_t st) {
     // consecutive (Morton-adjacent) queries per warp: up to BF_QPW, fewer when the call is small so that the
     // machine still gets ~48 warps per SM
-    int qpw = (int)(((long long)b * s) / (num_sms() * 48));
+    int qpw = (int)(((long long)b * s) / (device_sms() * 48));
     qpw = qpw < 1 ? 1 : (qpw > BF_QPW ? BF_QPW : qpw);
     const int per_cta = BF_CTA_WARPS * qpw;
     dim3 grid((s + per_cta - 1) / per_cta, b);

@@ -159,7 +159,7 @@ scatter_cm_csr_kernel(int c, int n, int m, int gdiv, const float *__restrict__ g
 static int build_csr(int b, int n, int m, const int *idx, int *offsets, int *perm, cudaStream_t st) {
     if (b > 65535) return KDPC_EUNSUPPORTED;
     // ~2 CTAs per SM over all clouds, at least 64 candidates per part (and one segment per thread when possible)
-    int parts = (2 * num_sms() + b - 1) / b;
+    int parts = (2 * device_sms() + b - 1) / b;
     if (parts > (n + 63) / 64) parts = (n + 63) / 64;
     if (parts < 1) parts = 1;
     const int per_part = (n + parts - 1) / parts;

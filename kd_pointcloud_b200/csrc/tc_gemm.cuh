@@ -116,7 +116,7 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
 static inline void plan_split_k(GemmShape &g) {
     g.splits = 1;
     g.chunks_per_split = g.num_chunks;
-    const int sms = num_sms();
+    const int sms = device_sms();
     if (g.num_tiles * 2 > sms || g.num_chunks < 4) return;
     int want = (int)(sms / g.num_tiles);
     if (want > g.num_chunks / 2) want = g.num_chunks / 2;       // >= 2 chunks per work item

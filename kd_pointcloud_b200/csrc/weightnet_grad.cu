@@ -142,7 +142,7 @@ weightnet_grad_reduce_kernel(long long nwarps, const float *__restrict__ partial
 
 static inline long long wg_grid(long long rows) {
     long long ctas = (rows + WG_THREADS - 1) / WG_THREADS;
-    const long long cap = 2LL * num_sms();      // the final reduction walks one partial per warp
+    const long long cap = 2LL * device_sms();      // the final reduction walks one partial per warp
     return ctas < cap ? (ctas < 1 ? 1 : ctas) : cap;
 }
 

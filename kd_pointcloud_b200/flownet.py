@@ -123,7 +123,14 @@ class PointConvBidirection(nn.Module):
     def _sample_pyramid(self, pc_l0):
         return _SamplePyramid(pc_l0, [self.level1.npoint, self.level2.npoint, self.level3.npoint, self.level4.npoint])
 
-    def forward(self, xyz1, xyz2, color1, color2):
+    def sample_geometry(self, xyz1, xyz2):
+        """The part of the forward that depends on the input COORDINATES only: the 2B-cloud batch and its four-level
+        FPS pyramid.  ``forward(..., geometry=g)`` consumes it; the runner computes it for batch i+1 on a second stream
+        while batch i's forward runs (the pyramid is a 1.3 ms latency chain that leaves most SMs idle)."""
+        pc_l0 = torch.cat([xyz1, xyz2], dim=0).contiguous()
+        return pc_l0, self._sample_pyramid(pc_l0)
+
+    def forward(self, xyz1, xyz2, color1, color2, geometry=None):
         # xyz*, color*: [B,N,3]   (models_bid_pointconv.py:74-92)
         B = xyz1.shape[0]
         up = self.upsample.forward_pm
@@ -134,7 +141,9 @@ class PointConvBidirection(nn.Module):
         npts = (self.level1.npoint, self.level2.npoint, self.level3.npoint, self.level4.npoint)
         gkey = (KF._tkey(xyz1), KF._tkey(xyz2), npts)
         hit = _GEOMETRY_CACHE.get(gkey) if (KF._CACHE_ENABLED and not xyz1.requires_grad and not xyz2.requires_grad) else None
-        if hit is not None:
+        if geometry is not None:
+            pc_l0, pyramid = geometry
+        elif hit is not None:
             pc_l0, pyramid = hit[0], hit[1]
         else:
             pc_l0 = both(xyz1, xyz2).contiguous()

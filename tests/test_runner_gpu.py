@@ -43,3 +43,41 @@ def test_runner_graph_host_and_pipelined_calls_agree():
     assert abs(m[0] - o[0]) < 2e-6 * abs(o[0]) + 1e-9
     for i in (1, 2, 3, 5):
         assert round(m[i] * B * N) == round(o[i] * B * N)
+
+
+def test_pipelined_runner_equals_plain_runner():
+    """Sampling pyramid of batch i+1 on a second stream beside the forward of batch i (one-CTA FPS kernel, persistent
+    kernels capped to the SMs it leaves free): same metrics and flows as the single-graph runner, batch for batch."""
+    from kd_pointcloud_b200 import flownet
+    from kd_pointcloud_b200.runner import FlowRunner, PipelinedFlowRunner
+    from kd_pointcloud_b200.synth import make_pairs, synthetic_state_dict
+    torch.manual_seed(0)
+    model = flownet.teacher()
+    model.load_state_dict(synthetic_state_dict(model.state_dict(), 0))
+    model = model.to(DEV).eval()
+    B, N = 2, 4096
+    host = [_pinned(make_pairs(B, N, seed=300 + i)) for i in range(5)]
+    dev_batches = [{k: v.to(DEV) for k, v in b.items()} for b in host]
+    plain = FlowRunner(model, B, N, DEV, use_graph=True)
+    assert plain.warmup_and_capture(host[0], warmup=1)
+    ref, ref_flow = [], []
+    for b in host:
+        ref.append(plain.run_host(b))
+        ref_flow.append(plain.out_flow.clone())
+    ref_m = []
+    for b in host:
+        plain.run_host(b)
+        ref_m.append(plain.out_metrics.clone())
+    pipe = PipelinedFlowRunner(model, B, N, DEV)
+    assert pipe.warmup_and_capture(host[0], warmup=1) and 0 < pipe.sm_limit < 148
+    for _ in range(2):                                                  # twice: slots and events are reused
+        got = pipe.run_resident(dev_batches)
+        torch.cuda.synchronize()
+        for a, b in zip(got, ref_m):
+            assert torch.equal(a, b)
+    assert torch.equal(pipe.out_flow[(len(host) - 1) & 1], ref_flow[-1])
+    assert pipe.run_host_pipelined(iter(host)) == ref
+    assert pipe.run_host_pipelined(iter(host[:1])) == ref[:1]
+    assert pipe.run_host_pipelined(iter([])) == []
+    from kd_pointcloud_b200 import _lib
+    assert _lib.lib().kdpc_sm_limit() == 0                              # the cap only applies while capturing
