@@ -40,6 +40,9 @@ def parse():
                     help="infer = configs[2] (the headline); kd_train = configs[3]/[4]: teacher fwd + student fwd/bwd + "
                          "fused KD loss + Adam, gradients all-reduced over NCCL when N > 1")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="time the single-graph runner (one batch at a time) instead of the two-stream pipeline that "
+                         "overlaps the next batch's sampling pyramid with the current forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the GPU-side baseline leg (the unmodified reference model on its own torch layers + its own "
@@ -373,6 +376,12 @@ def run_kdpc(args):
     runner = FlowRunner(model, B, NPOINTS, dev, use_graph=not args.no_graph)
     graphed = runner.warmup_and_capture(resident[0], warmup=2)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pipelined = graphed and not args.no_pipeline and 2 * B <= 32
+    pipe = None
+    if pipelined:
+        from kd_pointcloud_b200.runner import PipelinedFlowRunner
+        pipe = PipelinedFlowRunner(model, B, NPOINTS, dev)
+        pipe.warmup_and_capture(resident[0], warmup=1)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -400,19 +409,52 @@ def run_kdpc(args):
         evs.append((a, b))
     barrier()
     t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t_clock0 = t_wall0                                       # clocks are sampled over BOTH timed regions (single graph, pipeline)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     eager_launches = ops.LAUNCHES - launches0
     launches = runner.launches_per_step * args.steps if graphed else eager_launches
     epe_last = float(runner.out_epe.item())
+    single_ms_step = dev_ms / args.steps
+
+    # ---------------- the same K batches through the two-stream pipeline (the reported value) ----------------------
+    # step i = forward of batch i (stream A) beside the sampling pyramid of batch i+1 (stream B).  The timed region starts
+    # with batch 0's pyramid already computed and ends when batch K's pyramid is: K pyramids + K forwards = K whole
+    # batches.  The L2 flush and the device-to-device load of the next batch are INSIDE the timed region.
+    if pipe is not None:
+        main = torch.cuda.current_stream(dev)
+        for rep in range(2):                                 # rep 0: warm-up of the pipeline itself
+            pipe.load(resident[0], 0)
+            pipe.launch_fps(0)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall0 = time.time()
+            a.record()
+            for i in range(args.steps):
+                slot = i & 1
+                pipe.load(resident[(i + 1) % pool], slot ^ 1)
+                pipe.launch_fps(slot ^ 1)
+                flush.zero_()                                # evict L2 between timed iterations
+                pipe.launch_main(slot)
+            main.wait_stream(pipe.stream_b)                  # the last pyramid belongs to the timed region
+            b.record()
+            barrier()
+            t_wall1 = time.time()
+            dev_ms = a.elapsed_time(b)
+        last_slot = (args.steps - 1) & 1
+        epe_pipe = float(pipe.out_metrics[last_slot][0].item())
+        assert abs(epe_pipe - epe_last) < 1e-6, (epe_pipe, epe_last)      # same last batch, same result as the single graph
+        launches = pipe.launches_per_step * args.steps
+
+    clocks = sampler.stop(t_clock0, t_wall1) if sampler else None
 
     # ---------------- end to end through the public call, host buffers --------------------------
     # (the public streaming call: pinned host batches in, one EPE3D per batch out; the H2D of batch i+1 overlaps the
     # kernels of batch i, every step still moves its own inputs and reads its own result)
-    runner.run_host_pipelined(host[i % pool] for i in range(min(2, args.warmup)))
+    e2e_runner = pipe if pipe is not None else runner
+    e2e_runner.run_host_pipelined(host[i % pool] for i in range(min(2, args.warmup)))
     barrier()
     t0 = time.perf_counter()
-    epes = runner.run_host_pipelined(host[i % pool] for i in range(args.steps))
+    epes = e2e_runner.run_host_pipelined(host[i % pool] for i in range(args.steps))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -445,7 +487,13 @@ def run_kdpc(args):
             "data": "synthetic",
             "config": cfg,
             "details": {"global_pairs_per_step": B * world, "sharding": "batch-sharded, no collectives",
-                        "cuda_graph": bool(graphed), "l2": "256 MB flush between timed iterations",
+                        "cuda_graph": bool(graphed), "l2": "256 MB flush between timed iterations (inside the timed region "
+                                                           "of the pipelined run)",
+                        "pipeline": ("two streams: forward of batch i beside the sampling pyramid (4-level FPS) of batch i+1; "
+                                     "K pyramids + K forwards inside the timed region; results bit-identical to the single "
+                                     "graph (tests/test_runner_gpu.py)") if pipe is not None else "none (single graph per batch)",
+                        "single_graph_ms_per_step": single_ms_step, "single_graph_pairs_per_s": B * world / (single_ms_step * 1e-3),
+                        "pipeline_sm_limit": None if pipe is None else pipe.sm_limit,
                         "epe3d_last_step": epe_last, "epe3d_pair0_last_step": epe_pair0,
                         "parity": "FPS/kNN indices bit-exact; layer outputs 1e-4 relative on every element with shared "
                                   "kNN inputs; whole model: < 0.5 % of elements off by > 1e-4 of range (K-th-neighbour "

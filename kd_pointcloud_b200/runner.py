@@ -227,19 +227,17 @@ class PipelinedFlowRunner:
                         self.launches_per_step = ops.LAUNCHES - n0
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            # TWO memory pools: G_fps[s ^ 1] runs concurrently with G_main[s], so the sampling graphs must never reuse
-            # memory the forward graphs freed during capture (graphs that share a pool must not overlap in time);
-            # the two sampling graphs are serialised on stream B, the two forward graphs on stream A
-            pool_f = pool_m = None
+            # FOUR private memory pools, one per graph: a graph's temporaries are recycled inside its own pool only.
+            # G_fps[s ^ 1] runs concurrently with G_main[s], and the OUTPUTS of G_fps[s] (the pyramid) must survive
+            # a replay of G_fps[s ^ 1] - with a shared pool that replay's temporaries landed on them (seen as rare
+            # 1e-5 .. 1e-2 EPE differences).
             for slot in (0, 1):
                 gf = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gf, pool=pool_f):
+                with torch.cuda.graph(gf):
                     self._fps_part(slot)
-                pool_f = gf.pool()
                 gm = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gm, pool=pool_m):
+                with torch.cuda.graph(gm):
                     self._main_part(slot)
-                pool_m = gm.pool()
                 self.g_fps[slot], self.g_main[slot] = gf, gm
             self._keepalive = KF.weight_cache_tensors()
         finally:
