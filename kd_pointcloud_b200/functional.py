@@ -109,6 +109,20 @@ def clear_caches(weights: bool = False) -> None:
         _WN_CACHE.clear()
 
 
+def snapshot_neighbour_caches():
+    """The current kNN results and sorted clouds (what a coordinate-only pre-pass computed), to be re-installed later by
+    ``seed_neighbour_caches`` - the runner computes them for batch i+1 on a second stream."""
+    return dict(_KNN_CACHE.d), dict(_SORT_CACHE.d)
+
+
+def seed_neighbour_caches(snapshot) -> None:
+    knn, srt = snapshot
+    for k, v in srt.items():
+        _SORT_CACHE.put(k, v)
+    for k, v in knn.items():
+        _KNN_CACHE.put(k, v)
+
+
 def set_cache_enabled(flag: bool) -> None:
     global _CACHE_ENABLED
     _CACHE_ENABLED = bool(flag)

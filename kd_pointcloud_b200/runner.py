@@ -159,7 +159,9 @@ class PipelinedFlowRunner:
 
         stream A:  G_main[slot]   the forward of batch i consuming its pyramid        (persistent kernels capped to
                                                                                         ``num_sms - 2B`` CTAs)
-        stream B:  G_fps[slot^1]  the pyramid of batch i+1 with the ONE-CTA-per-cloud FPS kernel (2B SMs)
+        stream B:  G_fps[slot^1]  the pyramid of batch i+1 with the ONE-CTA-per-cloud FPS kernel (2B SMs), followed by
+                                  every neighbour search that needs input coordinates only (14 of the forward's 22 kNN
+                                  sets and 8 of its 11 spatial sorts); the forward finds them in the kNN cache
 
     with events in both directions (G_main(i) waits for G_fps(i); G_fps(i+2) waits for G_main(i), which reads the same
     pyramid buffers).  The persistent tcgen05 kernels assign tiles statically to their CTAs, so they must not be
@@ -168,10 +170,12 @@ class PipelinedFlowRunner:
     Every batch still gets the whole forward; only the order across batches changes.  Two slots of static buffers.
     """
 
-    def __init__(self, model: torch.nn.Module, batch: int, npoints: int = 8192, device="cuda"):
+    def __init__(self, model: torch.nn.Module, batch: int, npoints: int = 8192, device="cuda", precompute_knn: bool = True):
         self.model = model.eval()
         self.device = torch.device(device)
         self.batch = batch
+        self.precompute_knn = precompute_knn and hasattr(model, "precompute_neighbours")
+        self.neighbours = [None, None]
         self.static = [{k: torch.zeros(batch, npoints, 3, device=self.device) for k in KEYS} for _ in range(2)]
         self.geometry = [None, None]
         self.out_flow = [None, None]
@@ -193,12 +197,20 @@ class PipelinedFlowRunner:
         L.kdpc_fps_set_cluster(0)                           # one CTA per cloud: 2B SMs, leaves the rest to stream A
         try:
             with torch.no_grad():
+                KF.clear_caches()
                 self.geometry[slot] = self.model.sample_geometry(s["pos1"], s["pos2"])
+                if self.precompute_knn:
+                    # + every coordinate-only neighbour search of the forward (their results wait in the caches)
+                    self.model.precompute_neighbours(self.geometry[slot])
+                    self.neighbours[slot] = KF.snapshot_neighbour_caches()
+                KF.clear_caches()
         finally:
             L.kdpc_fps_set_cluster(1)
 
     def _main_part(self, slot: int):
         KF.clear_caches()
+        if self.neighbours[slot] is not None:
+            KF.seed_neighbour_caches(self.neighbours[slot])
         s = self.static[slot]
         with torch.no_grad():
             flows = self.model(s["pos1"], s["pos2"], s["color1"], s["color2"], geometry=self.geometry[slot])[0]

@@ -68,8 +68,10 @@ def test_pipelined_runner_equals_plain_runner():
     for b in host:
         plain.run_host(b)
         ref_m.append(plain.out_metrics.clone())
+    from kd_pointcloud_b200 import ops
     pipe = PipelinedFlowRunner(model, B, N, DEV)
     assert pipe.warmup_and_capture(host[0], warmup=1) and 0 < pipe.sm_limit < 148
+    assert pipe.precompute_knn and pipe.neighbours[0] is not None and len(pipe.neighbours[0][0]) == 14   # kNN sets moved to stream B
     for _ in range(2):                                                  # twice: slots and events are reused
         got = pipe.run_resident(dev_batches)
         torch.cuda.synchronize()
