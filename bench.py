@@ -361,6 +361,27 @@ def run_kdpc(args):
     host = [{k: v.pin_memory() for k, v in make_pairs(B, NPOINTS, seed=1234 + 1000 * rank + i).items()} for i in range(pool)]
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
 
+    if args.profile_one and not args.no_pipeline:
+        # the FORWARD part of the pipelined step (stream A's graph), eagerly, between cudaProfilerStart/Stop
+        from kd_pointcloud_b200 import _lib
+        from kd_pointcloud_b200.runner import PipelinedFlowRunner
+        pipe = PipelinedFlowRunner(model, B, NPOINTS, dev)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        pipe.sm_limit = max(n_sm // 2, n_sm - 2 * B)
+        _lib.lib().kdpc_set_sm_limit(pipe.sm_limit)
+        for slot in (0, 1):
+            pipe.load(resident[slot], slot)
+        for _ in range(2):
+            pipe._fps_part(0)
+            pipe._main_part(0)
+        pipe._fps_part(1)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        pipe._main_part(1)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_one": "pipelined forward part", "epe3d": float(pipe.out_metrics[1][0].item())}))
+        return
     if args.profile_one:
         runner = FlowRunner(model, B, NPOINTS, dev, use_graph=False)
         runner.warmup_and_capture(resident[0], warmup=2)
@@ -380,7 +401,7 @@ def run_kdpc(args):
     pipe = None
     if pipelined:
         from kd_pointcloud_b200.runner import PipelinedFlowRunner
-        pipe = PipelinedFlowRunner(model, B, NPOINTS, dev)
+        pipe = PipelinedFlowRunner(model, B, NPOINTS, dev, dual_forward=os.environ.get("KDPC_DUAL_FORWARD", "1") == "1")
         pipe.warmup_and_capture(resident[0], warmup=1)
 
     def barrier():
@@ -423,19 +444,17 @@ def run_kdpc(args):
     if pipe is not None:
         main = torch.cuda.current_stream(dev)
         for rep in range(2):                                 # rep 0: warm-up of the pipeline itself
-            pipe.load(resident[0], 0)
-            pipe.launch_fps(0)
+            pipe.launch_fps(0, resident[0])
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_wall0 = time.time()
             a.record()
             for i in range(args.steps):
                 slot = i & 1
-                pipe.load(resident[(i + 1) % pool], slot ^ 1)
-                pipe.launch_fps(slot ^ 1)
+                pipe.launch_fps(slot ^ 1, resident[(i + 1) % pool])    # device-to-device load of the next batch + its geometry
                 flush.zero_()                                # evict L2 between timed iterations
                 pipe.launch_main(slot)
-            main.wait_stream(pipe.stream_b)                  # the last pyramid belongs to the timed region
+            pipe.join()                                      # the last pyramid (and both forward streams) belong to the timed region
             b.record()
             barrier()
             t_wall1 = time.time()
@@ -494,6 +513,7 @@ def run_kdpc(args):
                                      "graph (tests/test_runner_gpu.py)") if pipe is not None else "none (single graph per batch)",
                         "single_graph_ms_per_step": single_ms_step, "single_graph_pairs_per_s": B * world / (single_ms_step * 1e-3),
                         "pipeline_sm_limit": None if pipe is None else pipe.sm_limit,
+                        "pipeline_forward_streams": None if pipe is None else (2 if pipe.dual_forward else 1),
                         "epe3d_last_step": epe_last, "epe3d_pair0_last_step": epe_pair0,
                         "parity": "FPS/kNN indices bit-exact; layer outputs 1e-4 relative on every element with shared "
                                   "kNN inputs; whole model: < 0.5 % of elements off by > 1e-4 of range (K-th-neighbour "

@@ -170,7 +170,8 @@ class PipelinedFlowRunner:
     Every batch still gets the whole forward; only the order across batches changes.  Two slots of static buffers.
     """
 
-    def __init__(self, model: torch.nn.Module, batch: int, npoints: int = 8192, device="cuda", precompute_knn: bool = True):
+    def __init__(self, model: torch.nn.Module, batch: int, npoints: int = 8192, device="cuda", precompute_knn: bool = True,
+                 dual_forward: bool = False):
         self.model = model.eval()
         self.device = torch.device(device)
         self.batch = batch
@@ -184,6 +185,8 @@ class PipelinedFlowRunner:
         self.g_main = [None, None]
         self.launches_per_step = 0
         self.stream_b = torch.cuda.Stream(device=self.device)
+        self.stream_a = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        self.dual_forward = dual_forward
         self.fps_done = [torch.cuda.Event(), torch.cuda.Event()]
         self.main_done = [torch.cuda.Event(), torch.cuda.Event()]
         self._main_ran = [False, False]
@@ -259,15 +262,19 @@ class PipelinedFlowRunner:
 
     def load(self, batch: Dict[str, torch.Tensor], slot: int) -> int:
         nbytes = 0
+        if self._main_ran[slot]:                            # the forward that last read this slot's inputs is done
+            torch.cuda.current_stream(self.device).wait_event(self.main_done[slot])
         for k in KEYS:
             self.static[slot][k].copy_(batch[k], non_blocking=True)
             nbytes += batch[k].numel() * batch[k].element_size()
         return nbytes
 
     # ---- pipeline primitives --------------------------------------------------------------------------------------
-    def launch_fps(self, slot: int) -> None:
-        """Sampling pyramid of the batch in ``slot`` on stream B (after the inputs of that slot, written on the current
-        stream, are in place, and after the previous forward that read this slot's pyramid)."""
+    def launch_fps(self, slot: int, batch: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Sampling pyramid (+ coordinate-only kNN) of the batch in ``slot`` on stream B, after the previous forward that
+        read this slot's inputs / pyramid.  ``batch``: device tensors copied into the slot's input buffers ON STREAM B
+        first (so that the caller's stream never waits for a forward); without it the inputs written on the current
+        stream (``load``) are used."""
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -275,15 +282,38 @@ class PipelinedFlowRunner:
             self.stream_b.wait_event(ready)
             if self._main_ran[slot]:
                 self.stream_b.wait_event(self.main_done[slot])
+            if batch is not None:
+                for k in KEYS:
+                    self.static[slot][k].copy_(batch[k], non_blocking=True)
             self.g_fps[slot].replay()
             self.fps_done[slot].record(self.stream_b)
 
     def launch_main(self, slot: int) -> None:
         main = torch.cuda.current_stream(self.device)
-        main.wait_event(self.fps_done[slot])
-        self.g_main[slot].replay()
-        self.main_done[slot].record(main)
+        if self.dual_forward:
+            # the two slots' forwards on their OWN streams: forward i+1 may start while forward i is still running; the
+            # many-CTA kernels of one (kNN, sorts, interpolation) fill the issue slots the other's one-CTA-per-SM tcgen05
+            # kernels leave idle, and a persistent kernel's tail overlaps the next one's ramp
+            st = self.stream_a[slot]
+            ready = torch.cuda.Event()
+            ready.record(main)                             # this slot's inputs (and the L2 flush) were queued on `main`
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                st.wait_event(self.fps_done[slot])
+                self.g_main[slot].replay()
+                self.main_done[slot].record(st)
+        else:
+            main.wait_event(self.fps_done[slot])
+            self.g_main[slot].replay()
+            self.main_done[slot].record(main)
         self._main_ran[slot] = True
+
+    def join(self) -> None:
+        """Make the current stream wait for everything the pipeline has in flight."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self.stream_b)
+        for st in self.stream_a:
+            main.wait_stream(st)
 
     def run_resident(self, batches, on_step=None) -> list:
         """Device-resident batches through the two-stream pipeline; returns per-batch device metric tensors (clones).
@@ -292,17 +322,20 @@ class PipelinedFlowRunner:
         n = len(batches)
         if n == 0:
             return out
-        self.load(batches[0], 0)
-        self.launch_fps(0)
+        self.launch_fps(0, batches[0])
         for i in range(n):
             slot = i & 1
             if i + 1 < n:
-                self.load(batches[i + 1], slot ^ 1)
-                self.launch_fps(slot ^ 1)                  # overlaps launch_main(slot) below
+                self.launch_fps(slot ^ 1, batches[i + 1])  # overlaps launch_main(slot) below
             if on_step is not None:
                 on_step(i)
             self.launch_main(slot)
-            out.append(self.out_metrics[slot].clone())
+            if self.dual_forward:
+                with torch.cuda.stream(self.stream_a[slot]):
+                    out.append(self.out_metrics[slot].clone())
+            else:
+                out.append(self.out_metrics[slot].clone())
+        self.join()
         return out
 
     def run_host_pipelined(self, host_batches) -> list:
@@ -353,12 +386,15 @@ class PipelinedFlowRunner:
                 res.append(float(self._res_host[j][0]))
             main.wait_event(h2d_done[slot])
             self.launch_main(slot)
-            self._res_host[slot].copy_(self.out_metrics[slot], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(main)
+            rs = self.stream_a[slot] if self.dual_forward else main       # the stream this slot's forward runs on
+            with torch.cuda.stream(rs):
+                self._res_host[slot].copy_(self.out_metrics[slot], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(rs)
             pending.append((slot, ev))
             i += 1
         for j, ev in pending:
             ev.synchronize()
             res.append(float(self._res_host[j][0]))
+        self.join()
         return res

@@ -45,7 +45,8 @@ def test_runner_graph_host_and_pipelined_calls_agree():
         assert round(m[i] * B * N) == round(o[i] * B * N)
 
 
-def test_pipelined_runner_equals_plain_runner():
+@pytest.mark.parametrize("dual_forward", [False, True])
+def test_pipelined_runner_equals_plain_runner(dual_forward):
     """Sampling pyramid of batch i+1 on a second stream beside the forward of batch i (one-CTA FPS kernel, persistent
     kernels capped to the SMs it leaves free): same metrics and flows as the single-graph runner, batch for batch."""
     from kd_pointcloud_b200 import flownet
@@ -69,7 +70,7 @@ def test_pipelined_runner_equals_plain_runner():
         plain.run_host(b)
         ref_m.append(plain.out_metrics.clone())
     from kd_pointcloud_b200 import ops
-    pipe = PipelinedFlowRunner(model, B, N, DEV)
+    pipe = PipelinedFlowRunner(model, B, N, DEV, dual_forward=dual_forward)   # True: the two slots' forwards on their own streams
     assert pipe.warmup_and_capture(host[0], warmup=1) and 0 < pipe.sm_limit < 148
     assert pipe.precompute_knn and pipe.neighbours[0] is not None and len(pipe.neighbours[0][0]) == 14   # kNN sets moved to stream B
     for _ in range(2):                                                  # twice: slots and events are reused
