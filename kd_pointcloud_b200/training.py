@@ -11,6 +11,7 @@ device scalar and leaves the read to the caller.
 from __future__ import annotations
 
 import copy
+import os
 from typing import Callable, Dict, Optional
 
 import torch
@@ -19,14 +20,49 @@ from . import functional as KF
 from . import losses
 
 
+OVERLAP_TEACHER = os.environ.get("KDPC_OVERLAP_TEACHER", "1") != "0"
+_SIDE = {}
+
+
+def _teacher_and_student_forward(teacher, student, p1, p2, c1, c2):
+    """Teacher forward (no grad) and student forward of one KD step.  Both see the same clouds, so the sampling pyramid and
+    every coordinate-only neighbour set are computed ONCE up front; the teacher's forward then runs on a side stream while
+    the student's forward is issued on the current one (the teacher is the inference path: one-CTA-per-SM tcgen05 kernels
+    with idle issue slots; the student's training path is mostly many-CTA kernels).  Joined before the loss."""
+    fused = (OVERLAP_TEACHER and p1.is_cuda and hasattr(teacher, "sample_geometry") and hasattr(teacher, "precompute_neighbours")
+             and getattr(teacher, "level1", None) is not None and getattr(student, "level1", None) is not None
+             and teacher.level1.npoint == student.level1.npoint)
+    teacher.eval()
+    if not fused:
+        with torch.no_grad():
+            t_out = teacher(p1, p2, c1, c2)
+        student.train()
+        return t_out, student(p1, p2, c1, c2)
+    dev = p1.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    with torch.no_grad():
+        geo = teacher.sample_geometry(p1, p2)
+        teacher.precompute_neighbours(geo)                 # shared, read-only from here on (functional's kNN / sort caches)
+    side.wait_stream(main)
+    with torch.cuda.stream(side), torch.no_grad():
+        t_out = teacher(p1, p2, c1, c2, geometry=geo)
+    student.train()
+    s_out = student(p1, p2, c1, c2, geometry=geo)
+    main.wait_stream(side)
+    for group in t_out:                                     # produced on the side stream, consumed (loss) on this one
+        for t in group:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(main)
+    return t_out, s_out
+
+
 def _forward_backward(teacher, student, batch, optimizer, gamma, beta, layers, hint_mode, global_batch=None) -> torch.Tensor:
     KF.clear_caches()
     p1, p2, c1, c2, flow = batch["pos1"], batch["pos2"], batch["color1"], batch["color2"], batch["flow"]
-    teacher.eval()
-    with torch.no_grad():
-        t_out = teacher(p1, p2, c1, c2)
-    student.train()
-    s_out = student(p1, p2, c1, c2)
+    t_out, s_out = _teacher_and_student_forward(teacher, student, p1, p2, c1, c2)
     loss = losses.cross_biDirection_loss_ht(s_out[0], s_out[5], s_out[6], s_out[1], s_out[2], flow, t_out[0], t_out[5],
                                             t_out[6], t_out[1], t_out[2], gamma, beta, layer=layers, hint_mode=hint_mode,
                                             global_batch=global_batch)
