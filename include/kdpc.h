@@ -132,6 +132,10 @@ int kdpc_knn_bruteforce(int b, int s, int n, int k, const float *query, const fl
  * reused by any number of kdpc_knn_sorted calls (as queries or as candidates). */
 long long kdpc_spatial_sort_bytes(int b, int n);
 int kdpc_spatial_sort(int b, int n, const float *xyz, void *out, kdpc_stream_t stream);
+/* The same representation for a DISPLACED copy of an already sorted cloud (a warped cloud, pointconv_util.py:2114-2142):
+ * the parent's order is reused, the tile boxes are recomputed from the new coordinates; kdpc_knn_sorted results are
+ * unchanged (the search needs valid boxes, not a good order). */
+int kdpc_spatial_reorder(int b, int n, const float *xyz, const void *parent_ws, void *ws, kdpc_stream_t stream);
 /* Exact kNN between two sorted clouds by best-first search over candidate tiles with a conservative
  * distance bound (knn_bf.cu).  direct = 0: square_distance rounding (knn_point); direct = 1: the
  * pointnet2 kernels' (dx^2+dy^2+dz^2) rounding (three_nn).  Output rows are in ORIGINAL query order. */

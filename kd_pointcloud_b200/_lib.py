@@ -92,6 +92,7 @@ _SIGNATURES = {
     "kdpc_knn": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_knn_bruteforce": [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_spatial_sort": [c_int, c_int, _P, _P, _P],
+    "kdpc_spatial_reorder": [c_int, c_int, _P, _P, _P, _P],
     "kdpc_dataprep_mask": [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_dataprep_select": [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_linear_dw": [c_longlong, c_int, c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, _P],

@@ -101,6 +101,7 @@ def clear_caches(weights: bool = False) -> None:
     _KNN_CACHE.clear()
     _CSR_CACHE.clear()
     _SORT_CACHE.clear()
+    _SORT_PARENT.clear()
     for c in _EXTRA_CACHES:
         c.clear()
     if weights:
@@ -148,6 +149,18 @@ def cm(x: torch.Tensor) -> torch.Tensor:
 _SORT_CACHE = _LRU(48)
 
 
+_SORT_PARENT = _LRU(16)         # displaced cloud -> the cloud it was displaced from (PointWarping)
+USE_SORT_REUSE = os.environ.get("KDPC_SORT_REUSE", "1") != "0"
+
+
+def hint_displaced_copy(child: torch.Tensor, parent: torch.Tensor) -> None:
+    """``child`` [B,N,3] is a smooth displacement of ``parent`` (same shape): when a kNN needs the child sorted, the parent's
+    Morton order is reused (kdpc_spatial_reorder) instead of sorting again.  Results do not change."""
+    if USE_SORT_REUSE and _CACHE_ENABLED and child.shape == parent.shape and child.is_cuda:
+        c = child.detach()
+        _SORT_PARENT.put(_tkey(c if c.is_contiguous() else c.contiguous()), (parent.detach(), child))
+
+
 def _sorted_cloud(xyz_d: torch.Tensor) -> torch.Tensor:
     """Morton-sorted copy of a contiguous [B,N,3] cloud, cached per tensor (storage, version): every point
     set of the pyramid takes part in several kNN calls (as queries and as candidates)."""
@@ -170,7 +183,12 @@ def _sorted_cloud(xyz_d: torch.Tensor) -> torch.Tensor:
             out = buf[(off // per) * each:(off // per + B) * each]
             _SORT_CACHE.put(key, (out, xyz_d))
             return out
-    out = K.spatial_sort(xyz_d)
+    par = _SORT_PARENT.get(key)
+    if par is not None and ops.SORT_MIN_N <= N <= ops.SORT_MAX_N:
+        pd = par[0] if par[0].is_contiguous() else par[0].contiguous()
+        out = K.spatial_reorder(xyz_d, _sorted_cloud(pd))          # the parent's order, boxes from the new coordinates
+    else:
+        out = K.spatial_sort(xyz_d)
     _SORT_CACHE.put(key, (out, xyz_d))
     return out
 

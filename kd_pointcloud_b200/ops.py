@@ -340,6 +340,23 @@ def _spatial_sort(xyz: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _spatial_reorder(xyz: torch.Tensor, parent_sorted: torch.Tensor) -> torch.Tensor:
+    """Sorted-cloud buffer of xyz [B,N,3] in the order of ``parent_sorted`` (the buffer of a cloud xyz is a displaced
+    copy of): no second sort, boxes recomputed (kdpc_spatial_reorder)."""
+    _req(xyz, torch.float32, 3, "xyz")
+    _req(parent_sorted, torch.uint8, 1, "sorted parent")
+    B, N, _ = xyz.shape
+    if parent_sorted.numel() != _lib.lib().kdpc_spatial_sort_bytes(B, N):
+        raise ValueError("kdpc: the parent's sorted-cloud buffer does not match xyz")
+    with _guard(xyz):
+        out = torch.empty_like(parent_sorted)
+        _call("kdpc_spatial_reorder", B, N, _p(xyz), _p(parent_sorted), _p(out), _stream())
+    return out
+
+
+_register("spatial_reorder(Tensor xyz, Tensor parent_sorted) -> Tensor", _spatial_reorder, lambda xyz, p: torch.empty_like(p))
+
+
 def _knn_sorted(qsorted: torch.Tensor, csorted: torch.Tensor, b: int, s: int, n: int, k: int) -> torch.Tensor:
     _req(qsorted, torch.uint8, 1, "sorted queries")
     _req(csorted, torch.uint8, 1, "sorted candidates")

@@ -444,7 +444,11 @@ class PointWarping(nn.Module):
     def forward_pm(self, xyz1, xyz2, flow1=None):
         if flow1 is None:
             return xyz2
-        return xyz2 - _interp(xyz2, xyz1 + flow1, flow1)
+        carried = xyz1 + flow1
+        KF.hint_displaced_copy(carried, xyz1)               # both warped clouds are displaced copies of sorted clouds:
+        warped = xyz2 - _interp(xyz2, carried, flow1)       # their kNNs reuse the parents' Morton order (same results)
+        KF.hint_displaced_copy(warped, xyz2)
+        return warped
 
     def forward(self, xyz1, xyz2, flow1=None):
         if flow1 is None:

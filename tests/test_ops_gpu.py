@@ -272,6 +272,39 @@ def test_build_csr_inverse_index():
             assert np.array_equal(seg, np.nonzero(flat[b] == i)[0])     # ascending members
 
 
+def test_knn_on_displaced_clouds_reuses_the_parent_order_with_identical_results():
+    """Warped clouds (PointWarping) are sorted by re-using the parent's Morton order (kdpc_spatial_reorder): the kNN
+    results must not change - for a smooth displacement, for an incoherent one (loose boxes), and for a permutation-like
+    jump - as queries and as candidates."""
+    g = torch.Generator().manual_seed(8)
+    d = make_pairs(4, 8192, seed=12)
+    base, other = d["pos1"].to(DEV), d["pos2"].to(DEV)
+    for kind in ("smooth", "noise", "shuffle"):
+        if kind == "smooth":
+            moved = base + d["flow"].to(DEV)
+        elif kind == "noise":
+            moved = base + 3.0 * torch.randn(base.shape, generator=g).to(DEV)
+        else:
+            moved = base[:, torch.randperm(8192, generator=g).to(DEV)].contiguous()
+        for k in (3, 32):
+            KF.clear_caches()
+            ref_a = KF.knn_idx(k, moved, other)                 # moved = candidates
+            ref_b = KF.knn_idx(k, other, moved)                 # moved = queries
+            KF.clear_caches()
+            KF._sorted_cloud(base)                              # the parent is sorted (as in the model)
+            KF.hint_displaced_copy(moved, base)
+            n0 = K_LAUNCHES()
+            got_a = KF.knn_idx(k, moved, other)
+            got_b = KF.knn_idx(k, other, moved)
+            assert torch.equal(got_a, ref_a) and torch.equal(got_b, ref_b), (kind, k)
+    KF.clear_caches()
+
+
+def K_LAUNCHES():
+    from kd_pointcloud_b200 import ops
+    return ops.LAUNCHES
+
+
 def test_build_csr_large_multi_part_and_skewed():
     """Model-size lists (8192 candidates x 32 selections, several CTAs per cloud), a skewed list (every entry selects
     one of 5 candidates: long segments) and candidates nobody selects."""
