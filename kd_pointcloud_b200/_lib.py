@@ -182,8 +182,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_pointconv_set_precompute.argtypes = [c_int]
         if os.environ.get("KDPC_PC_PRECOMPUTE", "1") == "0":
             L.kdpc_pointconv_set_precompute(0)
-        if os.environ.get("KDPC_TC_ASYNC", "1") == "0":
-            L.kdpc_tc_set_async(0)
+        if os.environ.get("KDPC_TC_ASYNC", "2") != "2":          # A/B switch: 0 = synchronous producers, 1 = cp.async rows (2 = tensor-map TMA rows, default)
+            L.kdpc_tc_set_async(int(os.environ["KDPC_TC_ASYNC"]))
         if os.environ.get("KDPC_FPS_CLUSTER", "1") != "1":       # A/B switch for measurements (0 = off, or a forced shape)
             L.kdpc_fps_set_cluster(int(os.environ["KDPC_FPS_CLUSTER"]))
         _lib = L

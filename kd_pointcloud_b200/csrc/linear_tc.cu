@@ -90,7 +90,37 @@ linear_simt_kernel(long long m, int n, int k, const float *__restrict__ x, int l
 using namespace kdpc;
 using namespace kdpc::tc;
 
-static int g_tc_async = 1;
+// cuTensorMapEncodeTiled through the runtime (no libcuda link dependency); nullptr when the driver lacks it
+typedef CUresult (*kdpc_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static kdpc_encode_tiled_fn tensor_map_encoder() {
+    static kdpc_encode_tiled_fn fn = nullptr;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<kdpc_encode_tiled_fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// [M, K] fp32 rows of pitch ldx: box = 32 columns x 128 rows, SWIZZLE_128B, out-of-range elements read as zero
+static bool make_row_tensor_map(CUtensorMap *tm, const float *x, long long m, int k, int ldx) {
+    kdpc_encode_tiled_fn enc = tensor_map_encoder();
+    if (enc == nullptr) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)m};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldx * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)PlainTmaProducer::BOX_COLS, (cuuint32_t)TILE_M};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_tc_async = 2;              // 0 = synchronous producers, 1 = cp.async (LDGSTS) rows, 2 = tensor-map TMA rows (default)
 KDPC_API int kdpc_tc_async_enabled(void) { return g_tc_async; }
 KDPC_API void kdpc_tc_set_async(int on) { g_tc_async = on; }
 static void *g_tc_trace = nullptr;
@@ -140,6 +170,25 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
         return KDPC_EINVAL;
     GemmShape g = make_shape(m, n, k, wpacked);
     if (ws != nullptr) plan_split_k(g);                      // small-M / large-K layers: spread K over idle SMs
+    if (g.splits == 1 && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled() == 2) {
+        // streaming layers, rows by 2-D tensor-map TMA: two UTMALDG per chunk from one thread
+        using P = PlainTmaProducer;
+        P::Args pa;
+        if (make_row_tensor_map(&pa.tmap, x, m, k, ldx)) {
+            pa.k = k;
+            for (int raw = P::kLookahead + 1; raw >= 2; --raw) {
+                GemmShape ga = make_shape(m, n, k, wpacked, P::kRawBytes, raw);
+                if (ga.stages < 2) continue;
+                const size_t smem_a = smem_bytes(ga.n_pad, ga.stages, ga.raw_bytes * ga.raw_stages);
+                auto kern_a = tc_gemm_kernel<P, StoreEpilogue>;
+                KDPC_ENSURE_SMEM(kern_a, SMEM_BUDGET + 1024);
+                StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
+                const unsigned grid = (unsigned)(ga.num_tiles < num_sms() ? ga.num_tiles : num_sms());
+                kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
+                KDPC_RETURN_LAST();
+            }
+        }
+    }
     if (g.splits == 1 && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled()) {
         // streaming layers: asynchronous row fetch, 2 raw buffers ahead if they fit next to 2 operand stages, else 1
         using P = PlainAsyncProducer;

@@ -15,6 +15,7 @@
 // Pipelines: smem stages (full_a/full_b/empty mbarriers) and two TMEM accumulator buffers
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
+#include <cuda.h>           // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "tc_common.cuh"
 
 // A/B switch (kdpc_tc_set_async): 0 = synchronous register-staged producers everywhere
@@ -151,7 +152,7 @@ __device__ __forceinline__ void work_item(long long w, int splits, long long &ti
 
 template <class Producer, class Epilogue>
 __global__ void __launch_bounds__(num_threads<Producer>(), 1)
-tc_gemm_kernel(const GemmShape g, const typename Producer::Args pa, const typename Epilogue::Args ea) {
+tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Args pa, const typename Epilogue::Args ea) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[4], tmem_empty[4];
@@ -776,6 +777,72 @@ struct PlainAsyncProducer {
             uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
             if (u < units) {
                 const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+                const float v[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                split8(v, hi, lo);
+            }
+            if (u <= units) {                                // unit == units: the zero half of an odd last 16-wide K-step
+                const uint32_t off = sw128_offset(r, u);
+                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+            }
+        }
+    }
+};
+
+
+// ------------------------------------------------------------------------------------------
+// Plain fp32 rows fetched by 2-D TENSOR-MAP TMA (cp.async.bulk.tensor.2d -> SASS UTMALDG): ONE elected thread issues two
+// box copies per 128 x 64 chunk (columns c0 .. c0+31 and c0+32 .. c0+63: a SWIZZLE_128B box is at most 128 bytes wide),
+// instead of 64 warp-level LDGSTS requests (~1100 cycles of load/store-unit time per chunk, tools/trace_linear.py) or
+// 128 per-row bulk copies (~2300 cycles of TMA issue).  Rows beyond M and columns beyond K are zero-filled by the TMA
+// unit; the boxes land densely (128 B per row, 16-byte units XOR-swizzled by row & 7 - the same pattern the operand
+// tiles use), so the converting threads read them conflict-free without padding.
+struct PlainTmaProducer {
+    static constexpr int kWarps = 8, kGroups = 1;
+    static constexpr bool kAsync = true;
+    static constexpr int kIssuerWarps = 0;
+    static constexpr int kIssuers = 1, kLookahead = 2;       // raw_full[]: the expect_tx arrival of producer thread 0
+    static constexpr int BOX_COLS = 32, BOX_BYTES = TILE_M * 128;
+    static constexpr int kRawBytes = 2 * BOX_BYTES;
+    struct alignas(64) Args {
+        CUtensorMap tmap;        // [M, K] fp32, row pitch ldx * 4 bytes, box 32 x 128, SWIZZLE_128B, zero fill
+        int k;
+    };
+    static __device__ __forceinline__ void prologue(const Args &a, int tid, int) {
+        if (tid == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.tmap)) : "memory");
+    }
+    const Args &a;
+    const GemmShape &g;
+    __device__ PlainTmaProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
+    __device__ __forceinline__ void prime(int, int) {}
+    static __device__ __forceinline__ void tma_box(void *smem_dst, const CUtensorMap *tm, int col, int row, uint64_t *bar) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(col), "r"(row) : "memory");
+    }
+    __device__ __forceinline__ void issue(int tile, int chunk, int /*next_tile*/, unsigned char *raw, uint64_t *bar, int ptid) {
+        if (ptid != 0) return;
+        const int c0 = chunk * CHUNK_K;
+        const int boxes = (a.k - c0 > BOX_COLS) ? 2 : 1;
+        mbar_expect_tx(bar, (uint32_t)(boxes * BOX_BYTES));
+        tma_box(raw, &a.tmap, c0, tile * TILE_M, bar);
+        if (boxes == 2) tma_box(raw + BOX_BYTES, &a.tmap, c0 + BOX_COLS, tile * TILE_M, bar);
+    }
+    __device__ __forceinline__ void convert(int /*tile*/, int chunk, const unsigned char *raw, unsigned char *a_hi,
+                                            unsigned char *a_lo, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7;
+        const int units = min(8, (a.k - chunk * CHUNK_K) >> 3);          // k % 8 == 0
+        const unsigned char *row = raw + r * 128;
+        const int sw = r & 7;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+            const int u = half * 4 + uu;
+            uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+            if (u < units) {
+                const unsigned char *box = row + (u >> 2) * BOX_BYTES;   // unit u = floats 8u .. 8u+7 = pieces 2u, 2u+1 of its box
+                const int p0 = (2 * u) & 7;
+                const float4 g0 = *reinterpret_cast<const float4 *>(box + ((p0 ^ sw) << 4));
+                const float4 g1 = *reinterpret_cast<const float4 *>(box + (((p0 + 1) ^ sw) << 4));
                 const float v[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                 split8(v, hi, lo);
             }
