@@ -208,26 +208,33 @@ struct PointConvProducer {
 
     // one K-chunk (4 feature channels x this thread's 8 WeightNet outputs) from the gathered channels v[k]
     __device__ __forceinline__ void chunk_from(const float4 (&v)[NB], unsigned char *a_hi, int r) const {
-        float acc[4][8];
+        // packed fp32 FMAs (fma.rn.f32x2 -> SASS FFMA2): a 3-register FFMA issues every other cycle per sub-partition,
+        // FFMA2 does two per issue; each half is an IEEE fma, so the sums are bit-identical to the scalar loop
+        float2 acc2[4][4];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[ch][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc2[ch][j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
+            const float2 vx = make_float2(v[k].x, v[k].x), vy = make_float2(v[k].y, v[k].y);
+            const float2 vz = make_float2(v[k].z, v[k].z), vw = make_float2(v[k].w, v[k].w);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[0][j] = fmaf(v[k].x, wn[k][j], acc[0][j]);
-                acc[1][j] = fmaf(v[k].y, wn[k][j], acc[1][j]);
-                acc[2][j] = fmaf(v[k].z, wn[k][j], acc[2][j]);
-                acc[3][j] = fmaf(v[k].w, wn[k][j], acc[3][j]);
+            for (int j = 0; j < 4; ++j) {
+                const float2 w2 = make_float2(wn[k][2 * j], wn[k][2 * j + 1]);
+                acc2[0][j] = __ffma2_rn(vx, w2, acc2[0][j]);
+                acc2[1][j] = __ffma2_rn(vy, w2, acc2[1][j]);
+                acc2[2][j] = __ffma2_rn(vz, w2, acc2[2][j]);
+                acc2[3][j] = __ffma2_rn(vw, w2, acc2[3][j]);
             }
         }
         unsigned char *a_lo = a_hi + A_PART_BYTES;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             uint4 hi, lo;
-            split8(acc[ch], hi, lo);
+            const float acc[8] = {acc2[ch][0].x, acc2[ch][0].y, acc2[ch][1].x, acc2[ch][1].y,
+                                  acc2[ch][2].x, acc2[ch][2].y, acc2[ch][3].x, acc2[ch][3].y};
+            split8(acc, hi, lo);
             const uint32_t off = sw128_offset(r, ch * 2 + half);
             *reinterpret_cast<uint4 *>(a_hi + off) = hi;
             *reinterpret_cast<uint4 *>(a_lo + off) = lo;

@@ -515,10 +515,27 @@ struct StoreEpilogue {
         // rows, no residual.  Branch-free and fully unrolled: the generic path below carries a 64-bit division, eight
         // predicated scalar scale/shift loads and ~10 branches per row group and cost ~2700 cycles per 32 x 32 block
         // (tools/trace_linear.py: the epilogue, not HBM, paced the streaming layers at 26-34 % of the copy peak).
-        if (!partial && e.row_order == nullptr && e.residual == nullptr && vec && (g.n & 3) == 0 && row0 + 32 <= g.m &&
-            ((reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.shift)) & 15) == 0) {
+        if (!partial && (e.row_order == nullptr || e.rows_per_cloud >= 32) && e.residual == nullptr && vec && (g.n & 3) == 0 &&
+            row0 + 32 <= g.m && ((reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.shift)) & 15) == 0) {
             const bool clampd = e.lo <= e.hi;
-            float *orow = e.out + (row0 + rsub) * (long long)ld + c4;
+            // destination of this lane's 8 rows (i * 4 + rsub): plain order, or through the row order (the fused PointConv
+            // processes its rows in Morton order; one division per block, the block may straddle one cloud boundary)
+            float *orow[8];
+            if (e.row_order == nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) orow[i] = e.out + (row0 + rsub + i * 4) * (long long)ld + c4;
+            } else {
+                const long long b0 = (long long)((unsigned)row0 / (unsigned)e.rows_per_cloud);   // rows < 2^31 (launcher shapes)
+                const int p0 = (int)(row0 - b0 * e.rows_per_cloud) + rsub;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int pp = p0 + i * 4;
+                    long long b = b0;
+                    if (pp >= e.rows_per_cloud) { pp -= e.rows_per_cloud; ++b; }
+                    const long long row = b * e.rows_per_cloud + __ldg(e.row_order + b * e.order_stride + pp);
+                    orow[i] = e.out + row * (long long)ld + c4;
+                }
+            }
             for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
                 const int col = c0 + c4;
                 const bool live = col < g.n;                      // (n % 4 == 0: a lane's 4 columns are all in or all out)
@@ -545,7 +562,7 @@ struct StoreEpilogue {
                             y.x = fminf(fmaxf(y.x, e.lo), e.hi); y.y = fminf(fmaxf(y.y, e.lo), e.hi);
                             y.z = fminf(fmaxf(y.z, e.lo), e.hi); y.w = fminf(fmaxf(y.w, e.lo), e.hi);
                         }
-                        *reinterpret_cast<float4 *>(orow + (long long)(i * 4) * ld + c0) = y;
+                        *reinterpret_cast<float4 *>(orow[i] + c0) = y;
                     }
                 }
             }
