@@ -274,6 +274,9 @@ int kdpc_spatial_sort_order_stride(int n);
  * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out].
  * ws: kdpc_costvol_fused_ws_bytes(b,s,n,d) bytes (16-byte aligned) for the per-point features with the positional
  * encoding folded in; NULL selects the variant that evaluates the encoding per neighbour (no workspace). */
+/* Cost volume at the 8192-point level (d = 32, 16 < d_out <= 32): two 128-row tiles per pipeline iteration against the
+ * block-diagonal weight diag(W, W) (default 1); 0 = one tile per iteration at every level.  Same results. */
+void kdpc_costvol_set_pairing(int on);
 long long kdpc_costvol_fused_ws_bytes(int b, int s, int n, int d);
 int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float *xyz1, const float *xyz2,
                        const float *p1, const float *p2, const int *idx, const float *pos_w,

@@ -132,6 +132,7 @@ struct CostVolAsyncProducer {
         const int *idx;      // [B,S,32]
         int s, n, d;
         float slope;
+        long long points;    // B * S (the paired producer's row bound; its GemmShape counts 128-row iterations)
     };
     static __device__ __forceinline__ void prologue(const Args &, int, int) {}
     const Args &a;
@@ -243,6 +244,115 @@ struct CostVolAsyncProducer {
     }
 };
 
+// PAIRED variant for the 8192-point level (D = 32, D' <= 32).  A 128-row x K=32 tile is too little work per pipeline
+// iteration: tools/trace_costvol.py shows the single MMA warp's per-iteration control path (three mbarrier waits, the
+// fence, descriptors, two commits: ~1750 cycles) pacing the kernel while the tensor pipe is ~5 % busy.  So one
+// iteration carries TWO row tiles (8 points): the A stage row r holds [tile 0 row r, channels 0..31 | tile 1 row r,
+// channels 0..31] (K' = 64) and the weight is the block-diagonal 64 x 64 matrix diag(W, W) (costvol_pair_weight_kernel),
+// so the accumulator's columns 0..31 are tile 0's outputs and columns 32..63 tile 1's.  The tensor pipe multiplies the
+// two zero blocks as well (it has the time); waits, commits, barriers and loop overhead are paid once per 256 rows by
+// every role, and EIGHT epilogue warps (two per TMEM lane quarter, one per column half) keep the max-over-K off the
+// critical path.  126 -> 101-105 us at B = 8 x 8192 points, bit-identical.  What paces it now is the load/store unit: 66
+// warp-level LDGSTS per iteration (~28 cycles each) plus the conversion's LDS/STS (tools/trace_costvol.py).
+// Measured and rejected for the gathers (tools/gather4_probe.cu, same box): cp.async.bulk.tensor tile::gather4 (one
+// TMA request per 4 rows) - the TMA unit takes ~150 cycles per request, 5x the LDGSTS cost per row; plain LDG.128 ->
+// registers -> STS.128 from the issuer warps - halves the conversion time (no LDGSTS in the LSU queue) but one
+// iteration of loads in flight per warp cannot cover the L2 latency (158 us); 8 issuer warps instead of 4: -4 %.
+struct CostVolPairProducer {
+    static constexpr int kWarps = 8, kGroups = 1;
+    static constexpr bool kAsync = true;
+#ifndef KDPC_CV_PAIR_IW
+#define KDPC_CV_PAIR_IW 4
+#endif
+    static constexpr int kIssuerWarps = KDPC_CV_PAIR_IW, kEpilogueWarps = 8;
+    static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
+    static constexpr int D = 32;
+    static constexpr int ROWS = 2 * TILE_M, PTS = ROWS / CV_K;           // 256 neighbour rows = 8 points per iteration
+    static constexpr int ROW_PITCH = 144;                                // 128 B payload + 16 B: conflict-free 16-byte reads by row
+    static constexpr int kRawBytes = (ROWS + PTS) * ROW_PITCH;
+    static constexpr int RPT = ROWS * 8 / kIssuers;                      // neighbour rows per issuing thread (8 lanes per row)
+    static constexpr int RSTEP = kIssuers / 8;                           // thread t serves rows (t >> 3) + RSTEP j
+    static constexpr int JPP = CV_K / RSTEP;                             // consecutive j that belong to one point
+    using Args = CostVolAsyncProducer::Args;
+    static __device__ __forceinline__ void prologue(const Args &, int, int) {}
+    const Args &a;
+    const GemmShape &g;
+    uint32_t roff[RPT];           // element offset into p2q of the neighbour row that lands in rows (t >> 3) + RSTEP j of the NEXT issued iteration
+    uint32_t pt_off;              // element offset into p1q of the point row this thread copies a piece of (threads < 64)
+    uint32_t dst0;
+    uint32_t last_pt, last_row;
+
+    __device__ CostVolPairProducer(const Args &a_, const GemmShape &g_) : a(a_), g(g_) {}
+
+    // g.m = 128 x iterations ("virtual" rows); the real row count is points * 32 with points = a.points
+    __device__ __forceinline__ void load_rows(int tile, int ptid) {
+        const unsigned s = (unsigned)a.s, pt0 = (unsigned)tile * PTS;
+        const unsigned b0 = pt0 / s, left = (b0 + 1u) * s - pt0;  // points of the iteration before the next cloud starts
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {                           // row (t >> 3) + RSTEP j belongs to point pt0 + j / JPP
+            const unsigned jj = min((unsigned)(j / JPP), last_pt - pt0);   // (rows past the end repeat the last point's last row)
+            const unsigned b = b0 + (jj >= left ? (jj - left) / s + 1u : 0u);
+            const unsigned row = pt0 * CV_K + (unsigned)((ptid >> 3) + RSTEP * j);
+            roff[j] = (b * (unsigned)a.n + (unsigned)__ldg(a.idx + min(row, last_row))) * (unsigned)D;
+        }
+        const unsigned pt = min(pt0 + (unsigned)((ptid >> 3) & 7), last_pt);
+        pt_off = pt * (unsigned)D;
+    }
+    __device__ __forceinline__ void prime(int tile, int ptid) {
+        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + (ptid & 7) * 16);
+        last_pt = (unsigned)a.points - 1u;
+        last_row = (unsigned)a.points * CV_K - 1u;
+        load_rows(tile, ptid);
+    }
+    __device__ __forceinline__ void issue(int /*tile*/, int /*chunk*/, int next_tile, unsigned char *raw, uint64_t *bar, int ptid) {
+        const float *src = a.p2q + (ptid & 7) * 4;
+        const uint32_t dst = smem_u32(raw) + dst0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j)
+            cp_async_16(dst + j * (RSTEP * ROW_PITCH), src + roff[j]);
+        if (ptid < 8 * PTS)                                       // the 8 points' own rows: 8 pieces each
+            cp_async_16(smem_u32(raw + (ROWS + (ptid >> 3)) * ROW_PITCH) + (ptid & 7) * 16, a.p1q + pt_off + (ptid & 7) * 4);
+        cp_async_mbar_arrive(bar);
+        if (next_tile >= 0) load_rows(next_tile, ptid);
+    }
+    // thread (r, half): row r of row tile `half`, all 32 channels -> units 4 half .. 4 half + 3 of stage row r
+    __device__ __forceinline__ void convert(int /*tile*/, int /*chunk*/, const unsigned char *raw, unsigned char *a_hi,
+                                            unsigned char *a_lo, int ptid) {
+        const int r = ptid & 127, half = ptid >> 7;
+        const float4 *rr = reinterpret_cast<const float4 *>(raw + (half * TILE_M + r) * ROW_PITCH);
+        const float4 *pr = reinterpret_cast<const float4 *>(raw + (ROWS + half * (TILE_M / CV_K) + (r >> 5)) * ROW_PITCH);   // same for the warp
+        const float slope = a.slope;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+            const float4 q0 = pr[2 * u], q1 = pr[2 * u + 1];
+            float v[8] = {g0.x + q0.x, g0.y + q0.y, g0.z + q0.z, g0.w + q0.w,
+                          g1.x + q1.x, g1.y + q1.y, g1.z + q1.z, g1.w + q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], v[e] * slope);          // leaky / ReLU (0 <= slope < 1)
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t off = sw128_offset(r, half * 4 + u);
+            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+        }
+    }
+};
+
+// diag(W, W) in the packed layout (one chunk, n_pad = 64) from the packed W (one chunk, n_pad_src = 32 or 16):
+// rows 0..31 keep W's units 0..3, rows 32..63 carry them as units 4..7, everything else is zero
+__global__ void __launch_bounds__(256)
+costvol_pair_weight_kernel(int n_pad_src, const unsigned char *__restrict__ src, unsigned char *__restrict__ dst) {
+    const int t = threadIdx.x + blockIdx.x * blockDim.x;           // (part, row, unit): 2 x 64 x 8
+    if (t >= 2 * 64 * 8) return;
+    const int u = t & 7, row = (t >> 3) & 63, part = t >> 9;
+    const int srow = row & 31, su = row < 32 ? u : u - 4;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (su >= 0 && su < 4 && srow < n_pad_src)
+        v = *reinterpret_cast<const uint4 *>(src + (size_t)part * n_pad_src * 128 + sw128_offset(srow, su));
+    *reinterpret_cast<uint4 *>(dst + (size_t)part * 64 * 128 + sw128_offset(row, u)) = v;
+}
+
 // p2q = points2 + pos_w xyz2 (sign = +1, no bias);  p1q = points1 + pos_b - pos_w xyz1 (sign = -1, with bias)
 __global__ void __launch_bounds__(256)
 costvol_prep_kernel(long long rows1, long long rows2, int dvec, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
@@ -282,9 +392,15 @@ struct MaxKEpilogue {
         float *out;           // [points, ldo]
         int ldo;
         long long points;
+        int pair_n;           // 0, or D' of the paired layout: accumulator columns 32 h .. 32 h + D' - 1 = row tile h of the iteration
     };
     __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int /*split*/, uint32_t t_acc,
                                          int quarter, int lane) const {
+        if (e.pair_n > 0) {                                       // eight warps: (quarter & 3) = point of the row tile, quarter >> 2 = row tile
+            const int h = quarter >> 2;
+            pair_tile(e, tile * (2 * TILE_M / CV_K) + h * (TILE_M / CV_K) + (quarter & 3), t_acc + (uint32_t)(32 * h), lane);
+            return;
+        }
         const long long pt = tile * (TILE_M / CV_K) + quarter;
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
@@ -316,6 +432,30 @@ struct MaxKEpilogue {
             }
         }
     }
+    // one point's 32 neighbours x (up to) 32 channels at t_acc: same transpose-reduce
+    __device__ __forceinline__ void pair_tile(const Args &e, long long pt, uint32_t t_acc, int lane) const {
+        float v[32];
+        tmem_ld_32x32(t_acc, v);
+        int w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = f2ord(v[j]);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int j = 0; j < m; ++j) {
+                const int keep = up ? w[j + m] : w[j];
+                const int give = up ? w[j] : w[j + m];
+                w[j] = max(keep, __shfl_xor_sync(0xffffffffu, give, m));
+            }
+        }
+        if (pt < e.points && lane < e.pair_n) {
+            float y = ord2f(w[0]);
+            if (e.bias) y += __ldg(e.bias + lane);
+            y = y > 0.f ? y : y * e.slope;
+            e.out[pt * e.ldo + lane] = y;
+        }
+    }
 };
 
 }  // namespace tc
@@ -324,9 +464,13 @@ struct MaxKEpilogue {
 using namespace kdpc;
 using namespace kdpc::tc;
 
+static int kdpc_costvol_pairing = 1;
+/* A/B switch for measurements: 0 = one 128-row tile per pipeline iteration at every level (same results) */
+KDPC_API void kdpc_costvol_set_pairing(int on) { kdpc_costvol_pairing = on; }
+
 KDPC_API long long kdpc_costvol_fused_ws_bytes(int b, int s, int n, int d) {
     if (b <= 0 || s <= 0 || n <= 0 || d <= 0) return 0;
-    return ((long long)b * s + (long long)b * n) * d * 4;
+    return ((long long)b * s + (long long)b * n) * d * 4 + 2 * 64 * 128;     // p1q, p2q, the paired layout's diag(W, W)
 }
 
 KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, const float *xyz1, const float *xyz2,
@@ -341,7 +485,32 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
                          reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(pos_b);
     if (al % 16 != 0) return KDPC_EINVAL;
     const long long points = (long long)b * s;
-    MaxKEpilogue::Args ea{bias, slope_post, out, d_out, points};
+    MaxKEpilogue::Args ea{bias, slope_post, out, d_out, points, 0};
+    if (ws != nullptr && slope_pre >= 0.f && slope_pre < 1.f && kdpc_tc_async_enabled() && kdpc_costvol_pairing &&
+        d == CostVolPairProducer::D && d_out > 16 && d_out <= 32 && points >= 4096) {
+        // 8192-point level: two row tiles per pipeline iteration against diag(W, W)
+        using P = CostVolPairProducer;
+        const long long iters = (points + P::PTS - 1) / P::PTS;
+        float *p1q = reinterpret_cast<float *>(ws);
+        float *p2q = p1q + points * d;
+        unsigned char *w2 = reinterpret_cast<unsigned char *>(p2q + (long long)b * n * d);
+        GemmShape g = make_shape(iters * TILE_M, 32 + d_out, 2 * d, w2, P::kRawBytes, P::kLookahead + 1);
+        g.stages = 2;             // 2 x 48 KB of operand stages + 3 x 37 KB of staging: 212 KB (nothing here lives on L1 hits)
+        if (g.n_pad == 64) {
+            const long long total = (points + (long long)b * n) * (d / 4);
+            costvol_prep_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
+                points, (long long)b * n, d / 4, xyz1, xyz2, p1, p2, pos_w, pos_b, p1q, p2q);
+            costvol_pair_weight_kernel<<<4, 256, 0, to_stream(stream)>>>((d_out + 15) / 16 * 16, reinterpret_cast<const unsigned char *>(wpacked), w2);
+            P::Args pa{p1q, p2q, idx, s, n, d, slope_pre, points};
+            ea.pair_n = d_out;
+            const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
+            auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
+            KDPC_ENSURE_SMEM(kern, 216 * 1024);
+            const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
+            kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
+            KDPC_RETURN_LAST();
+        }
+    }
     if (ws != nullptr && slope_pre >= 0.f && slope_pre < 1.f && kdpc_tc_async_enabled()) {
         // asynchronous producer whenever its raw staging fits next to >= 2 operand stages
         using P = CostVolAsyncProducer;
@@ -353,7 +522,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
             const long long total = (points + (long long)b * n) * (d / 4);
             costvol_prep_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
                 points, (long long)b * n, d / 4, xyz1, xyz2, p1, p2, pos_w, pos_b, p1q, p2q);
-            P::Args pa{p1q, p2q, idx, s, n, d, slope_pre};
+            P::Args pa{p1q, p2q, idx, s, n, d, slope_pre, points};
             const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
             auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
             KDPC_ENSURE_SMEM(kern, SMEM_BUDGET + 1024);

@@ -37,7 +37,9 @@ namespace tc {
 //     interleaved into the FFMA loop): never faster - a warp-level LDGSTS whose lanes touch 16 lines blocks the
 //     issuing warp for ~150 cycles, and the 74 KB of staging take the L1 away;
 //   * software pipelining (chunk c+1's loads issued after chunk c's FFMAs, stage acquired after the FFMAs): 5 %
-//     slower, the extra live registers spill in the WeightNet phase;
+//     slower, the extra live registers spill in the WeightNet phase; refilling neighbour k's registers with the next
+//     pair's gather right after their last shuffle (no extra live registers on paper): ptxas hoists the loads and
+//     spills inside the loop (34 LDL per pair), 206 -> 243 us;
 //   * prefetch.global.L1 of every neighbour row's next 128-byte line two to six chunks ahead: 5 % slower;
 //   * 4 threads per row (16 producer warps at 96 registers, wn[9][4] each) for more latency hiding: 15 % slower - the
 //     kernel is bound by L1 line accesses (every warp request touches 16 neighbour rows = 16 wavefronts, 1152 per

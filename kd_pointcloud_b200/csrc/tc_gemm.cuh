@@ -43,8 +43,12 @@ template <class P> struct owns_loop<P, decltype((void)P::kOwnsLoop)> { static co
 // (kIssuers = 32 * kIssuerWarps) and raw_empty[] hands a staging slot back (one arrival per converting warp).
 template <class P, class = void> struct issuer_warps { static constexpr int value = 0; };
 template <class P> struct issuer_warps<P, decltype((void)P::kIssuerWarps)> { static constexpr int value = P::kIssuerWarps; };
+// Producers that declare kEpilogueWarps = 8 get two epilogue warps per TMEM lane quarter (the second four receive
+// quarter + 4 and work on their own column range of the accumulator): for tiles whose epilogue, not the MMA, paces the pipeline.
+template <class P, class = void> struct epilogue_warps { static constexpr int value = 4; };
+template <class P> struct epilogue_warps<P, decltype((void)P::kEpilogueWarps)> { static constexpr int value = P::kEpilogueWarps; };
 template <class Producer> constexpr int num_threads() {
-    return (Producer::kWarps + issuer_warps<Producer>::value + (merged_issuer<Producer>::value ? 4 : 5)) * 32;
+    return (Producer::kWarps + issuer_warps<Producer>::value + (merged_issuer<Producer>::value ? 0 : 1) + epilogue_warps<Producer>::value) * 32;
 }
 
 struct GemmShape {
@@ -163,6 +167,8 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
     constexpr bool MG = merged_issuer<Producer>::value;                      // warp PW = issuer AND epilogue of quarter 0
     constexpr int IW = issuer_warps<Producer>::value;                        // dedicated gather-issue warps PW..PW+IW-1
     constexpr int MW = PW + IW;                                              // the MMA issuer warp (epilogue warps follow)
+    constexpr int EW = epilogue_warps<Producer>::value;                      // 4, or 8 (two per TMEM lane quarter)
+    static_assert(EW == 4 || (EW == 8 && !MG), "epilogue warps: 4, or 8 without a merged issuer");
     static_assert(IW == 0 || (Producer::kAsync && !MG && ((MW + 1) & 3) == 1), "issuer warps: async producers, epilogue quarters 1,2,3,0");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
@@ -185,7 +191,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             }   // arrive.expect_tx per issuing thread
         for (int a = 0; a < 4; ++a) {
             mbar_init(&tmem_full[a], 1);     // tcgen05.commit
-            mbar_init(&tmem_empty[a], 4);    // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], EW);   // one arrive per epilogue warp
         }
         mbar_fence_init();
     }
@@ -451,13 +457,13 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             int split_;
             work_item(w, g.splits, tile, split_);
             const uint32_t acc = tcount & nacc_mask;
-            const bool tre = g.trace != nullptr && blockIdx.x == 0 && quarter == 1 && lane == 0 && tcount < 200;
+            const bool tre = g.trace != nullptr && blockIdx.x == 0 && warp == MW + 1 && lane == 0 && tcount < 200;
             if (tre) g.trace[tcount * 16 + 12] = clock64();
             mbar_wait(&tmem_full[acc], (tcount >> g.nacc_log2) & 1);
             if (tre) g.trace[tcount * 16 + 13] = clock64();
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
-            epi.tile(ea, g, tile, split_, t_acc, quarter, lane);
+            epi.tile(ea, g, tile, split_, t_acc, EW > 4 ? quarter + 4 * ((warp - MW - 1) >> 2) : quarter, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

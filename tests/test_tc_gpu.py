@@ -150,7 +150,8 @@ def test_pointconv_fused_matches_fp64(B, N, S, D, Cout, KN):
 
 
 @pytest.mark.parametrize("B,N1,N2,D", [(2, 1024, 1024, 32), (1, 333, 500, 64), (2, 256, 256, 256), (1, 8192, 8192, 32),
-                                        (1, 2048, 2048, 128), (3, 333, 500, 32), (5, 3, 40, 64), (2, 130, 64, 128)])
+                                        (1, 2048, 2048, 128), (3, 333, 500, 32), (5, 3, 40, 64), (2, 130, 64, 128),
+                                        (3, 1367, 1500, 32), (2, 4099, 4100, 32)])
 def test_costvol_fused_matches_fp64(B, N1, N2, D):
     torch.manual_seed(N1 + D)
     xyz1 = torch.rand(B, N1, 3, device=DEV) * 4
@@ -170,6 +171,14 @@ def test_costvol_fused_matches_fp64(B, N1, N2, D):
     assert y.shape == (B, N1, D)
     assert _err(y, ref) < 2e-5
     assert torch.equal(y, K.costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, 0.1, wp, D, b, 0.1))
+    # two row tiles per pipeline iteration against diag(W, W) (D = 32, >= 4096 points) == one tile per iteration, bit for bit
+    from kd_pointcloud_b200 import _lib
+    _lib.lib().kdpc_costvol_set_pairing(0)
+    try:
+        single = K.costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, 0.1, wp, D, b, 0.1)
+    finally:
+        _lib.lib().kdpc_costvol_set_pairing(1)
+    assert torch.equal(y, single)
 
 
 def test_fused_layers_match_unfused_modules():
