@@ -206,6 +206,9 @@ long long kdpc_packed_weight_bytes(int n, int k_packed);
 /* The fused tcgen05 layers stage their gathers asynchronously (bulk copies two pipeline iterations ahead);
  * kdpc_tc_set_async(0) selects the synchronous register-staged producers (same results; A/B measurements). */
 void kdpc_tc_set_async(int on);
+/* Small-M layers (<= half the SMs in 128-row tiles) with >= 128 outputs: work items are column blocks over the whole K
+ * (default 1: final results from the epilogue, no workspace); 0 = split-K + reduce as for the narrow layers. */
+void kdpc_linear_set_split_n(int on);
 /* debug (tools/trace_pointconv.py, tools/trace_costvol.py): while a device buffer of 200 x 16 int64 is set, CTA 0 of every
  * tcgen05 kernel writes per-iteration clock64 stamps of its producer, MMA and epilogue warps into it; NULL = off */
 void kdpc_tc_set_trace(void *device_buffer);

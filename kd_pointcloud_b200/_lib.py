@@ -184,6 +184,10 @@ def lib() -> ctypes.CDLL:
             L.kdpc_pointconv_set_precompute(0)
         if os.environ.get("KDPC_TC_ASYNC", "2") != "2":          # A/B switch: 0 = synchronous producers, 1 = cp.async rows (2 = tensor-map TMA rows, default)
             L.kdpc_tc_set_async(int(os.environ["KDPC_TC_ASYNC"]))
+        L.kdpc_linear_set_split_n.restype = None
+        L.kdpc_linear_set_split_n.argtypes = [c_int]
+        if os.environ.get("KDPC_SPLIT_N", "1") == "0":           # A/B switch for measurements
+            L.kdpc_linear_set_split_n(0)
         L.kdpc_costvol_set_pairing.restype = None
         L.kdpc_costvol_set_pairing.argtypes = [c_int]
         if os.environ.get("KDPC_CV_PAIR", "1") == "0":           # A/B switch for measurements
@@ -198,7 +202,7 @@ def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_set_sm_limit", "kdpc_sm_limit", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
             "kdpc_loss_workspace_bytes", "kdpc_linear_dw_ws_bytes", "kdpc_weightnet_grad_ws_bytes", "kdpc_dataprep_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
-            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing"] + list(_SIGNATURES)
+            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -120,9 +120,12 @@ static bool make_row_tensor_map(CUtensorMap *tm, const float *x, long long m, in
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int kdpc_linear_split_n = 1;
 static int g_tc_async = 2;              // 0 = synchronous producers, 1 = cp.async (LDGSTS) rows, 2 = tensor-map TMA rows (default)
 KDPC_API int kdpc_tc_async_enabled(void) { return g_tc_async; }
 KDPC_API void kdpc_tc_set_async(int on) { g_tc_async = on; }
+/* A/B switch for measurements: 0 = small-M layers always by split-K + reduce (results differ in the last bits: other summation order) */
+KDPC_API void kdpc_linear_set_split_n(int on) { kdpc_linear_split_n = on; }
 static void *g_tc_trace = nullptr;
 KDPC_API void *kdpc_tc_trace_buffer(void) { return g_tc_trace; }
 /* debug (tools/trace_*.py): every tcgen05 kernel launched while a buffer is set writes CTA 0's per-iteration clock64
@@ -156,7 +159,7 @@ KDPC_API int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const f
 KDPC_API long long kdpc_linear_tc_ws_bytes(long long m, int n, int k) {
     if (m <= 0 || n <= 0 || n > 256 || k <= 0) return 0;
     GemmShape g = make_shape(m, n, k, nullptr);
-    plan_split_k(g);
+    if (!(kdpc_linear_split_n && plan_split_n(g))) plan_split_k(g);
     return (long long)split_k_ws_bytes(g);
 }
 
@@ -169,7 +172,8 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
         (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0 || (reinterpret_cast<uintptr_t>(ws) % 16) != 0)
         return KDPC_EINVAL;
     GemmShape g = make_shape(m, n, k, wpacked);
-    if (ws != nullptr) plan_split_k(g);                      // small-M / large-K layers: spread K over idle SMs
+    // small-M layers: column blocks over idle SMs when there are >= 128 outputs, else (large K) split-K
+    if (!(kdpc_linear_split_n && plan_split_n(g)) && ws != nullptr) plan_split_k(g);
     if (g.splits == 1 && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled() == 2) {
         // streaming layers, rows by 2-D tensor-map TMA: two UTMALDG per chunk from one thread
         using P = PlainTmaProducer;
@@ -213,7 +217,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
     const long long work = g.num_tiles * g.splits;
     const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
     kern<<<grid, num_threads<PlainProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
-    if (g.splits > 1) return launch_splitk_reduce(g, ea, to_stream(stream));
+    if (g.splits > 1 && !g.nsplit) return launch_splitk_reduce(g, ea, to_stream(stream));
     KDPC_RETURN_LAST();
 }
 

@@ -177,6 +177,107 @@ pointconv_agg_grad_kernel(long long rows, int k, int c, const float *__restrict_
     }
 }
 
+
+// The same backward with ONE WARP per point and channel blocks of 64 (k <= 16): the CTA-per-point kernel above keeps
+// k x 16 partial sums per thread (248 registers: two CTAs = 8 warps per SM, every CTA a short latency chain, half its
+// threads idle in the second pass over c = 131 channels) and ran 10x above both its HBM and its FMA bound (1.9 ms for
+// 65536 x 9 x 131).  Here, per block of 64 channels:
+//   phase 1  lane = channel (two per lane): its 64-byte slice g[r,c,:] goes to registers (fully coalesced across the
+//            warp) and to shared memory, grouped[r,:,c] to shared memory; g_grouped[r,kk,c] = <wn[r,kk,:], g[r,c,:]> with
+//            the wn rows broadcast from shared memory;
+//   phase 2  lane = (w, kk parity): g_wn[r,kk,w] += sum_c grouped[r,kk,c] * g[r,c,w] from shared memory, one
+//            accumulator per (kk, w) walking c in ascending order (deterministic, no cross-lane reduction at all).
+// 80-112 registers, 4 warps and 33-40 KB of shared memory per CTA: 5-6 CTAs per SM.
+constexpr int AGW_WARPS = 4, AGW_CB = 64, AGW_GP = 20;        // g rows padded to 20 floats: conflict-free 16-byte accesses by row
+
+template <int KH>                                             // k <= 2 * KH
+__global__ void __launch_bounds__(AGW_WARPS * 32)
+pointconv_agg_grad_warp_kernel(long long rows, int k, int c, const float *__restrict__ grouped, const float *__restrict__ wn,
+                               const float *__restrict__ g, float *__restrict__ g_grouped, float *__restrict__ g_wn) {
+    __shared__ __align__(16) float s_g[AGW_WARPS][AGW_CB * AGW_GP];
+    __shared__ __align__(16) float s_x[AGW_WARPS][2 * KH * AGW_CB];
+    __shared__ __align__(16) float s_w[AGW_WARPS][2 * KH * 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * AGW_WARPS + warp;
+    if (r >= rows) return;                                    // (warps never meet at a CTA barrier)
+    float *sg = s_g[warp], *sx = s_x[warp], *sw = s_w[warp];
+    {
+        const float4 *w4 = reinterpret_cast<const float4 *>(wn + r * (long long)k * 16);
+        for (int i = lane; i < k * 4; i += 32) reinterpret_cast<float4 *>(sw)[i] = __ldg(w4 + i);
+    }
+    __syncwarp();
+    const int w = lane & 15, kh = lane >> 4;
+    float acc[KH];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) acc[i] = 0.f;
+    const float *xrow = grouped + r * (long long)k * c;
+    float *orow = g_grouped != nullptr ? g_grouped + r * (long long)k * c : nullptr;
+    for (int c0 = 0; c0 < c; c0 += AGW_CB) {
+        const int nv = min(AGW_CB, c - c0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cl = lane + 32 * h;
+            float4 *sgr = reinterpret_cast<float4 *>(sg + cl * AGW_GP);
+            if (cl < nv) {
+                const float4 *gp = reinterpret_cast<const float4 *>(g + (r * (long long)c + c0 + cl) * 16);
+                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
+                sgr[0] = g0; sgr[1] = g1; sgr[2] = g2; sgr[3] = g3;
+                if (g_wn != nullptr) {
+                    float xr[2 * KH];
+#pragma unroll
+                    for (int kk = 0; kk < 2 * KH; ++kk) xr[kk] = kk < k ? __ldg(xrow + (size_t)kk * c + c0 + cl) : 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < 2 * KH; ++kk)
+                        if (kk < k) sx[kk * AGW_CB + cl] = xr[kk];
+                }
+                if (orow != nullptr) {
+                    const float2 ga[8] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w),
+                                          make_float2(g2.x, g2.y), make_float2(g2.z, g2.w), make_float2(g3.x, g3.y), make_float2(g3.z, g3.w)};
+                    for (int kk = 0; kk < k; ++kk) {
+                        const float4 *wr = reinterpret_cast<const float4 *>(sw + kk * 16);
+                        const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+                        float2 a = make_float2(0.f, 0.f);       // even / odd w, added at the end (packed fp32 FMAs)
+                        a = __ffma2_rn(make_float2(w0.x, w0.y), ga[0], a); a = __ffma2_rn(make_float2(w0.z, w0.w), ga[1], a);
+                        a = __ffma2_rn(make_float2(w1.x, w1.y), ga[2], a); a = __ffma2_rn(make_float2(w1.z, w1.w), ga[3], a);
+                        a = __ffma2_rn(make_float2(w2.x, w2.y), ga[4], a); a = __ffma2_rn(make_float2(w2.z, w2.w), ga[5], a);
+                        a = __ffma2_rn(make_float2(w3.x, w3.y), ga[6], a); a = __ffma2_rn(make_float2(w3.z, w3.w), ga[7], a);
+                        orow[(size_t)kk * c + c0 + cl] = a.x + a.y;
+                    }
+                }
+            } else if (g_wn != nullptr && cl < ((nv + 3) & ~3)) {     // zero padding up to the next multiple of 4 channels (phase 2 walks by 4)
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                sgr[0] = z; sgr[1] = z; sgr[2] = z; sgr[3] = z;
+                for (int kk = 0; kk < k; ++kk) sx[kk * AGW_CB + cl] = 0.f;
+            }
+        }
+        if (g_wn == nullptr) continue;
+        __syncwarp();
+        for (int cc = 0; cc < nv; cc += 4) {
+            const float gv0 = sg[(cc + 0) * AGW_GP + w], gv1 = sg[(cc + 1) * AGW_GP + w];
+            const float gv2 = sg[(cc + 2) * AGW_GP + w], gv3 = sg[(cc + 3) * AGW_GP + w];
+#pragma unroll
+            for (int i = 0; i < KH; ++i) {
+                const int kk = 2 * i + kh;
+                if (kk < k) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(sx + kk * AGW_CB + cc);
+                    acc[i] = fmaf(xv.x, gv0, acc[i]);
+                    acc[i] = fmaf(xv.y, gv1, acc[i]);
+                    acc[i] = fmaf(xv.z, gv2, acc[i]);
+                    acc[i] = fmaf(xv.w, gv3, acc[i]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (g_wn != nullptr) {
+#pragma unroll
+        for (int i = 0; i < KH; ++i) {
+            const int kk = 2 * i + kh;
+            if (kk < k) g_wn[(r * (long long)k + kk) * 16 + w] = acc[i];
+        }
+    }
+}
+
 }  // namespace kdpc
 
 using namespace kdpc;
@@ -189,6 +290,12 @@ KDPC_API int kdpc_pointconv_agg_grad(long long rows, int k, int c, int wout, con
     const size_t smem = (size_t)k * wout * sizeof(float);
     if (smem > 32 * 1024) return KDPC_EUNSUPPORTED;
     cudaStream_t st = to_stream(stream);
+    if (k <= 16 && (reinterpret_cast<uintptr_t>(wn) % 16) == 0) {
+        const unsigned grid = (unsigned)div_up_ll(rows, AGW_WARPS);
+        if (k <= 10) pointconv_agg_grad_warp_kernel<5><<<grid, AGW_WARPS * 32, 0, st>>>(rows, k, c, grouped, wn, grad_out, grad_grouped, grad_wn);
+        else pointconv_agg_grad_warp_kernel<8><<<grid, AGW_WARPS * 32, 0, st>>>(rows, k, c, grouped, wn, grad_out, grad_grouped, grad_wn);
+        KDPC_RETURN_LAST();
+    }
     if (k <= 9)
         pointconv_agg_grad_kernel<16, 9><<<(unsigned)rows, AGG_THREADS, smem, st>>>(rows, k, c, grouped, wn, grad_out, grad_grouped, grad_wn);
     else

@@ -64,6 +64,9 @@ struct GemmShape {
     int stages;
     int splits;           // split-K: each tile's K chunks are spread over `splits` work items (partial sums to a workspace)
     int chunks_per_split;
+    int nsplit;           // 1: the `splits` work items of a tile are COLUMN blocks of n_pad outputs each (whole K, final
+                          // results, no workspace): split index j computes output columns j * n_pad .. (plan_split_n)
+    int w_n_pad;          // rows of the packed weight (= n_pad unless nsplit)
     int raw_bytes;        // bytes of one raw staging buffer of an asynchronous producer (0: none)
     int raw_stages;       // lookahead + 1
     long long num_tiles;
@@ -104,6 +107,8 @@ static inline GemmShape make_shape(long long m, int n, int k_packed, const void 
     g.wchunks = g.num_chunks;
     g.splits = 1;
     g.chunks_per_split = g.num_chunks;
+    g.nsplit = 0;
+    g.w_n_pad = g.n_pad;
     g.raw_bytes = raw_bytes;
     g.raw_stages = raw_stages;
     g.stages = pick_stages(g.n_pad, raw_bytes * raw_stages);
@@ -131,7 +136,28 @@ static inline void plan_split_k(GemmShape &g) {
     g.splits = (g.num_chunks + g.chunks_per_split - 1) / g.chunks_per_split;
 }
 static inline size_t split_k_ws_bytes(const GemmShape &g) {
-    return g.splits > 1 ? (size_t)g.splits * (size_t)g.m * g.n_pad * sizeof(float) : 0;
+    return g.splits > 1 && !g.nsplit ? (size_t)g.splits * (size_t)g.m * g.n_pad * sizeof(float) : 0;
+}
+// Split-N for small-M plain layers with >= 128 outputs (the 64 .. 4096-point levels: 4 .. 64 row tiles): a work item
+// is a 128-row x 64- (or 128-) column block over the WHOLE K.  Against split-K: final results straight from the
+// epilogue (no partial sums, no reduce launch), weight stages of 16 KB instead of 64, four pipeline stages; the rows
+// are re-read from L2 once per column block.  (4096 x 256 -> 256: 25-29 us as split-K + reduce.)
+static inline bool plan_split_n(GemmShape &g) {
+    const int sms = device_sms();
+    // (long K stays with split-K: its shorter accumulation chains keep the 1e-5 error budget of the K = 3120 layers)
+    if (g.num_tiles * 2 > sms || g.n_pad < 128 || (g.n_pad & 63) != 0 || g.num_chunks > 8) return false;
+    int nb = 64;
+    if (g.num_tiles * (g.n_pad / 64) > sms && g.n_pad > 128 && (g.n_pad & 127) == 0) nb = 128;
+    g.w_n_pad = g.n_pad;
+    g.splits = g.n_pad / nb;
+    g.nsplit = 1;
+    g.chunks_per_split = g.num_chunks;
+    g.n_pad = nb;
+    g.acc_stride = nb;
+    g.nacc_log2 = 2;
+    g.tmem_cols = 4 * nb;
+    g.stages = pick_stages(nb, 0);
+    return true;
 }
 
 // Producer concept:
@@ -284,7 +310,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             long long tile;
             int split_;
             work_item(w, g.splits, tile, split_);
-            const int c_begin = split_ * g.chunks_per_split;
+            const int c_begin = g.nsplit ? 0 : split_ * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             if constexpr (owns_loop<Producer>::value) {
                 // the producer drives the K loop of its tile itself (tight inner loops with its state in registers):
@@ -328,7 +354,13 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
                 mbar_wait(&empty[s], ph ^ 1);
                 if (ptid == 0) {                                  // weight chunk for this stage (bulk TMA, async)
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(c % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    if (g.nsplit) {                               // rows split_ * n_pad .. of the chunk: its hi and lo pieces
+                        const unsigned char *src = g.wpacked + (size_t)(c % g.wchunks) * (2 * g.w_n_pad * 128) + (size_t)split_ * g.n_pad * 128;
+                        tma_load_1d(b_base + (size_t)s * bbytes, src, (uint32_t)bbytes / 2, &full_b[s]);
+                        tma_load_1d(b_base + (size_t)s * bbytes + bbytes / 2, src + (size_t)g.w_n_pad * 128, (uint32_t)bbytes / 2, &full_b[s]);
+                    } else {
+                        tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(c % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    }
                 }
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
                 prod.fill(c, a_hi, a_hi + A_PART_BYTES, ptid);
@@ -388,7 +420,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             long long tile_;
             int split_;
             work_item(w, g.splits, tile_, split_);
-            const int c_begin = split_ * g.chunks_per_split;
+            const int c_begin = g.nsplit ? 0 : split_ * g.chunks_per_split;
             const int c_end = min(g.num_chunks, c_begin + g.chunks_per_split);
             const uint32_t acc = tcount & nacc_mask;
             mbar_wait(&tmem_empty[acc], ((tcount >> g.nacc_log2) & 1) ^ 1);
@@ -507,13 +539,26 @@ struct StoreEpilogue {
     static constexpr int TP = 36;                             // floats per staged row (32 + 4): conflict-free 16-byte accesses
     __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int split, uint32_t t_acc,
                                          int quarter, int lane) const {
+        if (g.nsplit) {                                           // column block `split`: the same epilogue on shifted pointers
+            const int n0 = split * g.n_pad;
+            Args e2 = e;
+            e2.out += n0;
+            if (e2.scale) e2.scale += n0;
+            if (e2.shift) e2.shift += n0;
+            if (e2.residual) e2.residual += n0;
+            tile_impl(e2, g, g.n - n0 < g.n_pad ? g.n - n0 : g.n_pad, false, tile, 0, t_acc, quarter, lane);
+            return;
+        }
+        tile_impl(e, g, g.n, g.splits > 1, tile, split, t_acc, quarter, lane);
+    }
+    __device__ __forceinline__ void tile_impl(const Args &e, const GemmShape &g, const int gn, const bool partial, long long tile,
+                                              int split, uint32_t t_acc, int quarter, int lane) const {
         __shared__ __align__(16) float stage[4][32 * TP];
         float *st = stage[quarter];
         const long long row0 = tile * TILE_M + quarter * 32;
-        const bool partial = g.splits > 1;
         float *obase = partial ? e.partial + (size_t)split * g.m * g.n_pad : e.out;
         const int ld = partial ? g.n_pad : e.ldo;
-        const int ncols = partial ? g.n_pad : g.n;
+        const int ncols = partial ? g.n_pad : gn;
         const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0 &&
                          (e.residual == nullptr || partial || (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // this lane's row within a group of 4, and its 4 columns
@@ -521,7 +566,7 @@ struct StoreEpilogue {
         // rows, no residual.  Branch-free and fully unrolled: the generic path below carries a 64-bit division, eight
         // predicated scalar scale/shift loads and ~10 branches per row group and cost ~2700 cycles per 32 x 32 block
         // (tools/trace_linear.py: the epilogue, not HBM, paced the streaming layers at 26-34 % of the copy peak).
-        if (!partial && (e.row_order == nullptr || e.rows_per_cloud >= 32) && e.residual == nullptr && vec && (g.n & 3) == 0 &&
+        if (!partial && (e.row_order == nullptr || e.rows_per_cloud >= 32) && e.residual == nullptr && vec && (gn & 3) == 0 &&
             row0 + 32 <= g.m && ((reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.shift)) & 15) == 0) {
             const bool clampd = e.lo <= e.hi;
             // destination of this lane's 8 rows (i * 4 + rsub): plain order, or through the row order (the fused PointConv
@@ -544,13 +589,13 @@ struct StoreEpilogue {
             }
             for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
                 const int col = c0 + c4;
-                const bool live = col < g.n;                      // (n % 4 == 0: a lane's 4 columns are all in or all out)
+                const bool live = col < gn;                      // (n % 4 == 0: a lane's 4 columns are all in or all out)
                 float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (live && e.scale) sc = __ldg(reinterpret_cast<const float4 *>(e.scale + col));   // in flight during the TMEM load
                 if (live && e.shift) sh = __ldg(reinterpret_cast<const float4 *>(e.shift + col));
                 float v[32];
                 tmem_ld_32x32(t_acc + (uint32_t)c0, v);           // warp-collective: no divergence around it
-                if (c0 >= g.n) continue;
+                if (c0 >= gn) continue;
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -588,7 +633,7 @@ struct StoreEpilogue {
             if (!partial) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (col + j < g.n) {
+                    if (col + j < gn) {
                         if (e.scale) sc[j] = __ldg(e.scale + col + j);
                         if (e.shift) sh[j] = __ldg(e.shift + col + j);
                     }

@@ -33,3 +33,6 @@ for n, (c, t) in sorted(by.items(), key=lambda kv: -kv[1][1]):
 print("--- calls > 40 us, in order")
 for n, a, t in rows:
     if t > 40: print(f"{t:8.1f} us  {n:24s} {a}")
+print("--- linear calls (m, n, k, ...), in order")
+for n, a, t in rows:
+    if n in ("kdpc_linear_tc", "kdpc_linear_simt"): print(f"{t:8.1f} us  {n:18s} {a[:4]}")
