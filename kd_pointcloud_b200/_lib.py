@@ -188,6 +188,10 @@ def lib() -> ctypes.CDLL:
         L.kdpc_linear_set_split_n.argtypes = [c_int]
         if os.environ.get("KDPC_SPLIT_N", "1") == "0":           # A/B switch for measurements
             L.kdpc_linear_set_split_n(0)
+        L.kdpc_linear_dw_set_async.restype = None
+        L.kdpc_linear_dw_set_async.argtypes = [c_int]
+        if os.environ.get("KDPC_DW_ASYNC", "1") == "0":          # A/B switch for measurements
+            L.kdpc_linear_dw_set_async(0)
         L.kdpc_costvol_set_pairing.restype = None
         L.kdpc_costvol_set_pairing.argtypes = [c_int]
         if os.environ.get("KDPC_CV_PAIR", "1") == "0":           # A/B switch for measurements
@@ -202,7 +206,7 @@ def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_set_sm_limit", "kdpc_sm_limit", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
             "kdpc_loss_workspace_bytes", "kdpc_linear_dw_ws_bytes", "kdpc_weightnet_grad_ws_bytes", "kdpc_dataprep_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
-            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n"] + list(_SIGNATURES)
+            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n", "kdpc_linear_dw_set_async"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -55,7 +55,9 @@ struct DwArgs {
     int n_tiles, k_tiles, splits;
     long long rows_per_split;        // multiple of DW_MCHUNK
     float *partial;                  // [splits][n_tiles * 128][k_tiles * 256]
+    int raw_stages;                  // > 0: narrow contiguous operands - row chunks staged by 1-D bulk TMA, raw_stages - 1 chunks ahead
 };
+constexpr int DW_MAX_RAW = 4;
 
 // unit = 8 consecutive floats of one source row -> (hi, lo) 16-byte units; `width` valid floats from `col0`
 __device__ __forceinline__ void dw_load_unit(const float *rowp, bool row_ok, int col0, int width, bool vec, float (&v)[8]) {
@@ -72,7 +74,7 @@ __device__ __forceinline__ void dw_load_unit(const float *rowp, bool row_ok, int
 __global__ void __launch_bounds__(DW_THREADS, 1)
 dw_tc_kernel(const DwArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[2], empty[2], done_bar;
+    __shared__ __align__(8) uint64_t full[2], empty[2], done_bar, raw_full[DW_MAX_RAW];
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = smem_u32(smem_raw);
@@ -96,6 +98,7 @@ dw_tc_kernel(const DwArgs a) {
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&full[s], DW_PRODUCERS / 32); mbar_init(&empty[s], 1); }
         mbar_init(&done_bar, 1);
+        for (int r = 0; r < DW_MAX_RAW; ++r) mbar_init(&raw_full[r], 1);     // expect_tx arrival of producer thread 0
         mbar_fence_init();
     }
     if (warp == DW_PRODUCERS / 32) tmem_alloc(&tmem_base_smem, 256u);
@@ -109,6 +112,92 @@ dw_tc_kernel(const DwArgs a) {
         const bool vec_y = (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dy) & 15) == 0 && (n0 & 3) == 0;
         const bool vec_x = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
         const int b_upr = kgroups * 8;                           // units per row of the X tile
+        if (a.raw_stages > 0) {
+            // Narrow layers over very many rows (cost-volume / positional layers: N, K <= 64 over 0.5 - 2 M rows).  The
+            // register-staged loop below has ONE 64-row chunk (<= 17 KB) per memory round trip per CTA and ran 8x above
+            // the HBM bound.  Here the operands are contiguous ([M, n] and [M, k], M % 64 == 0, one output tile): a chunk
+            // of each is ONE 1-D bulk TMA copy (64 n * 4 and 64 k * 4 bytes) issued raw_stages - 1 chunks ahead by
+            // thread 0, and the producers convert from shared memory only.
+            const int R = a.raw_stages;
+            const uint32_t ybytes = (uint32_t)DW_MCHUNK * a.n * 4u, xbytes = (uint32_t)DW_MCHUNK * a.k * 4u;
+            const uint32_t raw_bytes = (ybytes + xbytes + 15u) & ~15u;
+            unsigned char *raw_base = smem + 2 * (size_t)stage_bytes;
+            auto issue = [&](int c) {
+                const int slot = c % R;
+                unsigned char *dst = raw_base + (size_t)slot * raw_bytes;
+                const long long row0 = m_begin + (long long)c * DW_MCHUNK;
+                mbar_expect_tx(&raw_full[slot], ybytes + xbytes);
+                tma_load_1d(dst, a.dy + row0 * a.n, ybytes, &raw_full[slot]);
+                tma_load_1d(dst + ybytes, a.x + row0 * a.k, xbytes, &raw_full[slot]);
+            };
+            if (tid == 0)
+                for (int c = 0; c < R - 1 && c < chunks; ++c) issue(c);
+            const int a_live = (a.n + 7) >> 3, b_live = min(b_upr, (kw + 7) >> 3);
+            const bool vec_n = (a.n & 3) == 0, vec_k = (a.k & 3) == 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int s = c & 1;
+                // every producer is done converting chunk c - 1: its raw slot may be refilled
+                asm volatile("bar.sync 1, %0;" ::"n"(DW_PRODUCERS) : "memory");
+                if (tid == 0 && c + R - 1 < chunks) issue(c + R - 1);
+                mbar_wait(&empty[s], ((c >> 1) & 1) ^ 1);
+                unsigned char *st = smem + (size_t)s * stage_bytes;
+                unsigned char *a_hi = st, *a_lo = st + DW_A_PART, *b_hi = st + 2 * DW_A_PART, *b_lo = b_hi + b_part;
+                const bool first_fill = c < 2;
+                if (first_fill) {                                 // all-zero padding units, once per operand stage
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+                    for (int i = tid; i < DW_MCHUNK * (DW_TN / 8); i += DW_PRODUCERS) {
+                        const int r = i / (DW_TN / 8), u = i - r * (DW_TN / 8);
+                        if (u >= a_live) { const uint32_t off = mn_offset(u, r); *reinterpret_cast<uint4 *>(a_hi + off) = z; *reinterpret_cast<uint4 *>(a_lo + off) = z; }
+                    }
+                    for (int i = tid; i < DW_MCHUNK * b_upr; i += DW_PRODUCERS) {
+                        const int r = i / b_upr, u = i - r * b_upr;
+                        if (u >= b_live) { const uint32_t off = mn_offset(u, r); *reinterpret_cast<uint4 *>(b_hi + off) = z; *reinterpret_cast<uint4 *>(b_lo + off) = z; }
+                    }
+                }
+                mbar_wait(&raw_full[c % R], (uint32_t)((c / R) & 1));
+                const float *ry = reinterpret_cast<const float *>(raw_base + (size_t)(c % R) * raw_bytes);
+                const float *rx = reinterpret_cast<const float *>(raw_base + (size_t)(c % R) * raw_bytes + ybytes);
+                // unit = 8 consecutive floats of one row; consecutive threads take consecutive units (conflict-free reads)
+                auto load_unit = [&](const float *row, int col0, int width, bool vec, float (&v)[8]) {
+                    if (vec && col0 + 8 <= width) {
+                        const float4 p = *reinterpret_cast<const float4 *>(row + col0), q = *reinterpret_cast<const float4 *>(row + col0 + 4);
+                        v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = col0 + j < width ? row[col0 + j] : 0.f;
+                    }
+                };
+                for (int i = tid; i < DW_MCHUNK * a_live; i += DW_PRODUCERS) {
+                    const int r = i / a_live, u = i - r * a_live;
+                    float v[8];
+                    load_unit(ry + r * a.n, u * 8, a.n, vec_n, v);
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    const uint32_t off = mn_offset(u, r);
+                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                }
+                for (int i = tid; i < DW_MCHUNK * b_live; i += DW_PRODUCERS) {
+                    const int r = i / b_live, u = i - r * b_live;
+                    float v[8];
+                    load_unit(rx + r * a.k, u * 8, a.k, vec_k, v);
+                    const int oc = a.k - u * 8;                   // the all-ones column (bias gradient) inside this unit?
+                    if (a.k_eff != a.k && oc >= 0 && oc < 8) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q == oc) v[q] = 1.f;
+                    }
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    const uint32_t off = mn_offset(u, r);
+                    *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                    *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        } else
         for (int c = 0; c < chunks; ++c) {
             const int s = c & 1;
             mbar_wait(&empty[s], ((c >> 1) & 1) ^ 1);
@@ -289,6 +378,10 @@ static inline void dw_plan(long long m, int n, int k, bool bias, DwArgs &a) {
 using namespace kdpc;
 using namespace kdpc::tc;
 
+static int kdpc_dw_async = 1;
+/* A/B switch for measurements: 0 = register-staged row fetch for every shape (same results) */
+KDPC_API void kdpc_linear_dw_set_async(int on) { kdpc_dw_async = on; }
+
 KDPC_API long long kdpc_linear_dw_ws_bytes(long long m, int n, int k) {
     if (m <= 0 || n <= 0 || k <= 0) return 0;
     DwArgs a{};
@@ -307,6 +400,15 @@ KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy,
     dw_plan(m, n, k, db != nullptr, a);
     a.partial = reinterpret_cast<float *>(ws);
     const size_t smem = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)(DW_KT / 64) * DW_LBO) + 1024;
+    a.raw_stages = 0;
+    if (kdpc_dw_async && a.n_tiles == 1 && a.k_tiles == 1 && ldy == n && ldx == k && m % DW_MCHUNK == 0 && a.k_eff <= 64 &&
+        ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+        // narrow contiguous operands: raw row chunks by bulk TMA next to the two operand stages (one 64-column X group)
+        const size_t stages = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)DW_LBO);
+        const size_t raw = ((size_t)DW_MCHUNK * (n + k) * 4 + 15) & ~(size_t)15;
+        const long long fit = (long long)((smem - 1024 - stages) / raw);
+        if (fit >= 2) a.raw_stages = (int)(fit < DW_MAX_RAW ? fit : DW_MAX_RAW);
+    }
     KDPC_ENSURE_SMEM(dw_tc_kernel, (int)smem);
     cudaStream_t st = to_stream(stream);
     const unsigned grid = (unsigned)(a.n_tiles * a.k_tiles * a.splits);

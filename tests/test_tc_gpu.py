@@ -239,7 +239,8 @@ def test_wide_linear_blocks_written_in_place():
 
 
 @pytest.mark.parametrize("m,n,k", [(65536, 128, 128), (4096, 64, 2096), (1000, 32, 35), (128 * 3 + 5, 256, 256), (50, 16, 16),
-                                   (8192, 128, 1072), (300, 200, 520)])
+                                   (8192, 128, 1072), (300, 200, 520), (131072, 32, 32), (65536, 32, 3), (32768, 64, 63),
+                                   (16384, 64, 64), (6400, 48, 20), (64, 8, 3)])
 def test_linear_dw_matches_fp64(m, n, k):
     """dW = dY^T X on tcgen05 with MN-major operand tiles (csrc/dw_tc.cu) against an fp64 product: ragged row counts,
     N < 128 (zero-padded tile rows), K tails that are not multiples of 16 / 64 / 256, several split counts."""
@@ -256,6 +257,14 @@ def test_linear_dw_matches_fp64(m, n, k):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)                     # deterministic
     dw3, db3 = torch.ops.kdpc.linear_dw(dy, x, False)                        # without the bias column: same weight gradient
     assert db3.numel() == 0 and ((dw3.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    # narrow contiguous shapes take the bulk-TMA row fetch: same bits as the register-staged fetch
+    from kd_pointcloud_b200 import _lib
+    _lib.lib().kdpc_linear_dw_set_async(0)
+    try:
+        dw4, db4 = torch.ops.kdpc.linear_dw(dy, x, True)
+    finally:
+        _lib.lib().kdpc_linear_dw_set_async(1)
+    assert torch.equal(dw, dw4) and torch.equal(db, db4)
 
 
 def test_linear_tc_autograd_uses_the_tcgen05_weight_gradient():
