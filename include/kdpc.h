@@ -235,8 +235,9 @@ int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx, const f
 /* Weight gradient of y = x W^T (nn.Linear / 1x1 conv; reference: autograd of pointconv_util.py:20-54, 223, 250):
  * dw[n,k] = sum_m dy[m,n] * x[m,k] on tcgen05 with MN-major operand tiles (bf16 hi/lo, fp32 accumulation), the row range
  * split over CTAs and reduced in split order (deterministic).  ws: kdpc_linear_dw_ws_bytes(m, n, k) bytes. */
-/* narrow contiguous operands (n, k + 1 <= 64, ldy == n, ldx == k, m % 64 == 0): row chunks staged by bulk TMA several
- * chunks ahead (default 1); 0 = the register-staged fetch for every shape.  Same results. */
+/* narrow contiguous operands (n <= 128, k + 1 <= 128, ldy == n, ldx == k, m % 64 == 0): row chunks staged by bulk TMA
+ * several chunks ahead, same bits as the register-staged fetch; k + 1 <= 4 (3 -> D layers): weighted column sums on the
+ * CUDA cores in fp32 (no bf16 split: last-bit differences).  Default 1; 0 = the register-staged tcgen05 path for every shape. */
 void kdpc_linear_dw_set_async(int on);
 long long kdpc_linear_dw_ws_bytes(long long m, int n, int k);
 int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy, const float *x, int ldx, void *ws,

@@ -335,6 +335,75 @@ dw_tc_kernel(const DwArgs a) {
     }
 }
 
+// dW for layers with a tiny input width (the 3 -> D positional encodings over B*N*K rows: k + bias <= 4): the product is
+// k + 1 weighted column sums of dY - a tensor-core tile would be 98 % padding and the MN-major pipeline above runs such
+// shapes at ~1 TB/s.  CUDA cores: thread = (4 output columns, row lane), float4 loads of dY (coalesced), X broadcast per
+// row, fp32 accumulators walked in row order; the row lanes of a CTA are summed in lane order through shared memory and
+// every CTA leaves its [n x KE] partial in the SAME workspace layout as dw_tc_kernel, so dw_reduce_kernel finishes both.
+constexpr int DWS_THREADS = 512;
+template <int KE>                                          // k + (bias ? 1 : 0) <= KE = 4
+__global__ void __launch_bounds__(DWS_THREADS)
+dw_small_k_kernel(const DwArgs a) {
+    extern __shared__ float4 sred[];                       // [row lanes][column groups][KE]
+    const int cg = a.n >> 2;                               // column groups of 4 (n % 4 == 0)
+    const int lanes = DWS_THREADS / cg;                    // row lanes
+    const int c = threadIdx.x % cg, rl = threadIdx.x / cg;
+    const long long m_begin = (long long)blockIdx.x * a.rows_per_split;
+    const long long m_end = min(a.m, m_begin + a.rows_per_split);
+    float4 acc[KE];
+#pragma unroll
+    for (int j = 0; j < KE; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool bias = a.k_eff != a.k;
+    if (rl < lanes) {
+        long long row = m_begin + rl;
+        for (; row + 3LL * lanes < m_end; row += 4LL * lanes) {        // four rows in flight per thread
+            float4 d[4];
+            float xv[4][KE];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = row + (long long)u * lanes;
+                d[u] = ld_stream_f4(reinterpret_cast<const float4 *>(a.dy + r * a.ldy) + c);
+#pragma unroll
+                for (int j = 0; j < KE; ++j) xv[u][j] = j < a.k ? __ldg(a.x + r * a.ldx + j) : 1.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < KE; ++j) {
+                    acc[j].x = fmaf(d[u].x, xv[u][j], acc[j].x); acc[j].y = fmaf(d[u].y, xv[u][j], acc[j].y);
+                    acc[j].z = fmaf(d[u].z, xv[u][j], acc[j].z); acc[j].w = fmaf(d[u].w, xv[u][j], acc[j].w);
+                }
+        }
+        for (; row < m_end; row += lanes) {
+            const float4 d = ld_stream_f4(reinterpret_cast<const float4 *>(a.dy + row * a.ldy) + c);
+#pragma unroll
+            for (int j = 0; j < KE; ++j) {
+                const float xv = j < a.k ? __ldg(a.x + row * a.ldx + j) : 1.f;
+                acc[j].x = fmaf(d.x, xv, acc[j].x); acc[j].y = fmaf(d.y, xv, acc[j].y);
+                acc[j].z = fmaf(d.z, xv, acc[j].z); acc[j].w = fmaf(d.w, xv, acc[j].w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KE; ++j) sred[(rl * cg + c) * KE + j] = acc[j];
+    }
+    __syncthreads();
+    // thread (column group, j): its column group's lanes in lane order
+    if (threadIdx.x < cg * KE) {
+        const int cc = threadIdx.x / KE, j = threadIdx.x - cc * KE;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) {
+            const float4 v = sred[(l * cg + cc) * KE + j];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        if (j < a.k_eff) {
+            float *p = a.partial + ((size_t)blockIdx.x * a.n_tiles * DW_TN + (size_t)cc * 4) * ((size_t)a.k_tiles * DW_KT) + j;
+            const size_t ld = (size_t)a.k_tiles * DW_KT;
+            p[0] = t.x; p[ld] = t.y; p[2 * ld] = t.z; p[3 * ld] = t.w;
+        }
+    }
+    (void)bias;
+}
+
 // dW[n, k] = sum over splits, in split order; column k (when present) is the bias gradient db[n]
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(int n, int k, int k_eff, int splits, long long split_stride, int ldp, const float *__restrict__ partial,
@@ -401,23 +470,32 @@ KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy,
     a.dy = dy; a.x = x; a.m = m; a.n = n; a.k = k; a.ldy = ldy; a.ldx = ldx;
     dw_plan(m, n, k, db != nullptr, a);
     a.partial = reinterpret_cast<float *>(ws);
-    const size_t smem = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)(DW_KT / 64) * DW_LBO) + 1024;
+    size_t smem = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)(DW_KT / 64) * DW_LBO) + 1024;
+    if (smem < 226 * 1024) smem = 226 * 1024;              // (the TMA-staged path puts its raw ring behind the operand stages)
     a.raw_stages = 0;
-    if (kdpc_dw_async && a.n_tiles == 1 && a.k_tiles == 1 && ldy == n && ldx == k && m % DW_MCHUNK == 0 && a.k_eff <= 64 &&
+    cudaStream_t st = to_stream(stream);
+    const int ldp = a.k_tiles * DW_KT;
+    const long long split_stride = (long long)a.n_tiles * DW_TN * ldp;
+    const long long total = (long long)n * ((a.k_eff + 3) / 4);
+    if (kdpc_dw_async && a.k_eff <= 4 && n <= 256 && (n & 3) == 0 && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        // tiny input width: weighted column sums on the CUDA cores (same workspace layout, same reduce kernel)
+        const int lanes = DWS_THREADS / (n / 4);
+        dw_small_k_kernel<4><<<(unsigned)a.splits, DWS_THREADS, (size_t)lanes * (n / 4) * 4 * sizeof(float4), st>>>(a);
+        dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
+        KDPC_RETURN_LAST();
+    }
+    const int kgroups = (a.k_eff + 63) / 64;
+    if (kdpc_dw_async && a.n_tiles == 1 && a.k_tiles == 1 && ldy == n && ldx == k && m % DW_MCHUNK == 0 && kgroups <= 2 &&
         ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
-        // narrow contiguous operands: raw row chunks by bulk TMA next to the two operand stages (one 64-column X group)
-        const size_t stages = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)DW_LBO);
+        // narrow contiguous operands: raw row chunks by bulk TMA next to the two operand stages (<= two 64-column X groups)
+        const size_t stages = 2 * (2 * (size_t)DW_A_PART + 2 * (size_t)kgroups * DW_LBO);
         const size_t raw = ((size_t)DW_MCHUNK * (n + k) * 4 + 15) & ~(size_t)15;
         const long long fit = (long long)((smem - 1024 - stages) / raw);
         if (fit >= 2) a.raw_stages = (int)(fit < DW_MAX_RAW ? fit : DW_MAX_RAW);
     }
     KDPC_ENSURE_SMEM(dw_tc_kernel, (int)smem);
-    cudaStream_t st = to_stream(stream);
     const unsigned grid = (unsigned)(a.n_tiles * a.k_tiles * a.splits);
     dw_tc_kernel<<<grid, DW_THREADS, smem, st>>>(a);
-    const int ldp = a.k_tiles * DW_KT;
-    const long long split_stride = (long long)a.n_tiles * DW_TN * ldp;
-    const long long total = (long long)n * ((a.k_eff + 3) / 4);
     dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
     KDPC_RETURN_LAST();
 }

@@ -240,7 +240,7 @@ def test_wide_linear_blocks_written_in_place():
 
 @pytest.mark.parametrize("m,n,k", [(65536, 128, 128), (4096, 64, 2096), (1000, 32, 35), (128 * 3 + 5, 256, 256), (50, 16, 16),
                                    (8192, 128, 1072), (300, 200, 520), (131072, 32, 32), (65536, 32, 3), (32768, 64, 63),
-                                   (16384, 64, 64), (6400, 48, 20), (64, 8, 3)])
+                                   (16384, 64, 64), (6400, 48, 20), (64, 8, 3), (70001, 128, 3), (4099, 256, 3), (1000, 36, 2)])
 def test_linear_dw_matches_fp64(m, n, k):
     """dW = dY^T X on tcgen05 with MN-major operand tiles (csrc/dw_tc.cu) against an fp64 product: ragged row counts,
     N < 128 (zero-padded tile rows), K tails that are not multiples of 16 / 64 / 256, several split counts."""
@@ -264,7 +264,11 @@ def test_linear_dw_matches_fp64(m, n, k):
         dw4, db4 = torch.ops.kdpc.linear_dw(dy, x, True)
     finally:
         _lib.lib().kdpc_linear_dw_set_async(1)
-    assert torch.equal(dw, dw4) and torch.equal(db, db4)
+    if k + 1 > 4:
+        assert torch.equal(dw, dw4) and torch.equal(db, db4)
+    else:       # tiny input width: fp32 column sums on the CUDA cores instead of the bf16 hi/lo product - both inside the budget
+        assert ((dw4.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+        assert ((db4.double() - ref_b).abs().max() / ref_b.abs().max()).item() < 2e-5
 
 
 def test_linear_tc_autograd_uses_the_tcgen05_weight_gradient():
