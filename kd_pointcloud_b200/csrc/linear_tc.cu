@@ -84,6 +84,102 @@ linear_simt_kernel(long long m, int n, int k, const float *__restrict__ x, int l
     }
 }
 
+
+// Two shapes of the positional-encoding layers over B*N*K rows, where the generic kernel above runs at 1/4 - 1/7 of the
+// HBM bound (one thread per (row, 4 outputs) re-reads its weights for every row and walks its x row scalar by scalar):
+//   * k <= 4 (3 -> D forward): thread = (row, 4 outputs) as above, but a thread keeps its 4 x k weights and its affine in
+//     registers and walks rows grid-stride: the loop is 1-3 loads, 4k FMAs and one 16-byte store per row;
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+linear_smallk_kernel(long long m, int n, int k, const float *__restrict__ x, int ldx, const float *__restrict__ w,
+                     const float *__restrict__ scale, const float *__restrict__ shift, float slope, float lo, float hi,
+                     float *__restrict__ out, int ldo) {
+    const int ng = n >> 2;                                    // n % 4 == 0
+    const int g = threadIdx.x % ng, rl = threadIdx.x / ng, lanes = blockDim.x / ng;
+    if (rl >= lanes) return;
+    float wr[4][KMAX], sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) wr[j][kk] = kk < k ? __ldg(w + (size_t)(g * 4 + j) * k + kk) : 0.f;
+        sc[j] = scale ? __ldg(scale + g * 4 + j) : 1.f;
+        sh[j] = shift ? __ldg(shift + g * 4 + j) : 0.f;
+    }
+    const bool clampd = lo <= hi;
+    for (long long row = (long long)blockIdx.x * lanes + rl; row < m; row += (long long)gridDim.x * lanes) {
+        float xv[KMAX];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? __ldg(x + row * ldx + kk) : 0.f;
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) acc = fmaf(xv[kk], wr[j][kk], acc);     // same order as the generic kernel
+            float t = acc * sc[j];
+            t += sh[j];
+            t = t > 0.f ? t : t * slope;
+            if (clampd) t = fminf(fmaxf(t, lo), hi);
+            y[j] = t;
+        }
+        st_stream_f4(reinterpret_cast<float4 *>(out + row * ldo) + g, make_float4(y[0], y[1], y[2], y[3]));
+    }
+}
+//   * n <= 4 (D -> 3: flow heads, and the input gradient of the 3 -> D layers): 8 lanes share a row, each loads float4s of
+//     it (coalesced 128-byte requests), keeps partial dot products for the n outputs and the 8 lanes are summed by a
+//     fixed shuffle tree; lane 0 of the group applies the epilogue and stores.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+linear_smalln_kernel(long long m, int n, int k, const float *__restrict__ x, int ldx, const float *__restrict__ w,
+                     const float *__restrict__ scale, const float *__restrict__ shift, float slope, float lo, float hi,
+                     const float *__restrict__ residual, float *__restrict__ out, int ldo) {
+    const int sub = threadIdx.x & 7;
+    const long long rows_per_cta = blockDim.x >> 3;
+    const bool clampd = lo <= hi;
+    for (long long row = (long long)blockIdx.x * rows_per_cta + (threadIdx.x >> 3);; row += (long long)gridDim.x * rows_per_cta) {
+        // (whole warps leave together: rows_per_cta * gridDim.x strides keep a warp's 4 rows consecutive)
+        const bool live = row < m;
+        if (__all_sync(0xffffffffu, !live)) break;
+        float acc[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
+        if (live) {
+            const float4 *xr = reinterpret_cast<const float4 *>(x + row * ldx);
+            for (int q = sub; q < (k >> 2); q += 8) {         // k % 4 == 0
+                const float4 v = ld_stream_f4(xr + q);
+#pragma unroll
+                for (int j = 0; j < NMAX; ++j) {
+                    if (j < n) {
+                        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + (size_t)j * k) + q);
+                        acc[j] = fmaf(v.x, ww.x, acc[j]); acc[j] = fmaf(v.y, ww.y, acc[j]);
+                        acc[j] = fmaf(v.z, ww.z, acc[j]); acc[j] = fmaf(v.w, ww.w, acc[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+        }
+        if (live && sub == 0) {
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) {
+                if (j < n) {
+                    float y = acc[j];
+                    if (scale) y *= __ldg(scale + j);
+                    if (shift) y += __ldg(shift + j);
+                    y = y > 0.f ? y : y * slope;
+                    if (clampd) y = fminf(fmaxf(y, lo), hi);
+                    if (residual) y += __ldg(residual + row * ldo + j);
+                    out[row * ldo + j] = y;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace tc
 }  // namespace kdpc
 
@@ -225,6 +321,21 @@ KDPC_API int kdpc_linear_simt(long long m, int n, int k, const float *x, int ldx
                               const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
                               const float *residual, float *out, int ldo, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(x && w && out && m > 0 && n > 0 && k > 0 && ldx >= k && ldo >= n);
+    cudaStream_t st = to_stream(stream);
+    if (m >= 16384 && k <= 4 && (n & 3) == 0 && n <= 256 && residual == nullptr && (ldo & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int lanes = 256 / (n >> 2);
+        const long long want = (m + lanes - 1) / lanes;
+        const unsigned grid = (unsigned)(want < 8LL * device_sms() ? want : 8LL * device_sms());
+        linear_smallk_kernel<4><<<grid, 256, 0, st>>>(m, n, k, x, ldx, w, scale, shift, slope, clamp_lo, clamp_hi, out, ldo);
+        KDPC_RETURN_LAST();
+    }
+    if (m >= 16384 && n <= 4 && (k & 3) == 0 && (ldx & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+        const long long want = (m + 31) / 32;
+        const unsigned grid = (unsigned)(want < 8LL * device_sms() ? want : 8LL * device_sms());
+        linear_smalln_kernel<4><<<grid, 256, 0, st>>>(m, n, k, x, ldx, w, scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo);
+        KDPC_RETURN_LAST();
+    }
     const long long total = m * ((n + 3) / 4);
     linear_simt_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
         m, n, k, x, ldx, w, scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo);

@@ -60,15 +60,22 @@ def test_linear_tc_epilogue_variants_and_large_magnitudes():
     assert _err(y, _ref(x, w, slope=0.0)) < 2e-5
 
 
-@pytest.mark.parametrize("m,n,k", [(5000, 32, 3), (4096, 3, 64), (100, 5, 7), (1000, 64, 10)])
+@pytest.mark.parametrize("m,n,k", [(5000, 32, 3), (4096, 3, 64), (100, 5, 7), (1000, 64, 10), (70001, 32, 3), (16384, 256, 3),
+                                   (50000, 36, 2), (65539, 3, 64), (20000, 3, 128), (16385, 2, 36), (30000, 3, 32)])
 def test_linear_simt_matches_fp64(m, n, k):
+    """Generic CUDA-core kernel, and (m >= 16384) its two specialisations: k <= 4 with the weights in registers,
+    n <= 4 with eight lanes per row."""
     g = torch.Generator().manual_seed(m + n + k)
     x = torch.randn(m, k, generator=g).to(DEV)
     w = torch.randn(n, k, generator=g).to(DEV)
     shift = torch.randn(n, generator=g).to(DEV)
+    scale = torch.rand(n, generator=g).to(DEV) + 0.5
     res = torch.randn(m, n, generator=g).to(DEV)
     y = K.linear_simt(x, w, None, shift, 1.0, -2.0, 2.0, res)
     assert _err(y, _ref(x, w, shift=shift, clamp=(-2, 2), residual=res)) < 1e-6
+    y = K.linear_simt(x, w, scale, shift, 0.1, 1.0, 0.0, None)
+    assert _err(y, _ref(x, w, scale=scale, shift=shift, slope=0.1)) < 1e-6
+    assert torch.equal(y, K.linear_simt(x, w, scale, shift, 0.1, 1.0, 0.0, None))
 
 
 def test_fused_linear_frontend_matches_torch_modules():
