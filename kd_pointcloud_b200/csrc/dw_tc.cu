@@ -404,20 +404,29 @@ dw_small_k_kernel(const DwArgs a) {
     (void)bias;
 }
 
-// dW[n, k] = sum over splits, in split order; column k (when present) is the bias gradient db[n]
+// dW[n, k] = sum over the splits' partial tiles; column k (when present) is the bias gradient db[n].  One WARP per group of
+// four output columns: lane l adds splits l, l + 32, .. in order, then a fixed butterfly adds the 32 lanes (deterministic;
+// one thread per group walking up to 148 splits one after the other was 23 us per call, 1.8 ms of the KD step).
 __global__ void __launch_bounds__(256)
 dw_reduce_kernel(int n, int k, int k_eff, int splits, long long split_stride, int ldp, const float *__restrict__ partial,
                  float *__restrict__ dw, int lddw, float *__restrict__ db) {
     const int kq = (k_eff + 3) >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * kq) return;
+    const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= (long long)n * kq) return;                   // (whole warps)
     const int row = (int)(t / kq), c0 = (int)(t - (long long)row * kq) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *p = partial + (size_t)row * ldp + c0;
-    for (int s = 0; s < splits; ++s) {
+    for (int s = lane; s < splits; s += 32) {
         const float4 v = *reinterpret_cast<const float4 *>(p + (size_t)s * split_stride);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane != 0) return;
     const float o[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -481,7 +490,7 @@ KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy,
         // tiny input width: weighted column sums on the CUDA cores (same workspace layout, same reduce kernel)
         const int lanes = DWS_THREADS / (n / 4);
         dw_small_k_kernel<4><<<(unsigned)a.splits, DWS_THREADS, (size_t)lanes * (n / 4) * 4 * sizeof(float4), st>>>(a);
-        dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
+        dw_reduce_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
         KDPC_RETURN_LAST();
     }
     const int kgroups = (a.k_eff + 63) / 64;
@@ -496,6 +505,6 @@ KDPC_API int kdpc_linear_dw(long long m, int n, int k, const float *dy, int ldy,
     KDPC_ENSURE_SMEM(dw_tc_kernel, (int)smem);
     const unsigned grid = (unsigned)(a.n_tiles * a.k_tiles * a.splits);
     dw_tc_kernel<<<grid, DW_THREADS, smem, st>>>(a);
-    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
+    dw_reduce_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(n, k, a.k_eff, a.splits, split_stride, ldp, a.partial, dw, lddw, db);
     KDPC_RETURN_LAST();
 }
