@@ -109,6 +109,9 @@ def make_capturable_adam(params, lr: float = 1e-3, **kw) -> torch.optim.Adam:
     after capture: ``set_lr`` / an in-place scheduler update changes what the captured kernels read."""
     params = list(params)
     dev = params[0].device
+    # torch's FUSED implementation: one multi-tensor kernel over the 226 parameter tensors (the default foreach path was
+    # ~2 ms of a 36 ms step: a dozen elementwise launches over every tensor list); same update rule
+    kw.setdefault("fused", True)
     return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=dev), capturable=True, **kw)
 
 
