@@ -281,6 +281,17 @@ int kdpc_spatial_sort_order_stride(int n);
  * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out].
  * ws: kdpc_costvol_fused_ws_bytes(b,s,n,d) bytes (16-byte aligned) for the per-point features with the positional
  * encoding folded in; NULL selects the variant that evaluates the encoding per neighbour (no workspace). */
+/* Backward of kdpc_costvol_fused in its folded form (reference: autograd through CrossLayerLight.cross, pointconv_util.py:1826-1850,
+ * by loss.backward(), distilTrain.py:180), d = d_out = k = 32:  out[i,c] = act2(max_k (W act1(p2q[idx[i,k]] + p1q[i]) + bias)[c])
+ * with p1q = points1 + pos_b - pos_w xyz1 and p2q = points2 + pos_w xyz2 (the caller folds and un-folds the positional layer).
+ * One warp per point recomputes the row block and lets the gradient of out[i,c] through to the ONE neighbour that attains the
+ * maximum (the first one, like torch.max).  grad_p1q [b,s,d]; grad_rows [b*s*k, d] = gradient of every gathered p2q row, to be
+ * scattered with kdpc_scatter_rows_csr (deterministic; no float atomics); grad_w [d_out,d]; grad_b [d_out] or NULL.  w: fp32
+ * [d_out,d] (not packed).  ws: kdpc_costvol_grad_ws_bytes() bytes. */
+long long kdpc_costvol_grad_ws_bytes(void);
+int kdpc_costvol_grad(int b, int s, int n, int k, int d, int d_out, const float *p1q, const float *p2q, const int *idx,
+                      const float *w, const float *bias, float slope_pre, float slope_post, const float *grad_out,
+                      void *ws, float *grad_p1q, float *grad_rows, float *grad_w, float *grad_b, kdpc_stream_t stream);
 /* Cost volume at the 8192-point level (d = 32, 16 < d_out <= 32): two 128-row tiles per pipeline iteration against the
  * block-diagonal weight diag(W, W) (default 1); 0 = one tile per iteration at every level.  Same results. */
 void kdpc_costvol_set_pairing(int on);

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("KDPC_LIB") or os.path.join(_HERE, "libkdpc.so")   # KDPC_LIB: an experiment build (A/B measurements)
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu", "knn_feat.cu", "dataprep.cu", "dw_tc.cu", "weightnet_grad.cu"]
+           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu", "knn_feat.cu", "dataprep.cu", "dw_tc.cu", "weightnet_grad.cu", "costvol_grad.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 LINK_FLAGS = ARCH_FLAGS + ["-shared"]
@@ -115,6 +115,7 @@ _SIGNATURES = {
     "kdpc_flow_loss": [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "kdpc_hint_loss": [c_longlong, _P, _P, c_float, _P, _P, _P, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_costvol_grad": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
 }
 
@@ -149,6 +150,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         L.kdpc_flow_metrics_workspace_bytes.restype = c_longlong
         L.kdpc_flow_metrics_workspace_bytes.argtypes = []
+        L.kdpc_costvol_grad_ws_bytes.restype = c_longlong
+        L.kdpc_costvol_grad_ws_bytes.argtypes = []
         L.kdpc_costvol_fused_ws_bytes.restype = c_longlong
         L.kdpc_costvol_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int]
         L.kdpc_dataprep_workspace_bytes.restype = c_longlong
@@ -206,7 +209,7 @@ def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_set_sm_limit", "kdpc_sm_limit", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
             "kdpc_loss_workspace_bytes", "kdpc_linear_dw_ws_bytes", "kdpc_weightnet_grad_ws_bytes", "kdpc_dataprep_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
-            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n", "kdpc_linear_dw_set_async"] + list(_SIGNATURES)
+            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n", "kdpc_linear_dw_set_async", "kdpc_costvol_grad_ws_bytes"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -680,6 +680,61 @@ def fused_costvol(xyz1, xyz2, p1, p2, idx, pos, slope_pre: float, conv, slope_po
                            slope_post)
 
 
+class _CostVolFn(torch.autograd.Function):
+    """Fused cost-volume half in its folded form, out = act2(max_k(W act1(p2q[idx] + p1q) + b)) (D = D' = K = 32):
+    forward = the tcgen05 inference kernel (costvol_tc.cu), backward = ONE recomputing kernel in which only the arg-max
+    neighbour of every (point, channel) receives a gradient (costvol_grad.cu) + the deterministic CSR scatter of the
+    gathered rows' gradients.  Nothing of size [B,N,K,*] is saved."""
+
+    @staticmethod
+    def forward(ctx, p1q, p2q, idx, w2d, bias, slope_pre, slope_post):
+        ctx.save_for_backward(p1q, p2q, idx, w2d, bias)
+        ctx.slopes = (float(slope_pre), float(slope_post))
+        d = p1q.shape[2]
+        zero_w = p1q.new_zeros((d, 3))
+        zero_b = p1q.new_zeros((d,))
+        xyz1 = p1q.new_zeros((p1q.shape[0], p1q.shape[1], 3))
+        xyz2 = p1q.new_zeros((p2q.shape[0], p2q.shape[1], 3))
+        return K.costvol_fused(xyz1, xyz2, p1q.detach(), p2q.detach(), idx, zero_w, zero_b, ctx.slopes[0],
+                               K.pack_weight(w2d.detach().contiguous(), 0, 0, 0), w2d.shape[0],
+                               None if bias is None else bias.detach(), ctx.slopes[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        p1q, p2q, idx, w2d, bias = ctx.saved_tensors
+        g1, grows, gw, gb = K.costvol_grad(p1q, p2q, idx, w2d.detach().contiguous(), None if bias is None else bias.detach(),
+                                           ctx.slopes[0], ctx.slopes[1], g.contiguous())
+        g2 = None
+        if ctx.needs_input_grad[1]:
+            off, perm = _csr(idx, p2q.shape[1])
+            g2 = K.scatter_rows_csr(grows, None, off, perm, p2q.shape[1], 1)
+        return g1, g2, None, gw, (gb if bias is not None else None), None, None
+
+
+USE_FUSED_COSTVOL_GRAD = os.environ.get("KDPC_COSTVOL_GRAD", "1") != "0"      # A/B: 0 = autograd over the unfused op chain
+
+
+def costvol_autograd_available(points1: torch.Tensor, idx: torch.Tensor, conv, slope_pre: float) -> bool:
+    w = conv.weight
+    return (USE_TC_TRAINING and USE_FUSED_COSTVOL_GRAD and points1.is_cuda and points1.dtype == torch.float32
+            and points1.shape[2] == 32 and idx.shape[2] == 32 and w.shape[0] == 32 and w.reshape(32, -1).shape[1] == 32
+            and 0.0 <= slope_pre < 1.0)
+
+
+def costvol_autograd(xyz1, xyz2, points1, points2, idx, pos, slope_pre: float, conv, slope_post: float) -> torch.Tensor:
+    """Differentiable max_k act(conv(act(p2[idx] + p1 + pos(xyz2[idx] - xyz1)))) for the training path.  The positional
+    layer is linear, so it is folded into the point features once per POINT by small differentiable ops
+    (p2q = p2 + pos_w xyz2, p1q = p1 + pos_b - pos_w xyz1: autograd un-folds their gradients) and the [B,N,K,*] part runs
+    as _CostVolFn."""
+    d = points1.shape[2]
+    pw = pos.weight.reshape(d, 3)
+    lin = linear_small_autograd if linear_small_autograd_available(xyz1, pw) else (lambda x, w, b: torch.nn.functional.linear(x, w, b))
+    p2q = points2 + lin(xyz2.contiguous(), pw, None)
+    p1q = points1 + pos.bias - lin(xyz1.contiguous(), pw, None)
+    w2d = conv.weight.reshape(conv.weight.shape[0], -1)
+    return _CostVolFn.apply(p1q.contiguous(), p2q.contiguous(), _as_i32(idx), w2d, conv.bias, slope_pre, slope_post)
+
+
 # ------------------------------------------------------------------- WeightNet (training path)
 class _WeightNetFn(torch.autograd.Function):
     """relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3) on the first 3 columns of ``rel`` (pointconv_util.py:204-215, bn=False):

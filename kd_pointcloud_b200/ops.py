@@ -720,6 +720,31 @@ def _costvol_fused(xyz1, xyz2, p1, p2, idx, pos_w, pos_b, slope_pre: float, wpac
     return out
 
 
+def _costvol_grad(p1q, p2q, idx, w, bias, slope_pre: float, slope_post: float, grad_out):
+    """(grad_p1q [B,S,D], grad_rows [B,S,K,D], grad_w [D',D], grad_b [D']) of the fused cost volume in its folded form."""
+    for t, nm in ((p1q, "p1q"), (p2q, "p2q"), (grad_out, "grad_out")):
+        _req(t, torch.float32, 3, nm)
+    _req(idx, torch.int32, 3, "idx")
+    _req(w, torch.float32, 2, "weight")
+    B, S, D = p1q.shape
+    N, K, Dout = p2q.shape[1], idx.shape[2], w.shape[0]
+    if grad_out.shape != (B, S, Dout) or w.shape[1] != D or p2q.shape[2] != D:
+        raise ValueError("kdpc: costvol_grad shape mismatch")
+    with _guard(p1q):
+        g1 = torch.empty_like(p1q)
+        grows = torch.empty((B, S, K, D), dtype=torch.float32, device=p1q.device)
+        gw = torch.empty_like(w)
+        gb = torch.empty((Dout,), dtype=torch.float32, device=p1q.device)
+        ws = torch.empty((_lib.lib().kdpc_costvol_grad_ws_bytes(),), dtype=torch.uint8, device=p1q.device)
+        _call("kdpc_costvol_grad", B, S, N, K, D, Dout, _p(p1q), _p(p2q), _p(idx), _p(w), _p(bias), float(slope_pre),
+              float(slope_post), _p(grad_out), _p(ws), _p(g1), _p(grows), _p(gw), _p(gb), _stream())
+    return g1, grows, gw, gb
+
+
+_register("costvol_grad(Tensor p1q, Tensor p2q, Tensor idx, Tensor w, Tensor? bias, float slope_pre, float slope_post, "
+          "Tensor grad_out) -> (Tensor, Tensor, Tensor, Tensor)", _costvol_grad,
+          lambda p1q, p2q, idx, w, b, s0, s1, g: (torch.empty_like(p1q), p1q.new_empty(tuple(idx.shape) + (p1q.shape[2],)),
+                                                  torch.empty_like(w), w.new_empty((w.shape[0],))))
 _register("pointconv_fused(Tensor cand_xyz, Tensor query_xyz, Tensor feats, Tensor idx, float[] wn_params, "
           "Tensor wpacked, int n_out, Tensor? scale, Tensor? shift, float slope, Tensor? order=None) -> Tensor",
           _pointconv_fused,

@@ -329,6 +329,12 @@ class CrossLayerLight(nn.Module):
                 and KF.fused_linear_available(points1, mlp[0].composed_module[0].weight, mlp[0].composed_module[0].bias, None)):
             return KF.fused_costvol(xyz1, xyz2, points1, points2, idx, pos, _slope(self.relu), mlp[0].composed_module[0],
                                     _slope(mlp[0].composed_module[2]))
+        if (needs_grad and FUSED_COSTVOL and isinstance(bn, nn.Identity) and points2.shape[2] == D and len(mlp) == 1
+                and _is_pointwise(mlp[0].composed_module[0]) and isinstance(mlp[0].composed_module[1], nn.Identity)
+                and KF.costvol_autograd_available(points1, idx, mlp[0].composed_module[0], _slope(self.relu))):
+            # training, 8192-point level: fused forward + recomputing arg-max backward (csrc/costvol_grad.cu)
+            return KF.costvol_autograd(xyz1, xyz2, points1, points2, idx, pos, _slope(self.relu), mlp[0].composed_module[0],
+                                       _slope(mlp[0].composed_module[2]))
         if isinstance(bn, nn.Identity) and D % 4 == 0 and points2.shape[2] == D and not needs_grad:
             x = K.costvol_pre(xyz1.contiguous(), xyz2.contiguous(), points1.contiguous(), points2.contiguous(), idx,
                               pos.weight.reshape(D, 3), pos.bias, _slope(self.relu))

@@ -323,3 +323,50 @@ def test_small_channel_linear_autograd_matches_torch():
             res.append((y.detach(), x.grad, w.grad, b.grad))
         for a, r in zip(res[0], res[1]):
             assert a.shape == r.shape and ((a - r).abs().max() / r.abs().max()).item() < 2e-5
+
+
+@pytest.mark.parametrize("B,N1,N2", [(2, 700, 650), (1, 4096, 4096)])
+def test_costvol_autograd_matches_fp64(B, N1, N2):
+    """Training path of the 8192-point cost volume (D = D' = K = 32): fused tcgen05 forward + the recomputing arg-max
+    backward (csrc/costvol_grad.cu) against fp64 autograd of the reference's op chain (pointconv_util.py:1826-1850);
+    every input and parameter gradient, run-to-run identical."""
+    from kd_pointcloud_b200 import functional as KF
+    torch.manual_seed(N1)
+    D = 32
+    xyz1 = (torch.rand(B, N1, 3, device=DEV) * 4).requires_grad_(True)
+    xyz2 = (torch.rand(B, N2, 3, device=DEV) * 4).requires_grad_(True)
+    p1 = torch.randn(B, N1, D, device=DEV, requires_grad=True)
+    p2 = torch.randn(B, N2, D, device=DEV, requires_grad=True)
+    idx = K.knn(xyz1.detach(), xyz2.detach(), 32)
+    pos = torch.nn.Conv2d(3, D, 1).to(DEV)
+    conv = torch.nn.Conv2d(D, D, 1).to(DEV)
+    go = torch.randn(B, N1, D, device=DEV)
+    params = [xyz1, xyz2, p1, p2, pos.weight, pos.bias, conv.weight, conv.bias]
+
+    def run():
+        for t in params:
+            t.grad = None
+        assert KF.costvol_autograd_available(p1, idx, conv, 0.1)
+        out = KF.costvol_autograd(xyz1, xyz2, p1, p2, idx, pos, 0.1, conv, 0.1)
+        out.backward(go)
+        return out.detach().clone(), [t.grad.detach().clone() for t in params]
+
+    out, grads = run()
+    dd = [t.detach().double().requires_grad_(True) for t in params]
+    x1, x2, q1, q2, pw, pb, cw, cb = dd
+    gi = idx.long()
+    bi = torch.arange(B, device=DEV).view(B, 1, 1)
+    rel = x2[bi, gi] - x1.unsqueeze(2)
+    x = q2[bi, gi] + q1.unsqueeze(2) + rel @ pw.reshape(D, 3).t() + pb
+    h = torch.where(x > 0, x, x * 0.1)
+    z = h @ cw.reshape(D, D).t() + cb
+    z = torch.where(z > 0, z, z * 0.1)
+    ref = z.max(dim=2)[0]
+    ref.backward(go.double())
+    assert _err(out, ref.detach()) < 2e-5
+    for name, g, r in zip(("xyz1", "xyz2", "p1", "p2", "pos.w", "pos.b", "conv.w", "conv.b"), grads, dd):
+        rg = r.grad.reshape(g.shape)
+        l2 = ((g.double() - rg).norm() / rg.norm().clamp_min(1e-30)).item()
+        assert l2 < 1e-4, (name, l2)
+    out2, grads2 = run()
+    assert torch.equal(out, out2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))
