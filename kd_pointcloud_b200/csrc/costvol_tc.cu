@@ -394,7 +394,7 @@ struct MaxKEpilogue {
         long long points;
         int pair_n;           // 0, or D' of the paired layout: accumulator columns 32 h .. 32 h + D' - 1 = row tile h of the iteration
     };
-    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int /*split*/, uint32_t t_acc,
+    __device__ __forceinline__ void tile(const Args &e, const GemmShape &g, long long tile, int split, uint32_t t_acc,
                                          int quarter, int lane) const {
         if (e.pair_n > 0) {                                       // eight warps: (quarter & 3) = point of the row tile, quarter >> 2 = row tile
             const int h = quarter >> 2;
@@ -402,6 +402,7 @@ struct MaxKEpilogue {
             return;
         }
         const long long pt = tile * (TILE_M / CV_K) + quarter;
+        const int n0 = g.nsplit ? split * g.n_pad : 0;            // split-N: this work item's first output column
         for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
             float v[32];
             tmem_ld_32x32(t_acc + (uint32_t)c0, v);               // lane = neighbour k, v[j] = channel c0+j
@@ -423,7 +424,7 @@ struct MaxKEpilogue {
                 }
             }
             const int mine = w[0];
-            const int col = c0 + lane;
+            const int col = n0 + c0 + lane;
             if (pt < e.points && col < g.n) {
                 float y = ord2f(mine);
                 if (e.bias) y += __ldg(e.bias + col);
@@ -464,9 +465,10 @@ struct MaxKEpilogue {
 using namespace kdpc;
 using namespace kdpc::tc;
 
+static int kdpc_costvol_colblocks = 1;
 static int kdpc_costvol_pairing = 1;
 /* A/B switch for measurements: 0 = one 128-row tile per pipeline iteration at every level (same results) */
-KDPC_API void kdpc_costvol_set_pairing(int on) { kdpc_costvol_pairing = on; }
+KDPC_API void kdpc_costvol_set_pairing(int on) { kdpc_costvol_pairing = on & 1; kdpc_costvol_colblocks = !(on & 2); }   // bit 1: no column blocks
 
 KDPC_API long long kdpc_costvol_fused_ws_bytes(int b, int s, int n, int d) {
     if (b <= 0 || s <= 0 || n <= 0 || d <= 0) return 0;
@@ -516,6 +518,19 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
         using P = CostVolAsyncProducer;
         GemmShape g = make_shape(points * CV_K, d_out, d, wpacked, P::kRawBytes, P::kLookahead + 1);
         if (g.stages < 2) g = make_shape(points * CV_K, d_out, d, wpacked, P::kRawBytes, P::kLookahead);   // lookahead 1
+        if (g.stages < 2 && kdpc_costvol_colblocks && g.n_pad > 128 && (g.n_pad & 127) == 0) {
+            // D' = 256 (the 256-point level): 64 KB weight stages leave no room for the staging ring.  Work items become
+            // (row tile, 128-column block): 32 KB weight stages, the asynchronous producer fits - at the price of building
+            // every A tile once per column block (the synchronous register-staged producer was 72 us per call for 2048 points)
+            g.w_n_pad = g.n_pad;
+            g.splits = g.n_pad / 128;
+            g.nsplit = 1;
+            g.n_pad = 128;
+            g.acc_stride = 128;
+            g.nacc_log2 = 2;
+            g.tmem_cols = 512;
+            g.stages = 2;                  // 2 x 64 KB of operand stages + 2 x 36 KB of staging: 201 KB
+        }
         if (g.stages >= 2) {
             float *p1q = reinterpret_cast<float *>(ws);
             float *p2q = p1q + points * d;
@@ -525,8 +540,9 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
             P::Args pa{p1q, p2q, idx, s, n, d, slope_pre, points};
             const size_t smem = smem_bytes(g.n_pad, g.stages, g.raw_bytes * g.raw_stages);
             auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
-            KDPC_ENSURE_SMEM(kern, SMEM_BUDGET + 1024);
-            const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
+            KDPC_ENSURE_SMEM(kern, 216 * 1024);
+            const long long work = g.num_tiles * (g.nsplit ? g.splits : 1);
+            const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
             kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
             KDPC_RETURN_LAST();
         }

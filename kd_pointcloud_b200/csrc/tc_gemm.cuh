@@ -156,7 +156,7 @@ static inline bool plan_split_n(GemmShape &g) {
     g.acc_stride = nb;
     g.nacc_log2 = 2;
     g.tmem_cols = 4 * nb;
-    g.stages = pick_stages(nb, 0);
+    g.stages = pick_stages(nb, g.raw_bytes * g.raw_stages);
     return true;
 }
 
@@ -243,16 +243,19 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             // the gather latency never sits on the critical path and no register holds data in flight.
             // (all bookkeeping is incremental 32-bit arithmetic: 64-bit divisions cost more than the conversion itself)
             const int RAW = g.raw_stages, LA = RAW - 1;                     // 2 or 3 raw buffers: lookahead 1 or 2
-            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles, nchunks = g.num_chunks;
+            // (split-N plans: the cursors walk WORK ITEMS = (tile, column block), tl() is an item's row tile)
+            const int nsp = g.nsplit ? g.splits : 1;
+            auto tl = [&](int item) { return nsp == 1 ? item : item / nsp; };
+            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles * nsp, nchunks = g.num_chunks;
             int total = ((ntiles - (int)blockIdx.x + tile_step - 1) / tile_step) * nchunks;       // iterations of this CTA
             // cursors: `ah` = the iteration being issued (i + LA), `nx` = the one after it (index prefetch), `cu` = converted
             int ah_tile = (int)blockIdx.x, ah_chunk = 0, nx_tile = ah_tile, nx_chunk = 0, cu_tile = ah_tile, cu_chunk = 0;
             auto step = [&](int &t, int &c) { if (++c == nchunks) { c = 0; t += tile_step; } };
             step(nx_tile, nx_chunk);
             int ah_slot = 0, issued = 0;
-            if constexpr (IW == 0) prod.prime(ah_tile, ptid);
+            if constexpr (IW == 0) prod.prime(tl(ah_tile), ptid);
             auto issue_next = [&]() {
-                prod.issue(ah_tile, ah_chunk, nx_tile < ntiles ? nx_tile : -1, raw_base + (size_t)ah_slot * g.raw_bytes,
+                prod.issue(tl(ah_tile), ah_chunk, nx_tile < ntiles ? tl(nx_tile) : -1, raw_base + (size_t)ah_slot * g.raw_bytes,
                            &raw_full[ah_slot], ptid);
                 step(ah_tile, ah_chunk);
                 step(nx_tile, nx_chunk);
@@ -265,7 +268,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             }
             int s = 0, cu_slot = 0;
             uint32_t ph = 0, raw_ph = 0;
-            const bool b_resident = g.wchunks == 1;               // one weight chunk: each stage's copy is loaded once
+            const bool b_resident = g.wchunks == 1 && nsp == 1;   // one weight chunk: each stage's copy is loaded once
             auto stamp = [&](int i, int ev) {                     // debug trace of CTA 0 (kdpc_tc_set_trace)
                 if (g.trace != nullptr && blockIdx.x == 0 && tid == 0 && i < 200) g.trace[i * 16 + ev] = clock64();
             };
@@ -283,12 +286,19 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
                 stamp(i, 3);
                 if (ptid == 0 && (!b_resident || i < g.stages)) {
                     mbar_expect_tx(&full_b[s], (uint32_t)bbytes);
-                    tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(b_resident ? 0 : cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    if (nsp > 1) {                                // rows (item % splits) * n_pad .. of the chunk: its hi and lo pieces
+                        const int nb = cu_tile - tl(cu_tile) * nsp;
+                        const unsigned char *src = g.wpacked + (size_t)(cu_chunk % g.wchunks) * (2 * g.w_n_pad * 128) + (size_t)nb * g.n_pad * 128;
+                        tma_load_1d(b_base + (size_t)s * bbytes, src, (uint32_t)bbytes / 2, &full_b[s]);
+                        tma_load_1d(b_base + (size_t)s * bbytes + bbytes / 2, src + (size_t)g.w_n_pad * 128, (uint32_t)bbytes / 2, &full_b[s]);
+                    } else {
+                        tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(b_resident ? 0 : cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
+                    }
                 }
                 mbar_wait(&raw_full[cu_slot], raw_ph);
                 stamp(i, 4);
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
-                prod.convert(cu_tile, cu_chunk, raw_base + (size_t)cu_slot * g.raw_bytes, a_hi, a_hi + A_PART_BYTES, ptid);
+                prod.convert(tl(cu_tile), cu_chunk, raw_base + (size_t)cu_slot * g.raw_bytes, a_hi, a_hi + A_PART_BYTES, ptid);
                 stamp(i, 5);
                 fence_async_smem();
                 __syncwarp();
@@ -377,17 +387,19 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             const int itid = tid - PW * 32;
             Producer prod(pa, g);
             const int RAW = g.raw_stages;
-            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles, nchunks = g.num_chunks;
+            const int nsp = g.nsplit ? g.splits : 1;              // (work items = (tile, column block), as in the producers)
+            auto tl = [&](int item) { return nsp == 1 ? item : item / nsp; };
+            const int tile_step = (int)gridDim.x, ntiles = (int)g.num_tiles * nsp, nchunks = g.num_chunks;
             const int total = ((ntiles - (int)blockIdx.x + tile_step - 1) / tile_step) * nchunks;
             int ah_tile = (int)blockIdx.x, ah_chunk = 0, nx_tile = ah_tile, nx_chunk = 0;
             auto step = [&](int &t, int &c) { if (++c == nchunks) { c = 0; t += tile_step; } };
             step(nx_tile, nx_chunk);
-            prod.prime(ah_tile, itid);
+            prod.prime(tl(ah_tile), itid);
             int slot = 0;
             uint32_t eph = 0;                                     // parity of the slot's previous hand-back
             for (int i = 0; i < total; ++i) {
                 if (i >= RAW) mbar_wait(&raw_empty[slot], eph);   // the converters are done with this slot's last use
-                prod.issue(ah_tile, ah_chunk, nx_tile < ntiles ? nx_tile : -1, raw_base + (size_t)slot * g.raw_bytes,
+                prod.issue(tl(ah_tile), ah_chunk, nx_tile < ntiles ? tl(nx_tile) : -1, raw_base + (size_t)slot * g.raw_bytes,
                            &raw_full[slot], itid);
                 step(ah_tile, ah_chunk);
                 step(nx_tile, nx_chunk);
@@ -436,7 +448,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
                 if (trm) g.trace[it * 16 + 8] = clock64();
                 mbar_wait(&full_a[s], ph);
                 if (trm) g.trace[it * 16 + 9] = clock64();
-                if (!(Producer::kAsync && g.wchunks == 1 && it >= (uint32_t)g.stages)) mbar_wait(&full_b[s], ph);   // (resident weights)
+                if (!(Producer::kAsync && g.wchunks == 1 && !g.nsplit && it >= (uint32_t)g.stages)) mbar_wait(&full_b[s], ph);   // (resident weights)
                 if (trm) g.trace[it * 16 + 10] = clock64();
                 fence_after_sync();
                 {
