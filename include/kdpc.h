@@ -149,6 +149,8 @@ int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const int *idx,
 
 /* group / group_query, pointconv_util.py:135-182, fused: out[b,s,k,:] =
  * [cand_xyz[idx]-query_xyz[s] (3), feats[idx] (D)].  feats may be NULL (d = 0). */
+/* A/B switch for measurements and tests: 0 = always the shared-memory staged kernel (same results). */
+void kdpc_group_concat_set_direct(int on);
 int kdpc_group_concat(int b, int n, int s, int k, int d, const float *cand_xyz, const float *query_xyz,
                       const float *feats, const int *idx, float *out, kdpc_stream_t stream);
 

@@ -84,6 +84,31 @@ __global__ void group_cm_direct_kernel(int c, int n, int sk, const float *__rest
 // VEC = 4: C % 4 == 0 and both bases 16-byte aligned -> one float4 per thread, consecutive threads
 // cover consecutive 16-byte pieces of the same output row (fully coalesced stores, row-contiguous
 // 128-bit loads).
+// 16-byte variant for < 2^32 pieces: four pieces per thread (a warp covers 4 x 512 contiguous output bytes), the four
+// index loads and then the four row loads in flight before the first store, 32-bit index arithmetic, streaming stores
+// (the one-piece-per-thread kernel below reached 50 % of the copy peak at B=8, N=8192, K=16, C=64).
+__global__ void __launch_bounds__(256)
+gather_rows4_kernel(unsigned total, unsigned n, unsigned m, unsigned cvec, const float4 *__restrict__ f,
+                    const int *__restrict__ idx, float4 *__restrict__ out) {
+    const unsigned base = blockIdx.x * 1024u + threadIdx.x;
+    unsigned src[4], cv[4], bb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned e = base + 256u * j;
+        const unsigned r = e / cvec;
+        cv[j] = e - r * cvec;
+        bb[j] = r / m;
+        src[j] = e < total ? (unsigned)__ldg(idx + r) : 0u;
+    }
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + 256u * j < total) v[j] = __ldg(f + ((size_t)bb[j] * n + src[j]) * cvec + cv[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + 256u * j < total) st_stream_f4(out + base + 256u * j, v[j]);
+}
+
 template <int VEC>
 __global__ void gather_rows_kernel(long long total, int n, int m, int cvec, const float *__restrict__ f,
                                    const int *__restrict__ idx, float *__restrict__ out) {
@@ -162,6 +187,45 @@ group_concat_kernel(long long rows, int n, int s, int k, int d, const float *__r
     const float4 *s4 = reinterpret_cast<const float4 *>(stage);
     for (int e = tid; e < tot4; e += GC_THREADS) st_stream_f4(o4 + e, s4[e]);
     for (int e = (tot4 << 2) + tid; e < tot; e += GC_THREADS) out[o0 + e] = stage[e];
+}
+
+// Warp-per-row variant: lanes walk the row in steps of 32 floats - coalesced 128-byte loads of the feature row, coalesced
+// stores of the output row (which starts at an arbitrary 4-byte offset: W is odd), lanes 0..2 produce the relative
+// coordinates.  No shared-memory assembly, no CTA barriers; four rows per warp in flight (eight: slower).  (Measured and rejected: thread =
+// one 16-byte piece of the flat output with its four floats located by division - instruction-bound, 180 us against the
+// staged kernel's 115 us at B=8, N=8192, K=9, D=128.)
+constexpr int GCR = 4;              // rows per warp (independent loads in flight)
+__global__ void __launch_bounds__(256)
+group_concat_rows_kernel(unsigned rows, unsigned n, unsigned s, unsigned k, unsigned d, const float *__restrict__ cand_xyz,
+                         const float *__restrict__ query_xyz, const float *__restrict__ feats, const int *__restrict__ idx,
+                         float *__restrict__ out) {
+    const unsigned lane = threadIdx.x & 31u, warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    const unsigned w = 3u + d;
+    const unsigned r0 = warp * GCR;
+    if (r0 >= rows) return;
+    unsigned src[GCR], bs[GCR];
+    size_t cand[GCR];
+#pragma unroll
+    for (int j = 0; j < GCR; ++j) {
+        const unsigned r = min(r0 + j, rows - 1u);
+        bs[j] = r / k;
+        src[j] = (unsigned)__ldg(idx + r);
+        cand[j] = (size_t)(bs[j] / s) * n + src[j];
+    }
+    for (unsigned c0 = 0; c0 < d; c0 += 32u) {
+        float v[GCR];
+#pragma unroll
+        for (int j = 0; j < GCR; ++j) v[j] = c0 + lane < d ? __ldg(feats + cand[j] * d + c0 + lane) : 0.f;
+#pragma unroll
+        for (int j = 0; j < GCR; ++j)
+            if (r0 + j < rows && c0 + lane < d) __stcs(out + (size_t)(r0 + j) * w + 3u + c0 + lane, v[j]);
+    }
+    if (lane < 3u) {
+#pragma unroll
+        for (int j = 0; j < GCR; ++j)
+            if (r0 + j < rows)
+                out[(size_t)(r0 + j) * w + lane] = __ldg(cand_xyz + cand[j] * 3 + lane) - __ldg(query_xyz + (size_t)bs[j] * 3 + lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -255,6 +319,12 @@ KDPC_API int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const 
     const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
     if (vec) {
         const long long total = (long long)b * m * (c / 4);
+        if (total + 1024 < (1ll << 32)) {
+            gather_rows4_kernel<<<(unsigned)div_up_ll(total, 1024), 256, 0, st>>>(
+                (unsigned)total, (unsigned)n, (unsigned)m, (unsigned)(c / 4), reinterpret_cast<const float4 *>(f), idx,
+                reinterpret_cast<float4 *>(out));
+            KDPC_RETURN_LAST();
+        }
         gather_rows_kernel<4><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, m, c / 4, f, idx, out);
     } else {
         const long long total = (long long)b * m * c;
@@ -263,6 +333,9 @@ KDPC_API int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const 
     KDPC_RETURN_LAST();
 }
 
+static int kdpc_group_concat_direct = 1;     // (0: always the staged kernel; tests compare the two)
+extern "C" __attribute__((visibility("default"))) void kdpc_group_concat_set_direct(int on) { kdpc_group_concat_direct = on; }
+
 KDPC_API int kdpc_group_concat(int b, int n, int s, int k, int d, const float *cand_xyz, const float *query_xyz,
                                const float *feats, const int *idx, float *out, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(cand_xyz && query_xyz && idx && out && b > 0 && n > 0 && s > 0 && k > 0 && d >= 0);
@@ -270,6 +343,11 @@ KDPC_API int kdpc_group_concat(int b, int n, int s, int k, int d, const float *c
     if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return KDPC_EINVAL;
     if (d > 0 && (d % 4 == 0) && (reinterpret_cast<uintptr_t>(feats) % 16) != 0) return KDPC_EINVAL;
     const long long rows = (long long)b * s * k;
+    if (d >= 32 && rows + 1024 < (1ll << 32) && kdpc_group_concat_direct) {
+        group_concat_rows_kernel<<<(unsigned)div_up_ll(rows, 8 * GCR), 256, 0, to_stream(stream)>>>(
+            (unsigned)rows, (unsigned)n, (unsigned)s, (unsigned)k, (unsigned)d, cand_xyz, query_xyz, feats, idx, out);
+        KDPC_RETURN_LAST();
+    }
     const size_t smem = (size_t)GC_ROWS * (3 + d) * sizeof(float);
     if (smem > 200 * 1024) return KDPC_EUNSUPPORTED;
     KDPC_ENSURE_SMEM(group_concat_kernel, 200 * 1024);

@@ -234,6 +234,17 @@ def test_gather_rows_and_group_concat_exact(c):
     rel = O.index_points_group(xyz, idx) - q.view(2, 150, 1, 3)
     assert torch.equal(gc, torch.cat([rel, ref], dim=-1))
     assert torch.equal(KF.group_concat(xyz.to(DEV), q.to(DEV), None, idx.to(DEV)).cpu(), rel)
+    # the shared-memory staged kernel (rows * W not a multiple of 4, or >= 2^32 floats) gives the same bits
+    from kd_pointcloud_b200 import _lib
+    _lib.lib().kdpc_group_concat_set_direct(0)
+    try:
+        staged = KF.group_concat(xyz.to(DEV), q.to(DEV), feats.to(DEV), idx.to(DEV)).cpu()
+    finally:
+        _lib.lib().kdpc_group_concat_set_direct(1)
+    assert torch.equal(gc, staged)
+    idx9 = torch.randint(0, 900, (2, 150, 9), generator=g).int()           # K = 9: pieces straddle rows at every offset
+    gc9 = KF.group_concat(xyz.to(DEV), q.to(DEV), feats.to(DEV), idx9.to(DEV)).cpu()
+    assert torch.equal(gc9, torch.cat([O.index_points_group(xyz, idx9) - q.view(2, 150, 1, 3), O.index_points_group(feats, idx9)], dim=-1))
 
 
 def test_group_concat_backward_is_deterministic_and_correct():
