@@ -284,7 +284,7 @@ int kdpc_spatial_sort_order_stride(int n);
  * ws: kdpc_costvol_fused_ws_bytes(b,s,n,d) bytes (16-byte aligned) for the per-point features with the positional
  * encoding folded in; NULL selects the variant that evaluates the encoding per neighbour (no workspace). */
 /* Backward of kdpc_costvol_fused in its folded form (reference: autograd through CrossLayerLight.cross, pointconv_util.py:1826-1850,
- * by loss.backward(), distilTrain.py:180), d = d_out = k = 32:  out[i,c] = act2(max_k (W act1(p2q[idx[i,k]] + p1q[i]) + bias)[c])
+ * by loss.backward(), distilTrain.py:180), k = 32, d = d_out = 32 or 64:  out[i,c] = act2(max_k (W act1(p2q[idx[i,k]] + p1q[i]) + bias)[c])
  * with p1q = points1 + pos_b - pos_w xyz1 and p2q = points2 + pos_w xyz2 (the caller folds and un-folds the positional layer).
  * One warp per point recomputes the row block and lets the gradient of out[i,c] through to the ONE neighbour that attains the
  * maximum (the first one, like torch.max).  grad_p1q [b,s,d]; grad_rows [b*s*k, d] = gradient of every gathered p2q row, to be

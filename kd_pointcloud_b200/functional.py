@@ -681,7 +681,7 @@ def fused_costvol(xyz1, xyz2, p1, p2, idx, pos, slope_pre: float, conv, slope_po
 
 
 class _CostVolFn(torch.autograd.Function):
-    """Fused cost-volume half in its folded form, out = act2(max_k(W act1(p2q[idx] + p1q) + b)) (D = D' = K = 32):
+    """Fused cost-volume half in its folded form, out = act2(max_k(W act1(p2q[idx] + p1q) + b)) (K = 32, D = D' = 32 or 64):
     forward = the tcgen05 inference kernel (costvol_tc.cu), backward = ONE recomputing kernel in which only the arg-max
     neighbour of every (point, channel) receives a gradient (costvol_grad.cu) + the deterministic CSR scatter of the
     gathered rows' gradients.  Nothing of size [B,N,K,*] is saved."""
@@ -716,8 +716,9 @@ USE_FUSED_COSTVOL_GRAD = os.environ.get("KDPC_COSTVOL_GRAD", "1") != "0"      # 
 
 def costvol_autograd_available(points1: torch.Tensor, idx: torch.Tensor, conv, slope_pre: float) -> bool:
     w = conv.weight
+    d = points1.shape[2]
     return (USE_TC_TRAINING and USE_FUSED_COSTVOL_GRAD and points1.is_cuda and points1.dtype == torch.float32
-            and points1.shape[2] == 32 and idx.shape[2] == 32 and w.shape[0] == 32 and w.reshape(32, -1).shape[1] == 32
+            and d in (32, 64) and idx.shape[2] == 32 and w.shape[0] == d and w.reshape(d, -1).shape[1] == d
             and 0.0 <= slope_pre < 1.0)
 
 

@@ -325,14 +325,13 @@ def test_small_channel_linear_autograd_matches_torch():
             assert a.shape == r.shape and ((a - r).abs().max() / r.abs().max()).item() < 2e-5
 
 
-@pytest.mark.parametrize("B,N1,N2", [(2, 700, 650), (1, 4096, 4096)])
-def test_costvol_autograd_matches_fp64(B, N1, N2):
-    """Training path of the 8192-point cost volume (D = D' = K = 32): fused tcgen05 forward + the recomputing arg-max
+@pytest.mark.parametrize("B,N1,N2,D", [(2, 700, 650, 32), (1, 4096, 4096, 32), (2, 515, 700, 64), (1, 2048, 2048, 64)])
+def test_costvol_autograd_matches_fp64(B, N1, N2, D):
+    """Training path of the 8192- and 2048-point cost volumes (K = 32, D = D' = 32 / 64): fused tcgen05 forward + the recomputing arg-max
     backward (csrc/costvol_grad.cu) against fp64 autograd of the reference's op chain (pointconv_util.py:1826-1850);
     every input and parameter gradient, run-to-run identical."""
     from kd_pointcloud_b200 import functional as KF
     torch.manual_seed(N1)
-    D = 32
     xyz1 = (torch.rand(B, N1, 3, device=DEV) * 4).requires_grad_(True)
     xyz2 = (torch.rand(B, N2, 3, device=DEV) * 4).requires_grad_(True)
     p1 = torch.randn(B, N1, D, device=DEV, requires_grad=True)
