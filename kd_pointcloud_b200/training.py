@@ -109,9 +109,13 @@ def make_capturable_adam(params, lr: float = 1e-3, **kw) -> torch.optim.Adam:
     after capture: ``set_lr`` / an in-place scheduler update changes what the captured kernels read."""
     params = list(params)
     dev = params[0].device
-    # torch's FUSED implementation: one multi-tensor kernel over the 226 parameter tensors (the default foreach path was
-    # ~2 ms of a 36 ms step: a dozen elementwise launches over every tensor list); same update rule
-    kw.setdefault("fused", True)
+    # torch's default (foreach) implementation.  Its `fused=True` variant is ~1 ms faster per step but gave DIFFERENT updates
+    # with a tensor learning rate on this torch build (tools/cmp_adam.py: the loss falls 391 -> 379 -> 369 instead of
+    # 391 -> 339 -> 286 from the same weights and gradients), and an explicit fused=False silently selects the per-tensor
+    # loop (+4 ms): leave both unset unless KDPC_ADAM_FUSED=1 asks for the experiment.
+    import os
+    if os.environ.get("KDPC_ADAM_FUSED", "0") == "1":
+        kw.setdefault("fused", True)
     return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=dev), capturable=True, **kw)
 
 
