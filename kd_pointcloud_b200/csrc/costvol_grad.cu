@@ -90,13 +90,16 @@ costvol_grad_kernel(long long points, int s, int n, const float *__restrict__ p1
         for (int d = 0; d < D; ++d) dh[d] = 0.f;
         auto channel = [&](const int c) {
             // z[k, c] = b[c] + <W[c, :], h[k, :]> (weight row broadcast from shared memory)
-            float z = sb[c];
+            float z0 = sb[c], z1 = 0.f, z2 = 0.f, z3 = 0.f;       // four interleaved partial sums: a quarter of the chain latency
 #pragma unroll
             for (int q = 0; q < D / 4; ++q) {
                 const float4 t = *reinterpret_cast<const float4 *>(sw + c * D + 4 * q);
-                z = fmaf(t.x, h[4 * q], z); z = fmaf(t.y, h[4 * q + 1], z);
-                z = fmaf(t.z, h[4 * q + 2], z); z = fmaf(t.w, h[4 * q + 3], z);
+                z0 = fmaf(t.x, h[4 * q], z0); z1 = fmaf(t.y, h[4 * q + 1], z1);
+                z2 = fmaf(t.z, h[4 * q + 2], z2); z3 = fmaf(t.w, h[4 * q + 3], z3);
             }
+            const float z = (z0 + z1) + (z2 + z3);
+            // (Measured and rejected: deferring the arg-max lane's dh += g W[c, :] until after the loop, each lane walking only
+            // its own channels over a row-padded copy of W: -3 % at D = 32, and at D = 64 the copy costs the second resident CTA.)
             const int zo = cg_f2ord(z);
             const int m = __reduce_max_sync(0xffffffffu, zo);
             const int ks = __ffs(__ballot_sync(0xffffffffu, zo == m)) - 1;                   // first maximal neighbour
