@@ -284,6 +284,25 @@ def kernel_rooflines(torch, dev, B, hbm_peak, tc_peak):
     t = timeit(lambda: K.fps(xyz, 2048), iters=3)
     out["fps_8192_2048"] = {"shape": f"B={B} 8192->2048", "sec": t, "us_per_iter": t / 2047 * 1e6,
                             "bytes": B * (12 * N + 4 * 2048), "gbs": B * (12 * N + 4 * 2048) / t / 1e9}
+    # ---- training path (configs[3]/[4]): aggregation backward, weight gradient, arg-max cost-volume backward
+    grouped = K.group_concat(xyz, xyz, feats, idx9)
+    wn_out = torch.rand(B, N, Kn, 16, device=dev)
+    gagg = torch.randn(B, N, (D + 3) * 16, device=dev)
+    t = timeit(lambda: K.pointconv_agg_grad(grouped, wn_out, gagg, True, True), iters=4)
+    alg = 4 * B * N * (2 * Kn * (D + 3) + 2 * Kn * 16 + 16 * (D + 3))
+    out["pointconv_agg_grad"] = {"shape": f"rows={B * N} K={Kn} C={D + 3}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    del grouped, wn_out, gagg
+    dy, xr = torch.randn(B * N * 32, 32, device=dev), torch.randn(B * N * 32, 32, device=dev)
+    t = timeit(lambda: K.linear_dw(dy, xr, True), iters=4)
+    alg = 4 * B * N * 32 * 64
+    out["linear_dw"] = {"shape": f"M={B * N * 32} N=32 K=32", "bytes": alg, "sec": t, "gbs": alg / t / 1e9}
+    del dy, xr
+    w32 = torch.randn(Dc, Dc, device=dev) / Dc ** 0.5
+    gcv = torch.randn(B, N, Dc, device=dev)
+    t = timeit(lambda: K.costvol_grad(p1, p2, idx32, w32, pb, 0.1, 0.1, gcv), iters=4)
+    alg = 4 * B * N * (4 * Dc + 32 + 32 * Dc)
+    out["costvol_grad"] = {"shape": f"B={B} N={N} K=32 D={Dc}", "bytes": alg, "sec": t, "gbs": alg / t / 1e9,
+                           "note": "recomputing arg-max backward: FMA / latency bound, not HBM"}
     for k, v in out.items():
         v["frac_hbm"] = v["gbs"] / hbm_peak
     return out

@@ -139,6 +139,9 @@ int kdpc_spatial_reorder(int b, int n, const float *xyz, const void *parent_ws, 
 /* Exact kNN between two sorted clouds by best-first search over candidate tiles with a conservative
  * distance bound (knn_bf.cu).  direct = 0: square_distance rounding (knn_point); direct = 1: the
  * pointnet2 kernels' (dx^2+dy^2+dz^2) rounding (three_nn).  Output rows are in ORIGINAL query order. */
+/* K <= 4 with >= 64 queries per SM: one thread per query, 32 Morton-consecutive queries share one walk over the candidate
+ * tiles (default 1); 0 = one warp per query as for larger K.  Same results, bit for bit. */
+void kdpc_knn_set_few(int on);
 int kdpc_knn_sorted(int b, int s, int n, int k, int direct, const void *query_sorted, const void *cand_sorted,
                     int *idx32, long long *idx64, float *dist, kdpc_stream_t stream);
 

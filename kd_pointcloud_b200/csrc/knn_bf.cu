@@ -459,6 +459,115 @@ knn_bf_kernel(int s, int n, int k, int qpw, const void *__restrict__ qws, const 
     }
 }
 
+// ---- 2b. K <= 4 (3-NN of the warping / upsampling layers): one THREAD per query ----------------------------------
+// With three neighbours a whole warp per query spends its time on list upkeep and tile ranking, not on distances.  Here
+// a warp owns 32 Morton-consecutive queries and walks the candidate tiles ONCE for all of them: tiles are ranked by the
+// lower bound between the tile box and the WARP's query box (lanes hold KEYS tile keys each, redux.min pops the nearest),
+// a tile's 64 points are staged in shared memory and every lane tests all of them against its own query (broadcast
+// LDS.128, the K best as sorted 64-bit (distance, index) keys in registers), and the walk stops at the first tile whose
+// bound exceeds the LARGEST K-th distance of the 32 lanes.  More tiles per query than the per-query walk (~14 instead of
+// ~6), ~1/8 of the instructions per candidate; same (distance, index) order, so the results are bit-identical.
+constexpr int FEW_WARPS = 4, FEW_KMAX = 4;
+
+template <int MODE, int KEYS>
+__global__ void __launch_bounds__(FEW_WARPS * 32)
+knn_few_kernel(int s, int n, int k, const void *__restrict__ qws, const void *__restrict__ cws, int *__restrict__ idx32,
+               long long *__restrict__ idx64, float *__restrict__ dist_out) {
+    __shared__ float4 tp[FEW_WARPS][BF_TILE];
+    __shared__ int ti[FEW_WARPS][BF_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const SortedCloud Q = sorted_cloud_at(const_cast<void *>(qws), b, s);
+    const SortedCloud C = sorted_cloud_at(const_cast<void *>(cws), b, n);
+    const int ntiles = (n + BF_TILE - 1) / BF_TILE;
+    const int qpos = (blockIdx.x * FEW_WARPS + warp) * 32 + lane;
+    if ((blockIdx.x * FEW_WARPS + warp) * 32 >= s) return;             // whole warp beyond the cloud
+    const bool valid = qpos < s;
+    const float4 q = __ldg(Q.p4 + (valid ? qpos : s - 1));             // (idle lanes repeat the last query: the box stays tight)
+    // the warp's query box and largest |q|^2
+    float lo[3] = {q.x, q.y, q.z}, hi[3] = {q.x, q.y, q.z}, qqmax = q.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        qqmax = fmaxf(qqmax, __shfl_xor_sync(0xffffffffu, qqmax, o));
+    }
+    unsigned keys[KEYS];
+#pragma unroll
+    for (int e = 0; e < KEYS; ++e) {
+        const int t = e * 32 + lane;
+        keys[e] = BF_NONE;
+        if (t < ntiles) {
+            const float4 bl = __ldg(C.boxes + 2 * t), bh = __ldg(C.boxes + 2 * t + 1);
+            const float dx = fmaxf(0.f, fmaxf(bl.x - hi[0], lo[0] - bh.x));
+            const float dy = fmaxf(0.f, fmaxf(bl.y - hi[1], lo[1] - bh.y));
+            const float dz = fmaxf(0.f, fmaxf(bl.z - hi[2], lo[2] - bh.z));
+            const float lb = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - BF_MARGIN * (qqmax + bl.w);
+            keys[e] = lb > 0.f ? ((__float_as_uint(lb) & 0xffffff00u) | (unsigned)t) : (unsigned)t;
+        }
+    }
+    unsigned long long best[FEW_KMAX];
+#pragma unroll
+    for (int j = 0; j < FEW_KMAX; ++j) best[j] = BF_EMPTY;
+    float tau = INFINITY;                                               // this lane's K-th distance so far
+    while (true) {
+        unsigned cur = keys[0];
+#pragma unroll
+        for (int e = 1; e < KEYS; ++e) cur = min(cur, keys[e]);
+        cur = __reduce_min_sync(0xffffffffu, cur);
+        if (cur == BF_NONE) break;
+#pragma unroll
+        for (int e = 0; e < KEYS; ++e) keys[e] = keys[e] == cur ? BF_NONE : keys[e];
+        // largest K-th distance of the warp (taus are >= -tiny or +inf: compare through the order-preserving map)
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, (unsigned)(make_key(tau, 0) >> 32));
+        if (cur >= 256u && __uint_as_float(cur & 0xffffff00u) > key_dist((unsigned long long)tmax << 32)) break;
+        const int t = (int)(cur & 0xffu);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = t * BF_TILE + h * 32 + lane;
+            const bool v = i < n;
+            // slots beyond the cloud: a point at infinity (distance +inf in either formula), index INT_MAX
+            tp[warp][h * 32 + lane] = v ? __ldg(C.p4 + i) : (MODE == 0 ? make_float4(0.f, 0.f, 0.f, INFINITY) : make_float4(INFINITY, 0.f, 0.f, 0.f));
+            ti[warp][h * 32 + lane] = v ? __ldg(C.sidx + i) : 0x7fffffff;
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int j = 0; j < BF_TILE; ++j) {
+            const float4 c = tp[warp][j];
+            const float d = MODE == 0 ? expansion_dist(q.x, q.y, q.z, q.w, c.x, c.y, c.z, c.w)
+                                      : direct_dist(q.x - c.x, q.y - c.y, q.z - c.z);
+            if (d <= tau) {                                             // (ties on the distance: the index decides below)
+                unsigned long long x = make_key(d, ti[warp][j]);
+#pragma unroll
+                for (int r = 0; r < FEW_KMAX; ++r) {
+                    if (r < k) {
+                        const unsigned long long lo64 = x < best[r] ? x : best[r];
+                        x = x < best[r] ? best[r] : x;
+                        best[r] = lo64;
+                    }
+                }
+                tau = key_dist(best[k - 1]);
+            }
+        }
+    }
+    if (valid) {
+        const int qorig = __ldg(Q.sidx + qpos);
+        const size_t o = ((size_t)b * s + qorig) * k;
+#pragma unroll
+        for (int r = 0; r < FEW_KMAX; ++r) {
+            if (r < k) {
+                if (idx32) idx32[o + r] = key_idx(best[r]);
+                if (idx64) idx64[o + r] = key_idx(best[r]);
+                if (dist_out) dist_out[o + r] = key_dist(best[r]);
+            }
+        }
+    }
+}
+
 static inline int next_pow2(int n) {
     int p = 64;
     while (p < n) p <<= 1;
@@ -483,9 +592,25 @@ static int launch_sort(int b, int n, const float *xyz, void *ws, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
+static int kdpc_knn_few = 1;           // (0: always one warp per query; tests compare the two)
+
 template <int MODE>
 static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cws, int *idx32, long long *idx64,
                      float *dist, cudaStream_t st) {
+    const int ntiles_ = (n + BF_TILE - 1) / BF_TILE;
+    if (k <= FEW_KMAX && kdpc_knn_few && (long long)b * s >= 64LL * device_sms()) {
+        // few neighbours, enough queries to fill the machine with one thread each: shared tile walk per warp
+        dim3 grid((s + FEW_WARPS * 32 - 1) / (FEW_WARPS * 32), b);
+#define KDPC_FEW_CASE(KEYS) \
+        if (ntiles_ <= 32 * KEYS) { \
+            knn_few_kernel<MODE, KEYS><<<grid, FEW_WARPS * 32, 0, st>>>(s, n, k, qws, cws, idx32, idx64, dist); \
+            return (int)cudaGetLastError(); }
+        KDPC_FEW_CASE(1)
+        KDPC_FEW_CASE(2)
+        KDPC_FEW_CASE(4)
+        KDPC_FEW_CASE(8)
+#undef KDPC_FEW_CASE
+    }
     // consecutive (Morton-adjacent) queries per warp: up to BF_QPW, fewer when the call is small so that the
     // machine still gets ~48 warps per SM
     int qpw = (int)(((long long)b * s) / (device_sms() * 48));
@@ -508,6 +633,9 @@ static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cw
 }  // namespace kdpc
 
 using namespace kdpc;
+
+/* A/B switch for measurements and tests: 0 = K <= 4 searches also run one warp per query (same results). */
+KDPC_API void kdpc_knn_set_few(int on) { kdpc::kdpc_knn_few = on; }
 
 KDPC_API int kdpc_spatial_sort_order_offset(int n) {
     const size_t nt = (size_t)(n + BF_TILE - 1) / BF_TILE;

@@ -88,7 +88,8 @@ def test_knn_bit_exact_indices_and_distances(s, n, k, mode):
 @pytest.mark.parametrize("b,s,n,k,mode", [
     (8, 8192, 8192, 32, "ft3d"), (4, 8192, 8192, 32, "dup"), (4, 8192, 8192, 9, "cm"), (2, 8192, 8192, 3, "grid"),
     (4, 2048, 8192, 16, "kitti"), (4, 8192, 2048, 3, "ft3d"), (3, 1000, 5000, 10, "dup"), (2, 16384, 16384, 16, "ft3d"),
-    (2, 300, 256, 32, "grid"), (2, 257, 999, 5, "cm"),
+    (2, 300, 256, 32, "grid"), (2, 257, 999, 5, "cm"), (8, 8192, 8192, 3, "dup"), (8, 8192, 8192, 1, "cm"), (8, 2048, 8192, 4, "grid"),
+    (5, 1999, 3001, 3, "kitti"), (8, 8192, 2048, 2, "dup"),
 ])
 def test_knn_pruned_search_equals_brute_force(b, s, n, k, mode):
     """Size-independent property at full size: the best-first tile-pruned search (sorted clouds, conservative
@@ -102,6 +103,13 @@ def test_knn_pruned_search_equals_brute_force(b, s, n, k, mode):
     # cross-frame queries far from the candidates (warped clouds): bounds stay conservative
     far = (query + torch.tensor([3.0, -2.0, 5.0], device=DEV)).contiguous()
     assert torch.equal(K.knn(far, cand, k), K.knn_bruteforce(far, cand, k))
+    if k <= 4:          # one thread per query with a shared tile walk per warp (>= 64 queries per SM) == one warp per query
+        from kd_pointcloud_b200 import _lib
+        _lib.lib().kdpc_knn_set_few(0)
+        try:
+            assert torch.equal(K.knn_sorted(qs, cs, b, s, n, k), brute)
+        finally:
+            _lib.lib().kdpc_knn_set_few(1)
 
 
 def test_knn_pruned_degenerate_clouds():
