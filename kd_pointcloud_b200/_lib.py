@@ -152,8 +152,8 @@ def lib() -> ctypes.CDLL:
         L.kdpc_flow_metrics_workspace_bytes.argtypes = []
         L.kdpc_knn_set_few.restype = None
         L.kdpc_knn_set_few.argtypes = [c_int]
-        if os.environ.get("KDPC_KNN_FEW", "1") == "0":           # A/B switch for measurements
-            L.kdpc_knn_set_few(0)
+        if os.environ.get("KDPC_KNN_FEW", "0") == "1":           # A/B switch for measurements (default off: slower)
+            L.kdpc_knn_set_few(1)
         L.kdpc_group_concat_set_direct.restype = None
         L.kdpc_group_concat_set_direct.argtypes = [c_int]
         L.kdpc_costvol_grad_ws_bytes.restype = c_longlong

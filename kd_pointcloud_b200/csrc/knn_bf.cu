@@ -592,7 +592,7 @@ static int launch_sort(int b, int n, const float *xyz, void *ws, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
-static int kdpc_knn_few = 1;           // (0: always one warp per query; tests compare the two)
+static int kdpc_knn_few = 0;           // (1: K <= 4 by knn_few_kernel - measured 4x SLOWER than one warp per query, kept for the record; tests compare the two)
 
 template <int MODE>
 static int launch_bf(int b, int s, int n, int k, const void *qws, const void *cws, int *idx32, long long *idx64,

@@ -105,11 +105,11 @@ def test_knn_pruned_search_equals_brute_force(b, s, n, k, mode):
     assert torch.equal(K.knn(far, cand, k), K.knn_bruteforce(far, cand, k))
     if k <= 4:          # one thread per query with a shared tile walk per warp (>= 64 queries per SM) == one warp per query
         from kd_pointcloud_b200 import _lib
-        _lib.lib().kdpc_knn_set_few(0)
+        _lib.lib().kdpc_knn_set_few(1)
         try:
             assert torch.equal(K.knn_sorted(qs, cs, b, s, n, k), brute)
         finally:
-            _lib.lib().kdpc_knn_set_few(1)
+            _lib.lib().kdpc_knn_set_few(0)
 
 
 def test_knn_pruned_degenerate_clouds():
