@@ -121,7 +121,12 @@ struct CostVolAsyncProducer {
     // 4 extra warps do nothing but issue the gathers (a warp-level LDGSTS costs ~28 cycles of load/store-unit time and
     // blocks its warp meanwhile: issued by the converting warps it took 1000-1350 of the 2250-2650 cycles of a pipeline
     // iteration, tools/trace_costvol.py); the 8 producer warps only convert
-    static constexpr int kIssuerWarps = 4;
+#ifndef KDPC_CV_IW
+#define KDPC_CV_IW 4
+#endif
+    static constexpr int kIssuerWarps = KDPC_CV_IW;
+    static constexpr int RSTEP = 32 * kIssuerWarps / 8;          // thread t serves rows (t >> 3) + RSTEP j
+    static constexpr int JPP = CV_K / RSTEP;                     // consecutive j that belong to one point
     static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
     static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
     static constexpr int kRawBytes = (TILE_M + TILE_M / CV_K) * ROW_PITCH;     // 128 neighbour rows + 4 point rows
@@ -163,10 +168,10 @@ struct CostVolAsyncProducer {
         const unsigned b0 = pt0 / s, left = (b0 + 1u) * s - pt0;  // points of the tile before the next cloud starts
         const unsigned last_pt = (unsigned)(g.m >> 5) - 1u;
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) {                           // tile row (t >> 3) + 16 j belongs to point pt0 + (j >> 1)
-            const unsigned jj = min((unsigned)(j >> 1), last_pt - pt0);  // (rows past the end repeat the last point's last row)
+        for (int j = 0; j < RPT; ++j) {                           // tile row (t >> 3) + RSTEP j belongs to point pt0 + j / JPP
+            const unsigned jj = min((unsigned)(j / JPP), last_pt - pt0);  // (rows past the end repeat the last point's last row)
             const unsigned b = b0 + (jj >= left ? (jj - left) / s + 1u : 0u);
-            nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + 16 * j));
+            nbr[j] = __ldg(a.idx + row_of(tile, (ptid >> 3) + RSTEP * j));
             cloud_off[j] = b * (unsigned)a.n;
         }
         const unsigned pt = min(pt0 + (unsigned)((ptid >> 5) & 3), last_pt);
@@ -195,12 +200,12 @@ struct CostVolAsyncProducer {
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const uint32_t row_off = (cloud_off[j] + (uint32_t)nbr[j]) * (uint32_t)a.d;
-            if (q < ppr) cp_async_16(dst + j * (16 * ROW_PITCH), src + row_off);
-            if (q + 8 < ppr) cp_async_16(dst + j * (16 * ROW_PITCH) + 128, src + row_off + 32);
+            if (q < ppr) cp_async_16(dst + j * (RSTEP * ROW_PITCH), src + row_off);
+            if (q + 8 < ppr) cp_async_16(dst + j * (RSTEP * ROW_PITCH) + 128, src + row_off + 32);
         }
         {                                                        // the 4 points' own rows, one 16-byte piece per lane
             const int k = ptid & 31;
-            if (k < ppr)
+            if (k < ppr && ptid < 128)
                 cp_async_16(smem_u32(raw + (TILE_M + ((ptid >> 5) & 3)) * ROW_PITCH) + k * 16, a.p1q + pt_off + c0 + k * 4);
         }
         cp_async_mbar_arrive(bar);                               // arrives once this thread's copies have landed
