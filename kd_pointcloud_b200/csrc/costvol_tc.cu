@@ -262,12 +262,13 @@ struct CostVolAsyncProducer {
 // Measured and rejected for the gathers (tools/gather4_probe.cu, same box): cp.async.bulk.tensor tile::gather4 (one
 // TMA request per 4 rows) - the TMA unit takes ~150 cycles per request, 5x the LDGSTS cost per row; plain LDG.128 ->
 // registers -> STS.128 from the issuer warps - halves the conversion time (no LDGSTS in the LSU queue) but one
-// iteration of loads in flight per warp cannot cover the L2 latency (158 us); 8 issuer warps instead of 4: -4 %.
+// iteration of loads in flight per warp cannot cover the L2 latency (158 us).  8 issuer warps instead of 4: -5 % here (kept),
+// +3..5 % for the unpaired producer at D = 64 / 256 (not adopted there).
 struct CostVolPairProducer {
     static constexpr int kWarps = 8, kGroups = 1;
     static constexpr bool kAsync = true;
 #ifndef KDPC_CV_PAIR_IW
-#define KDPC_CV_PAIR_IW 4
+#define KDPC_CV_PAIR_IW 8
 #endif
     static constexpr int kIssuerWarps = KDPC_CV_PAIR_IW, kEpilogueWarps = 8;
     static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
