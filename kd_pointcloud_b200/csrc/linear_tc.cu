@@ -270,20 +270,23 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
     GemmShape g = make_shape(m, n, k, wpacked);
     // small-M layers: column blocks over idle SMs when there are >= 128 outputs, else (large K) split-K
     if (!(kdpc_linear_split_n && plan_split_n(g)) && ws != nullptr) plan_split_k(g);
-    if (g.splits == 1 && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled() == 2) {
-        // streaming layers, rows by 2-D tensor-map TMA: two UTMALDG per chunk from one thread
+    if ((g.splits == 1 || g.nsplit) && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled() == 2) {
+        // streaming layers, rows by 2-D tensor-map TMA: two UTMALDG per chunk from one thread.  Split-N plans too: every
+        // K chunk of a (row tile, column block) item is in flight from the start instead of one register round trip per chunk
         using P = PlainTmaProducer;
         P::Args pa;
         if (make_row_tensor_map(&pa.tmap, x, m, k, ldx)) {
             pa.k = k;
             for (int raw = P::kLookahead + 1; raw >= 2; --raw) {
                 GemmShape ga = make_shape(m, n, k, wpacked, P::kRawBytes, raw);
+                if (g.nsplit && !plan_split_n(ga)) continue;
                 if (ga.stages < 2) continue;
                 const size_t smem_a = smem_bytes(ga.n_pad, ga.stages, ga.raw_bytes * ga.raw_stages);
                 auto kern_a = tc_gemm_kernel<P, StoreEpilogue>;
                 KDPC_ENSURE_SMEM(kern_a, SMEM_BUDGET + 1024);
                 StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
-                const unsigned grid = (unsigned)(ga.num_tiles < num_sms() ? ga.num_tiles : num_sms());
+                const long long work_a = ga.num_tiles * (ga.nsplit ? ga.splits : 1);
+                const unsigned grid = (unsigned)(work_a < num_sms() ? work_a : num_sms());
                 kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
                 KDPC_RETURN_LAST();
             }

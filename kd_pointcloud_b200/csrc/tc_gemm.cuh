@@ -138,15 +138,16 @@ static inline void plan_split_k(GemmShape &g) {
 static inline size_t split_k_ws_bytes(const GemmShape &g) {
     return g.splits > 1 && !g.nsplit ? (size_t)g.splits * (size_t)g.m * g.n_pad * sizeof(float) : 0;
 }
-// Split-N for small-M plain layers with >= 128 outputs (the 64 .. 4096-point levels: 4 .. 64 row tiles): a work item
-// is a 128-row x 64- (or 128-) column block over the WHOLE K.  Against split-K: final results straight from the
+// Split-N for small-M plain layers with >= 64 outputs (the 64 .. 4096-point levels: 4 .. 64 row tiles): a work item
+// is a 128-row x 64- (32- for 64-wide layers, or 128-) column block over the WHOLE K.  Against split-K: final results straight from the
 // epilogue (no partial sums, no reduce launch), weight stages of 16 KB instead of 64, four pipeline stages; the rows
 // are re-read from L2 once per column block.  (4096 x 256 -> 256: 25-29 us as split-K + reduce.)
 static inline bool plan_split_n(GemmShape &g) {
     const int sms = device_sms();
     // (long K stays with split-K: its shorter accumulation chains keep the 1e-5 error budget of the K = 3120 layers)
-    if (g.num_tiles * 2 > sms || g.n_pad < 128 || (g.n_pad & 63) != 0 || g.num_chunks > 8) return false;
-    int nb = 64;
+    if (g.num_tiles * 2 > sms || g.n_pad < 64 || (g.n_pad & 63) != 0 || g.num_chunks > 8) return false;
+    if (g.n_pad == 64 && g.num_chunks < 2) return false;         // (a single-chunk 64-wide layer: nothing to gain)
+    int nb = g.n_pad == 64 ? 32 : 64;
     if (g.num_tiles * (g.n_pad / 64) > sms && g.n_pad > 128 && (g.n_pad & 127) == 0) nb = 128;
     g.w_n_pad = g.n_pad;
     g.splits = g.n_pad / nb;
