@@ -211,6 +211,11 @@ long long kdpc_packed_weight_bytes(int n, int k_packed);
 /* The fused tcgen05 layers stage their gathers asynchronously (bulk copies two pipeline iterations ahead);
  * kdpc_tc_set_async(0) selects the synchronous register-staged producers (same results; A/B measurements). */
 void kdpc_tc_set_async(int on);
+/* 1 = tcgen05 kernels are launched with programmatic dependent launch (default 0: measured neutral): their CTAs set up while the previous
+ * kernel drains and wait (griddepcontrol.wait) before touching global memory; CUDA-graph capture records programmatic
+ * edges.  Same results. */
+void kdpc_tc_set_pdl(int on);
+int kdpc_tc_pdl_enabled(void);
 /* Small-M layers (<= half the SMs in 128-row tiles) with >= 128 outputs: work items are column blocks over the whole K
  * (default 1: final results from the epilogue, no workspace); 0 = split-K + reduce as for the narrow layers. */
 void kdpc_linear_set_split_n(int on);

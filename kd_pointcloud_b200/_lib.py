@@ -150,6 +150,10 @@ def lib() -> ctypes.CDLL:
         L.kdpc_pointconv_fused_ws_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
         L.kdpc_flow_metrics_workspace_bytes.restype = c_longlong
         L.kdpc_flow_metrics_workspace_bytes.argtypes = []
+        L.kdpc_tc_set_pdl.restype = None
+        L.kdpc_tc_set_pdl.argtypes = [c_int]
+        if os.environ.get("KDPC_PDL", "0") == "1":               # A/B switch for measurements
+            L.kdpc_tc_set_pdl(1)
         L.kdpc_knn_set_few.restype = None
         L.kdpc_knn_set_few.argtypes = [c_int]
         if os.environ.get("KDPC_KNN_FEW", "0") == "1":           # A/B switch for measurements (default off: slower)
@@ -215,7 +219,7 @@ def exported_symbols():
     return ["kdpc_abi_version", "kdpc_error_string", "kdpc_set_sm_limit", "kdpc_sm_limit", "kdpc_packed_weight_bytes", "kdpc_knn_workspace_bytes",
             "kdpc_spatial_sort_bytes", "kdpc_costvol_fused_ws_bytes", "kdpc_linear_tc_ws_bytes", "kdpc_pointconv_fused_ws_bytes",
             "kdpc_loss_workspace_bytes", "kdpc_linear_dw_ws_bytes", "kdpc_weightnet_grad_ws_bytes", "kdpc_dataprep_workspace_bytes", "kdpc_flow_metrics_workspace_bytes", "kdpc_fps_set_cluster", "kdpc_fps_cluster_capacity", "kdpc_tc_set_async", "kdpc_tc_set_trace", "kdpc_tc_trace_buffer", "kdpc_pointconv_set_stages", "kdpc_pointconv_set_precompute",
-            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n", "kdpc_linear_dw_set_async", "kdpc_costvol_grad_ws_bytes", "kdpc_group_concat_set_direct", "kdpc_knn_set_few"] + list(_SIGNATURES)
+            "kdpc_tc_async_enabled", "kdpc_costvol_set_pairing", "kdpc_linear_set_split_n", "kdpc_linear_dw_set_async", "kdpc_costvol_grad_ws_bytes", "kdpc_group_concat_set_direct", "kdpc_knn_set_few", "kdpc_tc_set_pdl", "kdpc_tc_pdl_enabled"] + list(_SIGNATURES)
 
 
 def check(rc: int, what: str) -> None:

@@ -515,7 +515,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
             auto kern = tc_gemm_kernel<P, MaxKEpilogue>;
             KDPC_ENSURE_SMEM(kern, 216 * 1024);
             const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
-            kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
+            launch_tc(kern, grid, num_threads<P>(), smem, to_stream(stream), g, pa, ea);
             KDPC_RETURN_LAST();
         }
     }
@@ -549,7 +549,7 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
             KDPC_ENSURE_SMEM(kern, 216 * 1024);
             const long long work = g.num_tiles * (g.nsplit ? g.splits : 1);
             const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
-            kern<<<grid, num_threads<P>(), smem, to_stream(stream)>>>(g, pa, ea);
+            launch_tc(kern, grid, num_threads<P>(), smem, to_stream(stream), g, pa, ea);
             KDPC_RETURN_LAST();
         }
     }
@@ -559,6 +559,6 @@ KDPC_API int kdpc_costvol_fused(int b, int s, int n, int k, int d, int d_out, co
     auto kern = tc_gemm_kernel<CostVolProducer, MaxKEpilogue>;
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
     const unsigned grid = (unsigned)(g.num_tiles < num_sms() ? g.num_tiles : num_sms());
-    kern<<<grid, num_threads<CostVolProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
+    launch_tc(kern, grid, num_threads<CostVolProducer>(), smem, to_stream(stream), g, pa, ea);
     KDPC_RETURN_LAST();
 }

@@ -216,6 +216,10 @@ static bool make_row_tensor_map(CUtensorMap *tm, const float *x, long long m, in
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int g_tc_pdl = 0;              // measured neutral (single graph 4.897 vs 4.896 ms, pipeline 2246 vs 2263 pairs/s): off
+KDPC_API int kdpc_tc_pdl_enabled(void) { return g_tc_pdl; }
+/* A/B switch for measurements: 1 = programmatic dependent launch of the tcgen05 kernels (same results) */
+KDPC_API void kdpc_tc_set_pdl(int on) { g_tc_pdl = on; }
 static int kdpc_linear_split_n = 1;
 static int g_tc_async = 2;              // 0 = synchronous producers, 1 = cp.async (LDGSTS) rows, 2 = tensor-map TMA rows (default)
 KDPC_API int kdpc_tc_async_enabled(void) { return g_tc_async; }
@@ -287,7 +291,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
                 StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
                 const long long work_a = ga.num_tiles * (ga.nsplit ? ga.splits : 1);
                 const unsigned grid = (unsigned)(work_a < num_sms() ? work_a : num_sms());
-                kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
+                launch_tc(kern_a, grid, num_threads<P>(), smem_a, to_stream(stream), ga, pa, ea);
                 KDPC_RETURN_LAST();
             }
         }
@@ -304,7 +308,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
             P::Args pa{x, ldx, k};
             StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, nullptr};
             const unsigned grid = (unsigned)(ga.num_tiles < num_sms() ? ga.num_tiles : num_sms());
-            kern_a<<<grid, num_threads<P>(), smem_a, to_stream(stream)>>>(ga, pa, ea);
+            launch_tc(kern_a, grid, num_threads<P>(), smem_a, to_stream(stream), ga, pa, ea);
             KDPC_RETURN_LAST();
         }
     }
@@ -315,7 +319,7 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
     StoreEpilogue::Args ea{scale, shift, slope, clamp_lo, clamp_hi, residual, out, ldo, reinterpret_cast<float *>(ws)};
     const long long work = g.num_tiles * g.splits;
     const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
-    kern<<<grid, num_threads<PlainProducer>(), smem, to_stream(stream)>>>(g, pa, ea);
+    launch_tc(kern, grid, num_threads<PlainProducer>(), smem, to_stream(stream), g, pa, ea);
     if (g.splits > 1 && !g.nsplit) return launch_splitk_reduce(g, ea, to_stream(stream));
     KDPC_RETURN_LAST();
 }

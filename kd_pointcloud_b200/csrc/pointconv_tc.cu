@@ -364,7 +364,7 @@ static int launch_pointconv(long long m, int n_out, const typename PointConvProd
     KDPC_ENSURE_SMEM(kern, 201 * 1024);
     const long long work = g.num_tiles * g.splits;
     const unsigned grid = (unsigned)(work < num_sms() ? work : num_sms());
-    kern<<<grid, num_threads<P>(), smem, st>>>(g, pa, ea);
+    launch_tc(kern, grid, num_threads<P>(), smem, st, g, pa, ea);
     if (g.splits > 1) return launch_splitk_reduce(g, ea, st);
     return (int)cudaGetLastError();
 }

@@ -222,8 +222,10 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
         }
         mbar_fence_init();
     }
-    Producer::prologue(pa, tid, (int)blockDim.x);                            // optional CTA-wide staging (before the role split)
     if (warp == MW) tmem_alloc(&tmem_base_smem, (uint32_t)g.tmem_cols);
+    // everything above is private to the CTA; from here on global memory written by the previous kernel is read
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    Producer::prologue(pa, tid, (int)blockDim.x);                            // optional CTA-wide staging (before the role split)
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -522,6 +524,32 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
         fence_after_sync();
         tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
     }
+}
+
+// Launch with PROGRAMMATIC DEPENDENT LAUNCH (kdpc_tc_set_pdl(1); default off - measured neutral): the kernel's CTAs may be scheduled while the
+// previous kernel of the stream is still draining, run their set-up (mbarrier init, TMEM allocation, tensor-map
+// prefetch, role split) and wait at `griddepcontrol.wait` - placed in tc_gemm_kernel right before the first access to
+// global memory that a predecessor may have written - until that kernel has completed and flushed.  Stream capture
+// records the attribute as a programmatic edge, so the ~150 launches of a graphed forward lose most of their
+// launch-to-launch gaps.  Safe behind any predecessor (it need not trigger anything: its completion releases the wait).
+extern "C" int kdpc_tc_pdl_enabled(void);
+template <class Kern, class... Args>
+static inline void launch_tc(Kern kern, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const Args &...args) {
+    if (!kdpc_tc_pdl_enabled()) {
+        kern<<<grid, threads, smem, st>>>(args...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // ------------------------------------------------------------------------------------------
