@@ -328,7 +328,8 @@ def test_build_csr_large_multi_part_and_skewed():
     """Model-size lists (8192 candidates x 32 selections, several CTAs per cloud), a skewed list (every entry selects
     one of 5 candidates: long segments) and candidates nobody selects."""
     g = torch.Generator().manual_seed(6)
-    for n, s, k, hi in ((8192, 8192, 32, 8192), (2048, 8192, 3, 2048), (1000, 700, 9, 5), (64, 64, 16, 64)):
+    for n, s, k, hi in ((8192, 8192, 32, 8192), (2048, 8192, 3, 2048), (1000, 700, 9, 5), (64, 64, 16, 64), (256, 2048, 12, 256),
+                        (512, 4096, 9, 400)):
         idx = torch.randint(0, hi, (2, s, k), generator=g).int()
         off, perm = K.build_csr(idx.to(DEV), n)
         off, perm = off.cpu().numpy().astype(np.int64), perm.cpu().numpy()
