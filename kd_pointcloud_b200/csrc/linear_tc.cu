@@ -232,8 +232,12 @@ KDPC_API void *kdpc_tc_trace_buffer(void) { return g_tc_trace; }
  * stamps into it (200 x 16 int64, device memory); NULL = off */
 KDPC_API void kdpc_tc_set_trace(void *p) { g_tc_trace = p; }
 
+// rows of a packed weight: multiples of 16 up to 256 outputs; WIDE layers (n > 256: level3_1, the input gradients of the
+// PointConv linears) are padded to whole 128-row column blocks (kdpc_linear_tc walks them as split-N work items)
+static inline int packed_rows(int n) { return n > 256 ? (n + 127) / 128 * 128 : (n + 15) / 16 * 16; }
+
 KDPC_API long long kdpc_packed_weight_bytes(int n, int k_packed) {
-    const int n_pad = (n + 15) / 16 * 16;
+    const int n_pad = packed_rows(n);
     const int chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
     return (long long)chunks * 2 * n_pad * 128;
 }
@@ -241,14 +245,14 @@ KDPC_API long long kdpc_packed_weight_bytes(int n, int k_packed) {
 KDPC_API int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const float *w, void *out,
                               kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(w && out && n > 0 && k_src > 0);
-    if (n > 256) return KDPC_EUNSUPPORTED;
+    if (n > 32768 || (n > 256 && mode != 0)) return KDPC_EUNSUPPORTED;
     int k_packed = k_src;
     if (mode == 1) {
         KDPC_CHECK_ARGS(d >= 0 && wn > 0 && k_src == (d + 3) * wn);
         k_packed = (d + 4) * wn;
     }
     if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return KDPC_EINVAL;
-    const int n_pad = (n + 15) / 16 * 16;
+    const int n_pad = packed_rows(n);
     const int chunks = (k_packed + CHUNK_K - 1) / CHUNK_K;
     const long long total = (long long)chunks * n_pad * 8;
     pack_weight_kernel<<<(unsigned)div_up_ll(total, 256), 256, 0, to_stream(stream)>>>(
@@ -257,7 +261,7 @@ KDPC_API int kdpc_pack_weight(int n, int k_src, int mode, int d, int wn, const f
 }
 
 KDPC_API long long kdpc_linear_tc_ws_bytes(long long m, int n, int k) {
-    if (m <= 0 || n <= 0 || n > 256 || k <= 0) return 0;
+    if (m <= 0 || n <= 0 || n > 256 || k <= 0) return 0;          // (wide layers: column blocks, no workspace)
     GemmShape g = make_shape(m, n, k, nullptr);
     if (!(kdpc_linear_split_n && plan_split_n(g))) plan_split_k(g);
     return (long long)split_k_ws_bytes(g);
@@ -267,13 +271,32 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
                             const float *scale, const float *shift, float slope, float clamp_lo, float clamp_hi,
                             const float *residual, void *ws, float *out, int ldo, kdpc_stream_t stream) {
     KDPC_CHECK_ARGS(x && wpacked && out && m > 0 && n > 0 && k > 0 && ldx >= k && ldo >= n);
-    if (n > 256) return KDPC_EUNSUPPORTED;
+    if (n > 32768) return KDPC_EUNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) % 16) != 0 || (reinterpret_cast<uintptr_t>(out) % 16) != 0 ||
         (reinterpret_cast<uintptr_t>(wpacked) % 16) != 0 || (reinterpret_cast<uintptr_t>(ws) % 16) != 0)
         return KDPC_EINVAL;
-    GemmShape g = make_shape(m, n, k, wpacked);
-    // small-M layers: column blocks over idle SMs when there are >= 128 outputs, else (large K) split-K
-    if (!(kdpc_linear_split_n && plan_split_n(g)) && ws != nullptr) plan_split_k(g);
+    const bool wide = n > 256;
+    // WIDE layers (n > 256): ONE launch over (row tile, 128-column block) work items against a weight packed in whole column
+    // blocks - instead of one pack + one launch per 256 columns from the host (the KD step issued 257 such launches)
+    auto widen = [&](GemmShape &gs) {
+        gs.n = n;
+        gs.w_n_pad = packed_rows(n);
+        gs.splits = gs.w_n_pad / 128;
+        gs.nsplit = 1;
+        gs.chunks_per_split = gs.num_chunks;
+        gs.n_pad = 128;
+        gs.acc_stride = 128;
+        gs.nacc_log2 = 2;
+        gs.tmem_cols = 512;
+        gs.stages = pick_stages(128, gs.raw_bytes * gs.raw_stages);
+    };
+    GemmShape g = make_shape(m, wide ? 128 : n, k, wpacked);
+    if (wide) {
+        if ((long long)g.num_tiles * (packed_rows(n) / 128) >= (1ll << 31)) return KDPC_EUNSUPPORTED;
+        widen(g);
+    } else if (!(kdpc_linear_split_n && plan_split_n(g)) && ws != nullptr) {
+        plan_split_k(g);       // small-M layers: column blocks over idle SMs when there are >= 64 outputs, else (large K) split-K
+    }
     if ((g.splits == 1 || g.nsplit) && (k & 7) == 0 && (ldx & 3) == 0 && m * (long long)TILE_M < (1ll << 31) && kdpc_tc_async_enabled() == 2) {
         // streaming layers, rows by 2-D tensor-map TMA: two UTMALDG per chunk from one thread.  Split-N plans too: every
         // K chunk of a (row tile, column block) item is in flight from the start instead of one register round trip per chunk
@@ -282,8 +305,9 @@ KDPC_API int kdpc_linear_tc(long long m, int n, int k, const float *x, int ldx, 
         if (make_row_tensor_map(&pa.tmap, x, m, k, ldx)) {
             pa.k = k;
             for (int raw = P::kLookahead + 1; raw >= 2; --raw) {
-                GemmShape ga = make_shape(m, n, k, wpacked, P::kRawBytes, raw);
-                if (g.nsplit && !plan_split_n(ga)) continue;
+                GemmShape ga = make_shape(m, wide ? 128 : n, k, wpacked, P::kRawBytes, raw);
+                if (wide) widen(ga);
+                else if (g.nsplit && !plan_split_n(ga)) continue;
                 if (ga.stages < 2) continue;
                 const size_t smem_a = smem_bytes(ga.n_pad, ga.stages, ga.raw_bytes * ga.raw_stages);
                 auto kern_a = tc_gemm_kernel<P, StoreEpilogue>;

@@ -487,22 +487,10 @@ def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     _packed_weight = _packed_weight_cached if cache_weight else (lambda w: K.pack_weight(w.detach().contiguous(), 0, 0, 0))
     if k < 16 or n < 16 or k % 4 != 0:
         return K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
-    if n <= 256:
-        return K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
-    # wider layers: column blocks of 256 written in place (level3_1: 256 -> 512; input gradients of the PointConv linears)
-    if res is not None:
-        outs = []
-        for c0 in range(0, n, 256):
-            c1 = min(n, c0 + 256)
-            outs.append(K.linear_tc(x, _packed_weight(w2d[c0:c1]), c1 - c0, None if scale is None else scale[c0:c1].contiguous(),
-                                    None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi, res[..., c0:c1].contiguous()))
-        return torch.cat(outs, dim=-1)
-    out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
-    for c0 in range(0, n, 256):
-        c1 = min(n, c0 + 256)
-        ops.linear_tc_into(x, _packed_weight(w2d[c0:c1]), c1 - c0, out, c0, None if scale is None else scale[c0:c1].contiguous(),
-                           None if shift is None else shift[c0:c1].contiguous(), slope, lo, hi)
-    return out
+    # any width in ONE launch: layers wider than 256 outputs (level3_1: 256 -> 512; the input gradients of the PointConv
+    # linears, up to 8240 columns) run as (row tile, 128-column block) work items against a weight packed in whole column
+    # blocks (csrc/linear_tc.cu) - no per-block packing / launching from the host
+    return K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
 
 
 class _LinearTC(torch.autograd.Function):

@@ -32,6 +32,7 @@ def _err(a, b):
 @pytest.mark.parametrize("m,n,k", [
     (128, 64, 64), (128, 128, 128), (1000, 64, 64), (300, 32, 32), (4096, 128, 2096), (777, 96, 320), (129, 16, 16),
     (65536, 128, 512), (5000, 256, 256), (200, 24, 100), (64, 256, 4144), (20000, 48, 80), (1, 64, 64),
+    (3000, 512, 256), (1000, 2096, 128), (130, 8240, 256), (4096, 300, 64), (20000, 1072, 64),      # wide: one launch over column blocks
 ])
 def test_linear_tc_matches_fp64(m, n, k):
     g = torch.Generator().manual_seed(m + n + k)
