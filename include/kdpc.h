@@ -291,6 +291,14 @@ int kdpc_spatial_sort_order_stride(int n);
  * xyz1 [B,S,3], xyz2 [B,N,3], p1 [B,S,d], p2 [B,N,d], idx int32 [B,S,32] -> out [B,S,d_out].
  * ws: kdpc_costvol_fused_ws_bytes(b,s,n,d) bytes (16-byte aligned) for the per-point features with the positional
  * encoding folded in; NULL selects the variant that evaluates the encoding per neighbour (no workspace). */
+/* One Adam step over `count` fp32 tensors in one launch per 96 tensors (reference: torch.optim.Adam(lr, betas, eps,
+ * weight_decay) + optimizer.step(), distilTrain.py:134-135, 182; torch's capturable arithmetic: L2 weight decay, bias
+ * correction, no amsgrad).  params / grads / exp_avg / exp_avg_sq: HOST arrays of `count` device pointers (passed to the
+ * kernel by value: a CUDA graph records them); sizes: HOST array of element counts; lr, step: DEVICE fp32 scalars - the
+ * update uses t = *step + 1 and *step is incremented afterwards. */
+int kdpc_adam_step(int count, const void *const *params, const void *const *grads, const void *const *exp_avg,
+                   const void *const *exp_avg_sq, const long long *sizes, const float *lr, float beta1, float beta2,
+                   float eps, float weight_decay, float *step, kdpc_stream_t stream);
 /* Backward of kdpc_costvol_fused in its folded form (reference: autograd through CrossLayerLight.cross, pointconv_util.py:1826-1850,
  * by loss.backward(), distilTrain.py:180), k = 32, d = d_out = 32 or 64:  out[i,c] = act2(max_k (W act1(p2q[idx[i,k]] + p1q[i]) + bias)[c])
  * with p1q = points1 + pos_b - pos_w xyz1 and p2q = points2 + pos_w xyz2 (the caller folds and un-folds the positional layer).

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("KDPC_LIB") or os.path.join(_HERE, "libkdpc.so")   # KDPC_LIB: an experiment build (A/B measurements)
 SOURCES = ["abi.cu", "fps.cu", "knn.cu", "group.cu", "interp.cu", "pointconv.cu", "costvol.cu",
-           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu", "knn_feat.cu", "dataprep.cu", "dw_tc.cu", "weightnet_grad.cu", "costvol_grad.cu"]
+           "scatter.cu", "metrics.cu", "linear_tc.cu", "pointconv_tc.cu", "costvol_tc.cu", "knn_bf.cu", "loss.cu", "knn_feat.cu", "dataprep.cu", "dw_tc.cu", "weightnet_grad.cu", "costvol_grad.cu", "adam.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 LINK_FLAGS = ARCH_FLAGS + ["-shared"]
@@ -115,6 +115,7 @@ _SIGNATURES = {
     "kdpc_flow_loss": [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "kdpc_hint_loss": [c_longlong, _P, _P, c_float, _P, _P, _P, _P],
     "kdpc_build_csr": [c_int, c_int, c_int, _P, _P, _P, _P],
+    "kdpc_adam_step": [c_int, _P, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, _P],
     "kdpc_costvol_grad": [c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_scatter_rows_csr": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P],
 }

@@ -103,17 +103,76 @@ def supervised_step(model: torch.nn.Module, batch: Dict[str, torch.Tensor], opti
     return loss.detach()
 
 
-def make_capturable_adam(params, lr: float = 1e-3, **kw) -> torch.optim.Adam:
+class KdpcAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (L2 weight decay, bias correction, no amsgrad; distilTrain.py:134-135) as ONE kernel pass over all
+    parameter tensors (csrc/adam.cu) instead of a dozen foreach launches over the 226 tensor lists: 1.9 -> ~0.1 ms per KD
+    step.  Capturable by construction: the learning rate and the step count live in device tensors (``set_lr`` /
+    schedulers that rewrite ``param_group['lr']`` in place keep working after a CUDA-graph capture), the pointer table
+    travels in the kernel parameters.  State per parameter: ``exp_avg``, ``exp_avg_sq``; the step counter is one device
+    scalar kept in the state of the group's first parameter (``kdpc_step``)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(params)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        for g in self.param_groups:
+            dev = g["params"][0].device
+            if not isinstance(g["lr"], torch.Tensor):
+                g["lr"] = torch.tensor(float(g["lr"]), device=dev)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        import ctypes
+        from . import _lib
+        loss = closure() if closure is not None else None
+        for g in self.param_groups:
+            ps = [p for p in g["params"] if p.grad is not None]
+            if not ps:
+                continue
+            first = g["params"][0]
+            if "kdpc_step" not in self.state[first]:
+                self.state[first]["kdpc_step"] = torch.zeros((), dtype=torch.float32, device=first.device)
+            step = self.state[first]["kdpc_step"]
+            for p in ps:
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() or p.grad.dtype != torch.float32:
+                    raise ValueError("kdpc: KdpcAdam needs contiguous float32 parameters and gradients")
+            n = len(ps)
+            arr = ctypes.c_void_p * n
+            lr = g["lr"] if isinstance(g["lr"], torch.Tensor) else torch.tensor(float(g["lr"]), device=first.device)
+            with torch.cuda.device(first.device):
+                rc = _lib.lib().kdpc_adam_step(
+                    n, arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
+                    arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps]), arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
+                    (ctypes.c_longlong * n)(*[p.numel() for p in ps]), ctypes.c_void_p(lr.data_ptr()), float(g["betas"][0]),
+                    float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), ctypes.c_void_p(step.data_ptr()),
+                    ctypes.c_void_p(torch.cuda.current_stream(first.device).cuda_stream))
+            _lib.check(rc, "kdpc_adam_step")
+            # the kernel wrote through raw pointers: move the tensors' version counters like an in-place torch op would, so
+            # that everything keyed on (data_ptr, version) - packed weights, folded affines - is re-derived from the new
+            # values (without this the next forward silently used the OLD packed student weights: the loss fell 391 ->
+            # 379 -> 369 instead of 391 -> 339 -> 286; torch's own fused Adam showed the same symptom)
+            for p in ps:
+                torch.autograd.graph.increment_version(p)
+        return loss
+
+
+def make_capturable_adam(params, lr: float = 1e-3, **kw) -> torch.optim.Optimizer:
     """Adam for ``GraphedKDStep``: ``capturable=True`` and the learning rate as a DEVICE tensor, so that the reference's
     schedule (StepLR + the LEARNING_RATE_CLIP rewrite of ``param_group['lr']``, distilTrain.py:130-140) keeps working
     after capture: ``set_lr`` / an in-place scheduler update changes what the captured kernels read."""
     params = list(params)
     dev = params[0].device
-    # torch's default (foreach) implementation.  Its `fused=True` variant is ~1 ms faster per step but gave DIFFERENT updates
-    # with a tensor learning rate on this torch build (tools/cmp_adam.py: the loss falls 391 -> 379 -> 369 instead of
-    # 391 -> 339 -> 286 from the same weights and gradients), and an explicit fused=False silently selects the per-tensor
-    # loop (+4 ms): leave both unset unless KDPC_ADAM_FUSED=1 asks for the experiment.
+    # Default: KdpcAdam (one kernel pass, csrc/adam.cu; KDPC_ADAM=torch selects torch.optim.Adam's capturable foreach path:
+    # same updates, ~1.4 ms slower per step).  torch's `fused=True` variant (KDPC_ADAM_FUSED=1) trained visibly slower in
+    # tools/cmp_adam.py - the same symptom KdpcAdam showed before it moved the parameters' version counters: the caches of
+    # packed weights are keyed on (data_ptr, version) and kept serving the OLD student weights; and an explicit
+    # fused=False silently selects the per-tensor loop (+4 ms), so neither flag is ever passed by default.
     import os
+    if os.environ.get("KDPC_ADAM", "kdpc") == "kdpc" and not kw.get("amsgrad", False):
+        return KdpcAdam(params, lr=lr, **{k: v for k, v in kw.items() if k in ("betas", "eps", "weight_decay")})
     if os.environ.get("KDPC_ADAM_FUSED", "0") == "1":
         kw.setdefault("fused", True)
     return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=dev), capturable=True, **kw)

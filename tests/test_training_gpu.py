@@ -99,3 +99,28 @@ def test_eval_after_graph_replays_uses_the_trained_weights():
     short = {k: torch.cat([v, v], 0) for k, v in short.items()}
     assert torch.isfinite(stepper.step(short)).all()
     assert torch.isfinite(stepper.step(batches[2])).all()
+
+
+def test_kdpc_adam_matches_torch_adam():
+    """The one-pass Adam kernel (csrc/adam.cu) against torch.optim.Adam over five steps: ragged tensor sizes (chunk tails,
+    unaligned element counts), weight decay, a learning-rate change between steps, more than one launch worth of tensors."""
+    from kd_pointcloud_b200.training import KdpcAdam, set_lr
+    g = torch.Generator().manual_seed(11)
+    shapes = [(128, 2096), (33,), (7, 5, 3), (4096,), (1,), (257, 129)] + [(17 + i,) for i in range(120)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    for wd in (0.0, 1e-4):
+        pa = [t.clone().to(DEV).requires_grad_(True) for t in init]
+        pb = [t.clone().to(DEV).requires_grad_(True) for t in init]
+        oa = KdpcAdam(pa, lr=1e-3, weight_decay=wd)
+        ob = torch.optim.Adam(pb, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        for step in range(5):
+            grads = [torch.randn(s, generator=g).to(DEV) * (1.0 + step) for s in shapes]
+            for p, q, gr in zip(pa, pb, grads):
+                p.grad, q.grad = gr.clone(), gr.clone()
+            if step == 3:
+                set_lr(oa, 5e-4)
+                set_lr(ob, 5e-4)
+            oa.step()
+            ob.step()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=2e-5, atol=1e-7), (p - q).abs().max()

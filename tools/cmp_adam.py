@@ -12,12 +12,20 @@ teacher = flownet.teacher().to(dev)
 teacher.load_state_dict(synthetic_state_dict(teacher.state_dict(), 0))
 batch = {k: v.to(dev) for k, v in make_pairs(4, 4096, seed=3).items()}
 res = {}
-for fused in (False, True):
+makers = {
+    "torch.optim.Adam (plain: what distilTrain.py:134 builds)": lambda ps: torch.optim.Adam(ps, lr=1e-3),
+    "torch Adam capturable, tensor lr (default impl)": lambda ps: torch.optim.Adam(ps, lr=torch.tensor(1e-3, device=dev), capturable=True),
+    "torch Adam capturable, tensor lr, fused=True": lambda ps: torch.optim.Adam(ps, lr=torch.tensor(1e-3, device=dev), capturable=True, fused=True),
+    "KdpcAdam (csrc/adam.cu)": lambda ps: training.KdpcAdam(ps, lr=1e-3),
+}
+for name, mk in makers.items():
     student = flownet.student().to(dev)
     student.load_state_dict(synthetic_state_dict(student.state_dict(), 1))
-    opt = training.make_capturable_adam(student.parameters(), lr=1e-3, fused=fused)
-    losses = [float(training.kd_step(teacher, student, batch, opt)) for _ in range(3)]
-    res[fused] = (losses, [p.detach().clone() for p in student.parameters()])
-print("losses foreach", res[False][0], "fused", res[True][0])
-worst = max(((a - b).abs().max() / (a.abs().max() + 1e-12)).item() for a, b in zip(res[False][1], res[True][1]))
-print("max relative parameter difference after 3 steps:", worst)
+    opt = mk(list(student.parameters()))
+    losses = [round(float(training.kd_step(teacher, student, batch, opt)), 3) for _ in range(3)]
+    res[name] = (losses, [p.detach().clone() for p in student.parameters()])
+    print(f"{name:60s} losses {losses}")
+base = res["torch.optim.Adam (plain: what distilTrain.py:134 builds)"][1]
+for name, (_, ps) in res.items():
+    worst = max(((a - b).abs().max() / (a.abs().max() + 1e-12)).item() for a, b in zip(base, ps))
+    print(f"{name:60s} max relative parameter difference to plain Adam after 3 steps: {worst:.3e}")
