@@ -90,14 +90,15 @@ costvol_grad_kernel(long long points, int s, int n, const float *__restrict__ p1
         for (int d = 0; d < D; ++d) dh[d] = 0.f;
         auto channel = [&](const int c) {
             // z[k, c] = b[c] + <W[c, :], h[k, :]> (weight row broadcast from shared memory)
-            float z0 = sb[c], z1 = 0.f, z2 = 0.f, z3 = 0.f;       // four interleaved partial sums: a quarter of the chain latency
+            // four interleaved partial sums (a quarter of the chain latency) on packed fp32 FMAs (fma.rn.f32x2: half the issue slots)
+            float2 za = make_float2(sb[c], 0.f), zb = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < D / 4; ++q) {
                 const float4 t = *reinterpret_cast<const float4 *>(sw + c * D + 4 * q);
-                z0 = fmaf(t.x, h[4 * q], z0); z1 = fmaf(t.y, h[4 * q + 1], z1);
-                z2 = fmaf(t.z, h[4 * q + 2], z2); z3 = fmaf(t.w, h[4 * q + 3], z3);
+                za = __ffma2_rn(make_float2(t.x, t.y), make_float2(h[4 * q], h[4 * q + 1]), za);
+                zb = __ffma2_rn(make_float2(t.z, t.w), make_float2(h[4 * q + 2], h[4 * q + 3]), zb);
             }
-            const float z = (z0 + z1) + (z2 + z3);
+            const float z = (za.x + za.y) + (zb.x + zb.y);
             // (Measured and rejected: deferring the arg-max lane's dh += g W[c, :] until after the loop, each lane walking only
             // its own channels over a row-padded copy of W: -3 % at D = 32, and at D = 64 the copy costs the second resident CTA.)
             const int zo = cg_f2ord(z);
@@ -109,8 +110,10 @@ costvol_grad_kernel(long long points, int s, int n, const float *__restrict__ p1
 #pragma unroll
                 for (int q = 0; q < D / 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4 *>(sw + c * D + 4 * q);
-                    dh[4 * q] = fmaf(g, t.x, dh[4 * q]); dh[4 * q + 1] = fmaf(g, t.y, dh[4 * q + 1]);
-                    dh[4 * q + 2] = fmaf(g, t.z, dh[4 * q + 2]); dh[4 * q + 3] = fmaf(g, t.w, dh[4 * q + 3]);
+                    const float2 g2 = make_float2(g, g);
+                    const float2 d0 = __ffma2_rn(g2, make_float2(t.x, t.y), make_float2(dh[4 * q], dh[4 * q + 1]));
+                    const float2 d1 = __ffma2_rn(g2, make_float2(t.z, t.w), make_float2(dh[4 * q + 2], dh[4 * q + 3]));
+                    dh[4 * q] = d0.x; dh[4 * q + 1] = d0.y; dh[4 * q + 2] = d1.x; dh[4 * q + 3] = d1.y;
                 }
             }
             if constexpr (L::kSmemDw) {
