@@ -156,7 +156,18 @@ class PointConvBidirection(nn.Module):
         B = xyz1.shape[0]
         up = self.upsample.forward_pm
         cat_c = lambda *ts: torch.cat(ts, dim=2)
-        both = lambda a, b: torch.cat([a, b], dim=0)
+        both = KF.joined                      # cat along the batch axis (no copy when the halves already share a tensor)
+        # Inference: the per-level concatenations [encoder features | upsampled decoder features] are never copied
+        # together - the two 1x1 convolutions that produce the parts write straight into the column blocks of one
+        # buffer (the kernels take row strides), and the layers that read a part read the view.  Same values.
+        free = KF.concat_free(xyz1, xyz2, color1, color2)
+
+        def parts(rows_like, c_first, c_second):
+            """(whole, first, second): a [2B,N,c_first+c_second] buffer and its two column blocks, or Nones."""
+            if not free:
+                return None, None, None
+            whole = rows_like.new_empty(tuple(rows_like.shape[:2]) + (c_first + c_second,))
+            return whole, whole[:, :, :c_first], whole[:, :, c_first:]
 
         # ---- encoder: clouds 1 and 2 as one batch of 2B (weights are shared, no BN) --------------
         npts = (self.level1.npoint, self.level2.npoint, self.level3.npoint, self.level4.npoint)
@@ -173,25 +184,29 @@ class PointConvBidirection(nn.Module):
             pyramid = self._sample_pyramid(pc_l0)
             if KF._CACHE_ENABLED and not pyramid.overlapped:
                 _GEOMETRY_CACHE.put(gkey, (pc_l0, pyramid, xyz1, xyz2))
-        f_l0 = self.level0_1.forward_pm(self.level0.forward_pm(both(color1, color2)))
+        c_feat_l0, c0a, c0b = parts(pc_l0, self.level0_1.out_channels, self.deconv1_0.out_channels)
+        f_l0 = self.level0_1.forward_pm(self.level0.forward_pm(torch.cat([color1, color2], dim=0)), out=c0a)
         f_l0_1 = self.level0_2.forward_pm(f_l0)
         if pyramid.overlapped:
             knn_idx(self.flow0.pointconv_list[0].nsample, pc_l0[:B], pc_l0[:B])      # flow0's neighbourhoods (cached)
 
         pc_l1, f_l1, fps_l1 = self.level1.forward_pm(pc_l0, f_l0_1, pyramid.level(0))
-        f_l1 = self.level1_0.forward_pm(f_l1)
+        c_feat_l1, c1a, c1b = parts(pc_l1, self.level1_0.out_channels, self.deconv2_1.out_channels)
+        f_l1 = self.level1_0.forward_pm(f_l1, out=c1a)
         f_l1_2 = self.level1_1.forward_pm(f_l1)
 
         pc_l2, f_l2, fps_l2 = self.level2.forward_pm(pc_l1, f_l1_2, pyramid.level(1))
-        f_l2 = self.level2_0.forward_pm(f_l2)
+        c_feat_l2, c2a, c2b = parts(pc_l2, self.level2_0.out_channels, self.deconv3_2.out_channels)
+        f_l2 = self.level2_0.forward_pm(f_l2, out=c2a)
         f_l2_3 = self.level2_1.forward_pm(f_l2)
 
         pc_l3, f_l3, fps_l3 = self.level3.forward_pm(pc_l2, f_l2_3, pyramid.level(2))
-        f_l3 = self.level3_0.forward_pm(f_l3)
+        c_feat_l3, c3a, c3b = parts(pc_l3, self.level3_0.out_channels, self.deconv4_3.out_channels)
+        f_l3 = self.level3_0.forward_pm(f_l3, out=c3a)
         f_l3_4 = self.level3_1.forward_pm(f_l3)
 
         pc_l4, f_l4, _ = self.level4.forward_pm(pc_l3, f_l3_4, pyramid.level(3))
-        f_l4_3 = self.deconv4_3.forward_pm(up(pc_l3, pc_l4, f_l4))
+        f_l4_3 = self.deconv4_3.forward_pm(up(pc_l3, pc_l4, f_l4), out=c3b)
 
         # 3-NN index sets dense<-sparse, computed once for both clouds and reused below
         up32 = knn_idx(3, pc_l3, pc_l2)
@@ -206,13 +221,15 @@ class PointConvBidirection(nn.Module):
         feat1_l3, feat2_l3 = h(f_l3)
 
         # ---- l3 -------------------------------------------------------------------------------
-        c_feat_l3 = cat_c(f_l3, f_l4_3)
+        if not free:
+            c_feat_l3 = cat_c(f_l3, f_l4_3)
         c_feat1_l3, c_feat2_l3 = h(c_feat_l3)
         feat1_new_l3, feat2_new_l3, cross3 = self.cross3.forward_pm(pc1_l3, pc2_l3, c_feat1_l3, c_feat2_l3, c_feat_l3)
         feat3, flow3 = self.flow3.forward_pm(pc1_l3, feat1_l3, cross3)
 
-        f_l3_2 = self.deconv3_2.forward_pm(up(pc_l2, pc_l3, both(feat1_new_l3, feat2_new_l3), idx=up32))
-        c_feat_l2 = cat_c(f_l2, f_l3_2)
+        f_l3_2 = self.deconv3_2.forward_pm(up(pc_l2, pc_l3, both(feat1_new_l3, feat2_new_l3), idx=up32), out=c2b)
+        if not free:
+            c_feat_l2 = cat_c(f_l2, f_l3_2)
         c_feat1_l2, c_feat2_l2 = h(c_feat_l2)
 
         # ---- l2 -------------------------------------------------------------------------------
@@ -220,10 +237,11 @@ class PointConvBidirection(nn.Module):
         pc2_l2_warp = self.warping.forward_pm(pc1_l2, pc2_l2, up_flow2)
         feat1_new_l2, feat2_new_l2, cross2 = self.cross2.forward_pm(pc1_l2, pc2_l2_warp, c_feat1_l2, c_feat2_l2, c_feat_l2)
         feat3_up = up(pc1_l2, pc1_l3, feat3, idx=up32[:B])
-        feat2, flow2 = self.flow2.forward_pm(pc1_l2, cat_c(feat1_l2, feat3_up), cross2, up_flow2)
+        feat2, flow2 = self.flow2.forward_pm(pc1_l2, (feat1_l2, feat3_up), cross2, up_flow2)
 
-        f_l2_1 = self.deconv2_1.forward_pm(up(pc_l1, pc_l2, both(feat1_new_l2, feat2_new_l2), idx=up21))
-        c_feat_l1 = cat_c(f_l1, f_l2_1)
+        f_l2_1 = self.deconv2_1.forward_pm(up(pc_l1, pc_l2, both(feat1_new_l2, feat2_new_l2), idx=up21), out=c1b)
+        if not free:
+            c_feat_l1 = cat_c(f_l1, f_l2_1)
         c_feat1_l1, c_feat2_l1 = h(c_feat_l1)
 
         # ---- l1 -------------------------------------------------------------------------------
@@ -231,10 +249,11 @@ class PointConvBidirection(nn.Module):
         pc2_l1_warp = self.warping.forward_pm(pc1_l1, pc2_l1, up_flow1)
         feat1_new_l1, feat2_new_l1, cross1 = self.cross1.forward_pm(pc1_l1, pc2_l1_warp, c_feat1_l1, c_feat2_l1, c_feat_l1)
         feat2_up = up(pc1_l1, pc1_l2, feat2, idx=up21[:B])
-        feat1, flow1 = self.flow1.forward_pm(pc1_l1, cat_c(feat1_l1, feat2_up), cross1, up_flow1)
+        feat1, flow1 = self.flow1.forward_pm(pc1_l1, (feat1_l1, feat2_up), cross1, up_flow1)
 
-        f_l1_0 = self.deconv1_0.forward_pm(up(pc_l0, pc_l1, both(feat1_new_l1, feat2_new_l1), idx=up10))
-        c_feat_l0 = cat_c(f_l0, f_l1_0)
+        f_l1_0 = self.deconv1_0.forward_pm(up(pc_l0, pc_l1, both(feat1_new_l1, feat2_new_l1), idx=up10), out=c0b)
+        if not free:
+            c_feat_l0 = cat_c(f_l0, f_l1_0)
         c_feat1_l0, c_feat2_l0 = h(c_feat_l0)
 
         # ---- l0 -------------------------------------------------------------------------------
@@ -242,7 +261,7 @@ class PointConvBidirection(nn.Module):
         pc2_l0_warp = self.warping.forward_pm(pc1_l0, pc2_l0, up_flow0)
         _, _, cross0 = self.cross0.forward_pm(pc1_l0, pc2_l0_warp, c_feat1_l0, c_feat2_l0, c_feat_l0)
         feat1_up = up(pc1_l0, pc1_l1, feat1, idx=up10[:B])
-        _, flow0 = self.flow0.forward_pm(pc1_l0, cat_c(feat1_l0, feat1_up), cross0, up_flow0)
+        _, flow0 = self.flow0.forward_pm(pc1_l0, (feat1_l0, feat1_up), cross0, up_flow0)
 
         # ---- outputs in the reference's [B,C,N] layout (models_bid_pointconv.py:198-207) ------
         flows = [cm(flow0), cm(flow1), cm(flow2), cm(flow3)]

@@ -153,6 +153,28 @@ _SORT_PARENT = _LRU(16)         # displaced cloud -> the cloud it was displaced 
 USE_SORT_REUSE = os.environ.get("KDPC_SORT_REUSE", "1") != "0"
 
 
+def concat_free(*ts: torch.Tensor) -> bool:
+    """True on the inference path (no autograd, float32 CUDA tensors): layers may then write into / read from column
+    blocks and batch halves of shared activation buffers (``fused_linear(out=...)``) instead of producing tensors that
+    are concatenated afterwards.  Same kernels, same values - only the destinations differ."""
+    return CONCAT_FREE and not torch.is_grad_enabled() and all(t.is_cuda and t.dtype == torch.float32 for t in ts)
+
+
+CONCAT_FREE = os.environ.get("KDPC_CONCAT_FREE", "1") != "0"      # A/B switch (tests compare both settings bit for bit)
+
+
+def joined(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat([a, b], dim=0) - without the copy when a and b already ARE the two halves of one contiguous tensor
+    (CrossLayerLight writes its two directions into one [2B,N,C] buffer on the inference path)."""
+    base = a._base
+    if (base is not None and b._base is base and base.is_contiguous() and a.is_contiguous() and b.is_contiguous()
+            and base.dim() == a.dim() == b.dim() and base.shape[0] == a.shape[0] + b.shape[0]
+            and tuple(base.shape[1:]) == tuple(a.shape[1:]) == tuple(b.shape[1:]) and a.data_ptr() == base.data_ptr()
+            and b.data_ptr() == base.data_ptr() + a.numel() * a.element_size()):
+        return base
+    return torch.cat([a, b], dim=0)
+
+
 def hint_displaced_copy(child: torch.Tensor, parent: torch.Tensor) -> None:
     """``child`` [B,N,3] is a smooth displacement of ``parent`` (same shape): when a kNN needs the child sorted, the parent's
     Morton order is reused (kdpc_spatial_reorder) instead of sorting again.  Results do not change."""
@@ -475,22 +497,39 @@ def fused_linear_available(x: torch.Tensor, weight: torch.Tensor, bias, bn) -> b
 
 def fused_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
                  bn: Optional[torch.nn.Module] = None, slope: float = 1.0, clamp=None,
-                 residual: Optional[torch.Tensor] = None, cache_weight: bool = True) -> torch.Tensor:
+                 residual: Optional[torch.Tensor] = None, cache_weight: bool = True,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y[..., N] = clamp(leaky(bn(x[..., K] W^T + b), slope)) + residual in ONE kernel.
-    weight [N,K] (nn.Linear) or [N,K,1(,1)] (1x1 conv)."""
+    weight [N,K] (nn.Linear) or [N,K,1(,1)] (1x1 conv).
+    ``out``: optional row-strided [..., N] view to write into (a column block or a batch half of a wider activation
+    buffer, ``ops.row_stride``); ``x`` may be such a view as well - the tensor-core layers take both row strides, so the
+    inference forward needs no torch.cat around its 1x1 convolutions."""
     w2d = weight.reshape(weight.shape[0], -1)
     n, k = w2d.shape
-    x = x.contiguous()
     scale, shift = _fold_affine(bias, bn)
     lo, hi = (1.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
     res = None if residual is None else residual.contiguous()
     _packed_weight = _packed_weight_cached if cache_weight else (lambda w: K.pack_weight(w.detach().contiguous(), 0, 0, 0))
-    if k < 16 or n < 16 or k % 4 != 0:
-        return K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
-    # any width in ONE launch: layers wider than 256 outputs (level3_1: 256 -> 512; the input gradients of the PointConv
-    # linears, up to 8240 columns) run as (row tile, 128-column block) work items against a weight packed in whole column
-    # blocks (csrc/linear_tc.cu) - no per-block packing / launching from the host
-    return K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
+    tc = not (k < 16 or n < 16 or k % 4 != 0)
+    if tc and (out is not None or not x.is_contiguous()):
+        ldx = ops.row_stride(x)
+        if ldx is None or ldx % 4 != 0 or x.data_ptr() % 16 != 0:
+            x = x.contiguous()
+        if out is None:
+            out = torch.empty(tuple(x.shape[:-1]) + (n,), dtype=torch.float32, device=x.device)
+        return ops.linear_tc_into(x, _packed_weight(w2d), n, out, scale, shift, slope, lo, hi, res)
+    x = x.contiguous()
+    if not tc:
+        y = K.linear_simt(x, w2d.detach().contiguous(), scale, shift, slope, lo, hi, res)
+    else:
+        # any width in ONE launch: layers wider than 256 outputs (level3_1: 256 -> 512; the input gradients of the
+        # PointConv linears, up to 8240 columns) run as (row tile, 128-column block) work items against a weight packed
+        # in whole column blocks (csrc/linear_tc.cu) - no per-block packing / launching from the host
+        y = K.linear_tc(x, _packed_weight(w2d), n, scale, shift, slope, lo, hi, res)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
 
 
 class _LinearTC(torch.autograd.Function):

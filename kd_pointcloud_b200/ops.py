@@ -602,21 +602,53 @@ def _linear_tc(x, wpacked, n: int, scale, shift, slope: float, lo: float, hi: fl
     return out
 
 
-def linear_tc_into(x: torch.Tensor, wpacked: torch.Tensor, n: int, out: torch.Tensor, col0: int, scale=None, shift=None,
-                   slope: float = 1.0, lo: float = 1.0, hi: float = 0.0) -> None:
-    """out[..., col0:col0+n] = epilogue(x W^T) written in place into a column block of a wider contiguous tensor
-    (the kernel takes the output row stride): wide layers / wide input gradients need no torch.cat afterwards.
-    Not a dispatcher op (it mutates ``out``): inference and hand-written backward only."""
-    m, k = _linear_args(x, n, scale, shift, None)
-    ntot = out.shape[-1]
-    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != m * ntot or col0 % 4 != 0 or col0 + n > ntot:
-        raise ValueError("kdpc: linear_tc_into needs a contiguous float32 [..., Ntot] output and a 4-aligned column offset")
+def row_stride(t: torch.Tensor) -> Optional[int]:
+    """Elements between consecutive ROWS of ``t`` seen as a [rows, C] matrix (last axis unit-strided, every leading
+    axis a whole multiple of the one after it), or None when ``t`` is not such a view.  A column block
+    ``buf[..., c0:c0+C]`` of a contiguous tensor qualifies (stride = buf's width), and so does ``buf[:B]``."""
+    if t.dim() == 0 or (t.shape[-1] > 1 and t.stride(-1) != 1):
+        return None
+    ld, span = None, None
+    for size, stride in zip(reversed(t.shape[:-1]), reversed(t.stride()[:-1])):
+        if size == 1:
+            continue
+        if ld is None:
+            ld, span = stride, stride * size
+        elif stride != span:
+            return None
+        else:
+            span = stride * size
+    return t.shape[-1] if ld is None else ld
+
+
+def linear_tc_into(x: torch.Tensor, wpacked: torch.Tensor, n: int, out: torch.Tensor, scale=None, shift=None,
+                   slope: float = 1.0, lo: float = 1.0, hi: float = 0.0, residual=None) -> torch.Tensor:
+    """out[..., :n] = epilogue(x W^T) where BOTH ``x`` and ``out`` may be row-strided views (``row_stride``): a column
+    block of a wider activation buffer, or a batch half of one.  The kernels take the row strides of the operand and of
+    the result (ldx / ldo of kdpc_linear_tc), so a layer reads from and writes into the concatenated tensors its
+    neighbours use - no torch.cat before or after.  Not a dispatcher op (it mutates ``out``): inference only."""
+    if x.dtype != torch.float32 or out.dtype != torch.float32:
+        raise TypeError("kdpc: linear_tc_into needs float32 tensors")
+    k = x.shape[-1]
+    ldx, ldo = row_stride(x), row_stride(out)
+    m = x.numel() // max(k, 1)
+    if ldx is None or ldo is None or out.shape[-1] != n or out.numel() != m * n or ldx < k or ldo < n:
+        raise ValueError("kdpc: linear_tc_into needs row-strided [..., K] / [..., N] views with the same number of rows")
+    if (ldx % 4) or (ldo % 4) or (x.data_ptr() % 16) or (out.data_ptr() % 16):
+        raise ValueError("kdpc: linear_tc_into needs 16-byte aligned rows")
+    for t, nm in ((scale, "scale"), (shift, "shift")):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != n or not t.is_contiguous()):
+            raise ValueError(f"kdpc: {nm} must be a contiguous float32 [{n}]")
+    if residual is not None and (residual.dtype != torch.float32 or not residual.is_contiguous() or residual.numel() != m * n
+                                 or ldo != n):
+        raise ValueError("kdpc: linear_tc_into takes a residual only with a contiguous output of the same shape")
     with _guard(x):
         nws = _lib.lib().kdpc_linear_tc_ws_bytes(m, n, k)
         ws = torch.empty((nws,), dtype=torch.uint8, device=x.device) if nws else None
         if m * n:
-            _call("kdpc_linear_tc", m, n, k, _p(x), k, _p(wpacked), _p(scale), _p(shift), float(slope), float(lo),
-                  float(hi), None, _p(ws), out.data_ptr() + 4 * col0, ntot, _stream())
+            _call("kdpc_linear_tc", m, n, k, _p(x), ldx, _p(wpacked), _p(scale), _p(shift), float(slope), float(lo),
+                  float(hi), _p(residual), _p(ws), _p(out), ldo, _stream())
+    return out
 
 
 def _linear_dw(dy: torch.Tensor, x: torch.Tensor, want_bias: bool) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -43,16 +43,19 @@ def _is_pointwise(conv) -> bool:
 
 
 def _linear_pm(conv: nn.Module, x: torch.Tensor, norm: Optional[nn.Module] = None, act: Optional[nn.Module] = None,
-               clamp=None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+               clamp=None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """A 1x1 nn.Conv1d / nn.Conv2d / nn.Linear applied along the LAST axis of a point-major tensor,
     followed by an optional BatchNorm (over all leading axes), activation, clamp and residual add.
     Inference: ONE fused tcgen05 kernel (functional.fused_linear).  When a gradient is needed or
-    the BatchNorm is in training mode: the same math from torch ops (autograd)."""
+    the BatchNorm is in training mode: the same math from torch ops (autograd).
+    ``out`` (inference only, see ``_concat_free``): a row-strided view the fused kernel writes into."""
     w = conv.weight
     bn = None if (norm is None or isinstance(norm, nn.Identity)) else norm
     slope = 1.0 if act is None else _slope(act)
     if KF.fused_linear_available(x, w, conv.bias, bn):
-        return KF.fused_linear(x, w, conv.bias, bn, slope, clamp, residual)
+        return KF.fused_linear(x, w, conv.bias, bn, slope, clamp, residual, out=out)
+    if out is not None:
+        raise RuntimeError("kdpc: an output view is only supported on the fused inference path")
     w2d = w.reshape(w.shape[0], -1)
     if KF.linear_tc_autograd_available(x, w2d):
         if bn is None and act is not None and 0.0 <= slope < 1.0:
@@ -88,12 +91,12 @@ class _ComposedConv(nn.Module):
         perm_in = (0, 2, 1) if x.dim() == 3 else (0, 3, 2, 1)
         return _linear_pm(conv, x.permute(*perm_in), None, act).permute(*perm_in)
 
-    def forward_pm(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_pm(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x [..., Cin] -> [..., Cout] (channels last)."""
         conv, norm, act = self.composed_module[0], self.composed_module[1], self.composed_module[2]
         if not _is_pointwise(conv):
             raise NotImplementedError("forward_pm needs a 1x1 convolution")
-        return _linear_pm(conv, x, norm, act)
+        return _linear_pm(conv, x, norm, act, out=out)
 
 
 class Conv1d(_ComposedConv):
@@ -369,8 +372,15 @@ class CrossLayerLight(nn.Module):
         b = self.cross_pm(pc2, pc1, t11_2, t22_1, self.pos1, self.mlp1, self.bn1)
         if self.mlp2 is False:
             return a, b
-        a = _linear_pm(self.cross_t1, a)
-        b = _linear_pm(self.cross_t2, b)
+        if a.shape == b.shape and KF.concat_free(a, b):
+            # inference: both directions into the halves of ONE [2B,N,C] tensor - the caller's cat([a, b], dim=0)
+            # (the next level's upsampling runs over both clouds at once) is then functional.joined(a, b), no copy
+            ab = a.new_empty((2 * a.shape[0],) + tuple(a.shape[1:-1]) + (self.cross_t1.out_channels,))
+            a = _linear_pm(self.cross_t1, a, out=ab[:a.shape[0]])
+            b = _linear_pm(self.cross_t2, b, out=ab[a.shape[0]:])
+        else:
+            a = _linear_pm(self.cross_t1, a)
+            b = _linear_pm(self.cross_t2, b)
         c = self.cross_pm(pc1, pc2, a, b, self.pos2, self.mlp2, self.bn2)
         return a, b, c
 
@@ -493,7 +503,9 @@ class SceneFlowEstimatorResidual(nn.Module):
         self.fc = nn.Conv1d(last, 3, 1)
 
     def forward_pm(self, xyz, feats, cost_volume, flow=None):
-        x = torch.cat([feats, cost_volume], dim=2)
+        """``feats``: one [B,N,C] tensor or a tuple of them (concatenated here together with the cost volume in ONE
+        copy instead of the caller's cat followed by this one: same tensor)."""
+        x = torch.cat([*(feats if isinstance(feats, (tuple, list)) else (feats,)), cost_volume], dim=2)
         for pointconv in self.pointconv_list:
             x = pointconv.forward_pm(xyz, x)
         for conv in self.mlp_convs:

@@ -237,6 +237,26 @@ def test_batched_model_equals_oracle_and_single_runs():
                torch.norm(o[0][0].permute(0, 2, 1) - d["flow"][1:].cpu(), dim=2).mean().item()) < 1e-4
 
 
+def test_concat_free_forward_is_bit_identical_to_the_concatenating_forward():
+    """The inference forward writes its 1x1 convolutions into column blocks / batch halves of shared buffers
+    (functional.concat_free); with the switch off it concatenates like the reference.  Every output must be equal."""
+    model, _ = load(PointConvBidirection(), 7)
+    d = make_pairs(2, 4096, seed=51, device=DEV)
+    outs = []
+    for flag in (True, False):
+        KF.CONCAT_FREE = flag
+        try:
+            KF.clear_caches()
+            with torch.no_grad():
+                outs.append(model(d["pos1"], d["pos2"], d["color1"], d["color2"]))
+        finally:
+            KF.CONCAT_FREE = True
+    KF.clear_caches()
+    for a, b in zip(outs[0], outs[1]):
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and torch.equal(x, y)
+
+
 def test_training_path_matches_inference_path_and_oracle_gradients():
     """Grad-enabled forward (differentiable primitives + deterministic scatter) equals the fused
     no-grad forward, and its gradients equal autograd through the CPU oracle."""

@@ -246,6 +246,41 @@ def test_wide_linear_blocks_written_in_place():
     assert torch.equal(y[..., :256], lo)
 
 
+@pytest.mark.parametrize("rows,k,n,ctot,c0,otot,o0", [
+    ((16, 8192), 32, 64, 64, 0, 64, 0),          # level0_2 reading f_l0 out of the level-0 concatenation buffer
+    ((16, 2048), 64, 128, 96, 0, 128, 0),        # level1_1 (row stride 96)
+    ((16, 256), 256, 512, 320, 0, 512, 0),       # level3_1: strided operand of a WIDE layer (column blocks)
+    ((16, 512), 128, 64, 128, 0, 192, 128),      # deconv3_2 writing the second column block
+    ((4, 300), 64, 32, 100, 36, 52, 20),         # ragged rows, both views offset (16-byte aligned)
+    ((2, 4096), 256, 256, 256, 0, 512, 256),     # small-M layer on the split-N plan, strided result
+    ((1, 64), 4144, 256, 4144, 0, 320, 0),       # split-K plan (workspace + reduce) into a strided result
+])
+def test_linear_reads_and_writes_column_blocks(rows, k, n, ctot, c0, otot, o0):
+    """fused_linear on row-strided views (operand = column block of a wider tensor, result = column block of another)
+    is bit-identical to the contiguous call, and leaves the rest of the destination untouched."""
+    g = torch.Generator().manual_seed(k + n + ctot)
+    big = torch.randn(*rows, ctot, generator=g).to(DEV)
+    lin = torch.nn.Linear(k, n).to(DEV)
+    xv = big[..., c0:c0 + k]
+    with torch.no_grad():
+        ref = KF.fused_linear(xv.contiguous(), lin.weight, lin.bias, None, 0.1)
+        dest = torch.full((*rows, otot), 7.0, device=DEV)
+        got = KF.fused_linear(xv, lin.weight, lin.bias, None, 0.1, out=dest[..., o0:o0 + n])
+        only_x = KF.fused_linear(xv, lin.weight, lin.bias, None, 0.1)
+    assert got.data_ptr() == dest[..., o0:o0 + n].data_ptr()
+    assert torch.equal(dest[..., o0:o0 + n], ref) and torch.equal(only_x, ref)
+    keep = torch.ones(otot, dtype=torch.bool)
+    keep[o0:o0 + n] = False
+    assert bool((dest[..., keep.to(DEV)] == 7.0).all())
+    # batch halves of one tensor: the second half starts mid-buffer
+    with torch.no_grad():
+        both = torch.empty(2 * rows[0], *rows[1:], n, device=DEV)
+        KF.fused_linear(xv, lin.weight, lin.bias, None, 0.1, out=both[rows[0]:])
+        KF.fused_linear(xv, lin.weight, lin.bias, None, 0.1, out=both[:rows[0]])
+    assert torch.equal(both[:rows[0]], ref) and torch.equal(both[rows[0]:], ref)
+    assert KF.joined(both[:rows[0]], both[rows[0]:]) is both
+
+
 @pytest.mark.parametrize("m,n,k", [(65536, 128, 128), (4096, 64, 2096), (1000, 32, 35), (128 * 3 + 5, 256, 256), (50, 16, 16),
                                    (8192, 128, 1072), (300, 200, 520), (131072, 32, 32), (65536, 32, 3), (32768, 64, 63),
                                    (16384, 64, 64), (6400, 48, 20), (64, 8, 3), (70001, 128, 3), (4099, 256, 3), (1000, 36, 2)])
