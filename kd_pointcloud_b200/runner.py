@@ -10,6 +10,7 @@ flow out, with the host->device copies and the device->host read inside.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -227,6 +228,8 @@ class PipelinedFlowRunner:
         dev = self.device
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self.sm_limit = max(n_sm // 2, n_sm - 2 * self.batch)
+        if os.environ.get("KDPC_SM_LIMIT"):                 # measurements only (tools/gpu_sweep_pipeline.sh)
+            self.sm_limit = max(1, min(n_sm, int(os.environ["KDPC_SM_LIMIT"])))
         for slot in (0, 1):
             self.load(sample, slot)
         L.kdpc_set_sm_limit(self.sm_limit)
