@@ -150,6 +150,14 @@ int kdpc_knn_sorted(int b, int s, int n, int k, int direct, const void *query_so
  * [B,S,K,C] directly (the reference returns a permuted view of [B,C,S,K]). */
 int kdpc_gather_rows(int b, int n, int m, int c, const float *f, const int *idx, float *out, kdpc_stream_t stream);
 
+/* torch.cat((a, b, ...), dim = channels) of point-major activations - SceneFlowEstimatorResidual.forward,
+ * pointconv_util.py:2242 (`torch.cat([feats, cost_volume], dim = 1)`) and the feature concatenations of
+ * models_bid_pointconv.py:150-190: out[r, :] = [src[0][r, :width[0]] | src[1][r, :width[1]] | ...] for r < rows.
+ * src / ld / width are HOST arrays of nsrc <= 4 entries (device pointers, row strides and widths in floats); a source may
+ * be a column block of a wider tensor.  Widths, strides % 4 == 0 and 16-byte aligned pointers, else KDPC_EUNSUPPORTED. */
+int kdpc_concat_rows(long long rows, int nsrc, const float *const *src, const int *ld, const int *width, float *out,
+                     int ldo, kdpc_stream_t stream);
+
 /* group / group_query, pointconv_util.py:135-182, fused: out[b,s,k,:] =
  * [cand_xyz[idx]-query_xyz[s] (3), feats[idx] (D)].  feats may be NULL (d = 0). */
 /* A/B switch for measurements and tests: 0 = always the shared-memory staged kernel (same results). */

@@ -101,6 +101,7 @@ _SIGNATURES = {
     "kdpc_knn_sorted": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "kdpc_gather_rows": [c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_group_concat": [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
+    "kdpc_concat_rows": [c_longlong, c_int, _P, _P, _P, _P, c_int, _P],
     "kdpc_weightnet": [c_longlong, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
     "kdpc_pointconv_agg": [c_longlong, c_int, c_int, c_int, _P, _P, _P, _P],
     "kdpc_pointconv_agg_grad": [c_longlong, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],

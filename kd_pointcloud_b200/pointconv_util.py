@@ -505,7 +505,12 @@ class SceneFlowEstimatorResidual(nn.Module):
     def forward_pm(self, xyz, feats, cost_volume, flow=None):
         """``feats``: one [B,N,C] tensor or a tuple of them (concatenated here together with the cost volume in ONE
         copy instead of the caller's cat followed by this one: same tensor)."""
-        x = torch.cat([*(feats if isinstance(feats, (tuple, list)) else (feats,)), cost_volume], dim=2)
+        parts = [*(feats if isinstance(feats, (tuple, list)) else (feats,)), cost_volume]
+        if KF.concat_free(*parts) and len(parts) <= 4 and all(
+                t.shape[-1] % 4 == 0 and t.data_ptr() % 16 == 0 and (KF.ops.row_stride(t) or 1) % 4 == 0 for t in parts):
+            x = KF.ops.concat_rows(parts)          # one vectorised copy, strided parts welcome (csrc/group.cu)
+        else:
+            x = torch.cat(parts, dim=2)
         for pointconv in self.pointconv_list:
             x = pointconv.forward_pm(xyz, x)
         for conv in self.mlp_convs:

@@ -439,3 +439,27 @@ def test_square_distance_is_differentiable_like_the_reference():
     (ref * w.double()).sum().backward()
     assert ((src.grad.double() - s2.grad).abs().max() / s2.grad.abs().max()).item() < 1e-4
     assert ((dst.grad.double() - d2.grad).abs().max() / d2.grad.abs().max()).item() < 1e-4
+
+
+def test_concat_rows_equals_torch_cat_for_contiguous_and_strided_parts():
+    """kdpc_concat_rows (the estimator's [features | upsampled features | cost volume] tensor): bit-identical to
+    torch.cat for contiguous parts, column blocks and batch halves of wider tensors, 1..4 parts, odd row counts."""
+    from kd_pointcloud_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    wide = torch.randn(6, 333, 96, generator=g).to(DEV)
+    a = wide[:3, :, :32]                      # batch half + column block (row stride 96)
+    b = torch.randn(3, 333, 64, generator=g).to(DEV)
+    c = wide[3:, :, 64:]                      # second half, last column block
+    d = torch.randn(3, 333, 4, generator=g).to(DEV)
+    for parts in ((a,), (a, b), (a, b, c), (a, b, c, d), (d, c, b, a)):
+        got = ops.concat_rows(parts)
+        assert got.is_contiguous() and torch.equal(got, torch.cat(parts, dim=2))
+    dest = torch.full((3, 333, 200), -1.0, device=DEV)
+    ops.concat_rows((a, b), out=dest[:, :, 100:196])
+    assert torch.equal(dest[:, :, 100:196], torch.cat((a, b), dim=2))
+    assert bool((dest[:, :, :100] == -1).all()) and bool((dest[:, :, 196:] == -1).all())
+    assert ops.concat_rows((torch.empty(0, 5, 8, device=DEV), torch.empty(0, 5, 4, device=DEV))).shape == (0, 5, 12)
+    with pytest.raises(ValueError):
+        ops.concat_rows((a, torch.randn(3, 333, 6, device=DEV)))           # width % 4 != 0
+    with pytest.raises(ValueError):
+        ops.concat_rows((a, b.permute(0, 2, 1)[:, :333, :64]))             # not row-strided
