@@ -81,7 +81,16 @@ struct PointConvProducer {
     // only reader of its rows' gathered data (no cross-warp hand-over of staging buffers), the two half-lanes of a row
     // read the same 16 bytes (one broadcast shared-memory word / one coalesced global request), and lane (row, h)
     // fetches piece h of its own row's neighbours - no index exchange.
-    static __device__ __forceinline__ int tile_row(int ptid) { return (ptid >> 5) * 16 + ((ptid & 31) >> 1); }
+    // Which of the warp's 16 rows a lane pair owns: a 16-byte shared-memory store is processed per QUARTER warp (8 lanes =
+    // 4 rows x 2 halves), and in the SWIZZLE_128B layout rows r and r ^ 1 put their unit pair at the same bank group
+    // ((u ^ (r & 7)) >> 1 is the same), so four CONSECUTIVE rows per quarter hit only 16 of the 32 banks twice each
+    // (ncu: l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st = 58 % of the kernel's store wavefronts, the L1 data
+    // pipe the busiest unit at 59 %).  Quarter q therefore owns rows 8 (q >> 1) + (q & 1) + {0, 2, 4, 6}: four different
+    // bank groups, one wavefront per quarter.
+    static __device__ __forceinline__ int tile_row(int ptid) {
+        const int i = (ptid & 31) >> 1, q = i >> 2;
+        return (ptid >> 5) * 16 + ((q >> 1) << 3) + ((i & 3) << 1) + (q & 1);
+    }
     __device__ __forceinline__ void begin_tile(long long tile, int ptid) {
         const int r = tile_row(ptid);
         half = ptid & 1;
