@@ -128,7 +128,15 @@ struct CostVolAsyncProducer {
     static constexpr int RSTEP = 32 * kIssuerWarps / 8;          // thread t serves rows (t >> 3) + RSTEP j
     static constexpr int JPP = CV_K / RSTEP;                     // consecutive j that belong to one point
     static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
-    static constexpr int ROW_PITCH = 272;                    // 256 B payload + 16 B: conflict-free 16-byte reads by row
+#ifndef KDPC_CV_SWIZZLE
+#define KDPC_CV_SWIZZLE 1
+#endif
+    // Raw staging rows.  KDPC_CV_SWIZZLE = 1 (default): 256-byte rows, the eight 16-byte pieces of each 128-byte half stored
+    // at piece ^ (row & 7) - every LDGSTS quarter warp writes ONE aligned 128-byte line, and the converters' 16-byte reads
+    // by row stay conflict-free.  0: the padded layout (256 B + 16 B) it replaces: its rows start 16 bytes off the
+    // 32-byte sectors on every other row and ncu counted 10.5 shared-memory wavefronts per warp-level LDGSTS against
+    // an ideal of 4 (L1 Wavefronts Shared Excessive = 62 %; the L1 data pipe is the cost volume's busiest unit).
+    static constexpr int ROW_PITCH = KDPC_CV_SWIZZLE ? 256 : 272;
     static constexpr int kRawBytes = (TILE_M + TILE_M / CV_K) * ROW_PITCH;     // 128 neighbour rows + 4 point rows
     static constexpr int RPT = TILE_M * 8 / kIssuers;        // neighbour rows per issuing thread (8 lanes per row)
     struct Args {
@@ -178,7 +186,8 @@ struct CostVolAsyncProducer {
         pt_off = pt * (unsigned)a.d;
     }
     __device__ __forceinline__ void prime(int tile, int ptid) {
-        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + (ptid & 7) * 16);
+        static_assert(RSTEP % 8 == 0, "the swizzle term (row & 7) must not depend on j");
+        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + ((KDPC_CV_SWIZZLE ? ((ptid & 7) ^ ((ptid >> 3) & 7)) : (ptid & 7)) << 4));
         load_rows(tile, ptid);
     }
 
@@ -224,7 +233,8 @@ struct CostVolAsyncProducer {
         for (int uu = 0; uu < 4; ++uu) {
             if (uu < nu) {
                 const int u = u0 + uu;
-                const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+                const int sw = KDPC_CV_SWIZZLE ? (r & 7) : 0;                          // pieces of a 128-byte half: piece ^ (row & 7)
+                const float4 g0 = rr[(2 * u) ^ sw], g1 = rr[(2 * u + 1) ^ sw];
                 const float4 q0 = pr[2 * u], q1 = pr[2 * u + 1];
                 float v[8] = {g0.x + q0.x, g0.y + q0.y, g0.z + q0.z, g0.w + q0.w,
                               g1.x + q1.x, g1.y + q1.y, g1.z + q1.z, g1.w + q1.w};
@@ -274,7 +284,7 @@ struct CostVolPairProducer {
     static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
     static constexpr int D = 32;
     static constexpr int ROWS = 2 * TILE_M, PTS = ROWS / CV_K;           // 256 neighbour rows = 8 points per iteration
-    static constexpr int ROW_PITCH = 144;                                // 128 B payload + 16 B: conflict-free 16-byte reads by row
+    static constexpr int ROW_PITCH = KDPC_CV_SWIZZLE ? 128 : 144;        // swizzled 128-byte rows (see CostVolAsyncProducer), or 128 B + 16 B padding
     static constexpr int kRawBytes = (ROWS + PTS) * ROW_PITCH;
     static constexpr int RPT = ROWS * 8 / kIssuers;                      // neighbour rows per issuing thread (8 lanes per row)
     static constexpr int RSTEP = kIssuers / 8;                           // thread t serves rows (t >> 3) + RSTEP j
@@ -305,7 +315,8 @@ struct CostVolPairProducer {
         pt_off = pt * (unsigned)D;
     }
     __device__ __forceinline__ void prime(int tile, int ptid) {
-        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + (ptid & 7) * 16);
+        static_assert(RSTEP % 8 == 0, "the swizzle term (row & 7) must not depend on j");
+        dst0 = (uint32_t)((ptid >> 3) * ROW_PITCH + ((KDPC_CV_SWIZZLE ? ((ptid & 7) ^ ((ptid >> 3) & 7)) : (ptid & 7)) << 4));
         last_pt = (unsigned)a.points - 1u;
         last_row = (unsigned)a.points * CV_K - 1u;
         load_rows(tile, ptid);
@@ -330,7 +341,8 @@ struct CostVolPairProducer {
         const float slope = a.slope;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float4 g0 = rr[2 * u], g1 = rr[2 * u + 1];
+            const int sw = KDPC_CV_SWIZZLE ? (r & 7) : 0;
+            const float4 g0 = rr[(2 * u) ^ sw], g1 = rr[(2 * u + 1) ^ sw];
             const float4 q0 = pr[2 * u], q1 = pr[2 * u + 1];
             float v[8] = {g0.x + q0.x, g0.y + q0.y, g0.z + q0.z, g0.w + q0.w,
                           g1.x + q1.x, g1.y + q1.y, g1.z + q1.z, g1.w + q1.w};
