@@ -281,6 +281,10 @@ struct CostVolPairProducer {
 #define KDPC_CV_PAIR_IW 8
 #endif
     static constexpr int kIssuerWarps = KDPC_CV_PAIR_IW, kEpilogueWarps = 8;
+#ifndef KDPC_CV_RELAXED
+#define KDPC_CV_RELAXED 1
+#endif
+    static constexpr bool kRelaxedWaits = KDPC_CV_RELAXED != 0;          // nanosleep back-off in the converters' / epilogue warps' waits (tc_gemm.cuh)
     static constexpr int kIssuers = 32 * kIssuerWarps, kLookahead = 2;
     static constexpr int D = 32;
     static constexpr int ROWS = 2 * TILE_M, PTS = ROWS / CV_K;           // 256 neighbour rows = 8 points per iteration

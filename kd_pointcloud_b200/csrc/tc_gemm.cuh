@@ -47,6 +47,23 @@ template <class P> struct issuer_warps<P, decltype((void)P::kIssuerWarps)> { sta
 // quarter + 4 and work on their own column range of the accumulator): for tiles whose epilogue, not the MMA, paces the pipeline.
 template <class P, class = void> struct epilogue_warps { static constexpr int value = 4; };
 template <class P> struct epilogue_warps<P, decltype((void)P::kEpilogueWarps)> { static constexpr int value = P::kEpilogueWarps; };
+// P::kRelaxedWaits = true: the converting warps' wait for the gathered rows and the epilogue warps' wait for a finished
+// accumulator back off with nanosleep between polls.  In the paired cost volume HALF of all executed instructions were
+// bare try_wait polls (ncu source page: 35.7 M + 29.6 M of 131 M, issue slots 73 % busy) - on the schedulers that also
+// have to issue the gathers those warps are waiting for.
+template <class P, class = void> struct relaxed_waits { static constexpr bool value = false; };
+template <class P> struct relaxed_waits<P, decltype((void)P::kRelaxedWaits)> { static constexpr bool value = P::kRelaxedWaits; };
+template <bool RELAXED, unsigned NS>
+__device__ __forceinline__ void mbar_wait_poll(uint64_t *bar, uint32_t parity) {
+    if constexpr (!RELAXED) {
+        mbar_wait(bar, parity);
+    } else {
+        for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+            __nanosleep(NS);
+            if (spins > (1u << 22)) __trap();
+        }
+    }
+}
 template <class Producer> constexpr int num_threads() {
     return (Producer::kWarps + issuer_warps<Producer>::value + (merged_issuer<Producer>::value ? 0 : 1) + epilogue_warps<Producer>::value) * 32;
 }
@@ -298,7 +315,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
                         tma_load_1d(b_base + (size_t)s * bbytes, g.wpacked + (size_t)(b_resident ? 0 : cu_chunk % g.wchunks) * bbytes, (uint32_t)bbytes, &full_b[s]);
                     }
                 }
-                mbar_wait(&raw_full[cu_slot], raw_ph);
+                mbar_wait_poll<relaxed_waits<Producer>::value, 32>(&raw_full[cu_slot], raw_ph);
                 stamp(i, 4);
                 unsigned char *a_hi = a_base + (size_t)s * A_STAGE_BYTES;
                 prod.convert(tl(cu_tile), cu_chunk, raw_base + (size_t)cu_slot * g.raw_bytes, a_hi, a_hi + A_PART_BYTES, ptid);
@@ -506,7 +523,7 @@ tc_gemm_kernel(const GemmShape g, const __grid_constant__ typename Producer::Arg
             const uint32_t acc = tcount & nacc_mask;
             const bool tre = g.trace != nullptr && blockIdx.x == 0 && warp == MW + 1 && lane == 0 && tcount < 200;
             if (tre) g.trace[tcount * 16 + 12] = clock64();
-            mbar_wait(&tmem_full[acc], (tcount >> g.nacc_log2) & 1);
+            mbar_wait_poll<relaxed_waits<Producer>::value, 64>(&tmem_full[acc], (tcount >> g.nacc_log2) & 1);
             if (tre) g.trace[tcount * 16 + 13] = clock64();
             fence_after_sync();
             const uint32_t t_acc = tmem_base + acc * (uint32_t)g.acc_stride + ((uint32_t)(quarter * 32) << 16);
