@@ -54,20 +54,42 @@ __device__ __forceinline__ void interp3_weights(const float *__restrict__ q, con
     w0 = r[0] / norm; w1 = r[1] / norm; w2 = r[2] / norm;
 }
 
-template <int VEC>
-__global__ void interp3_kernel(long long total, int n, int s, int cvec, const float *__restrict__ q_xyz,
-                               const float *__restrict__ c_xyz, const int *__restrict__ idx,
-                               const float *__restrict__ feat, float *__restrict__ out, float *__restrict__ w_out) {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const long long r = e / cvec;                         // r = b*n + i
-    const int cv = (int)(e - r * cvec);
-    const long long b = r / n;
-    const int *ip = idx + r * 3;
-    const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
-    float w0, w1, w2;
-    interp3_weights(q_xyz + r * 3, c_xyz + (size_t)b * s * 3, i0, i1, i2, w0, w1, w2);
-    if (w_out != nullptr && cv == 0) { w_out[r * 3 + 0] = w0; w_out[r * 3 + 1] = w1; w_out[r * 3 + 2] = w2; }
+// thread = one 16-byte (VEC = 4) or 4-byte (VEC = 1) piece of an output row; the cvec pieces of a point are consecutive
+// threads.  The indices and the three inverse-distance weights of a point (3 square roots, 6 divisions, 15 loads) are
+// computed ONCE per point and warp - by the lane that holds the point's first piece, or by lane 0 when the point began in
+// the previous warp - and handed to the point's other lanes by shuffle (every lane used to recompute them: 16 times per
+// point at C = 64, which made the kernel instruction-bound at 19 % of the copy peak).  IT: 32-bit index arithmetic
+// whenever the piece count allows (two 64-bit divisions per thread otherwise).  Same values, bit for bit.
+template <int VEC, typename IT>
+__global__ void __launch_bounds__(256)
+interp3_kernel(IT total, int n, int s, int cvec, const float *__restrict__ q_xyz, const float *__restrict__ c_xyz,
+               const int *__restrict__ idx, const float *__restrict__ feat, float *__restrict__ out,
+               float *__restrict__ w_out) {
+    IT e = (IT)blockIdx.x * (IT)256 + (IT)threadIdx.x;
+    const bool live = e < total;
+    if (!live) e = total - 1;                             // the lane stays for the warp-wide exchange; it stores nothing
+    const IT r = e / (IT)cvec;                            // r = b*n + i
+    const int cv = (int)(e - r * (IT)cvec);
+    const IT b = r / (IT)n;
+    const int lane = threadIdx.x & 31;
+    const int leader = max(lane - cv, 0);                 // lane of this warp that computes this point's weights
+    int i0 = 0, i1 = 0, i2 = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (cv == 0 || lane == 0) {
+        const int *ip = idx + (size_t)r * 3;
+        i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+        interp3_weights(q_xyz + (size_t)r * 3, c_xyz + (size_t)b * s * 3, i0, i1, i2, w0, w1, w2);
+        if (w_out != nullptr && cv == 0 && live) {
+            w_out[(size_t)r * 3 + 0] = w0; w_out[(size_t)r * 3 + 1] = w1; w_out[(size_t)r * 3 + 2] = w2;
+        }
+    }
+    i0 = __shfl_sync(0xffffffffu, i0, leader);
+    i1 = __shfl_sync(0xffffffffu, i1, leader);
+    i2 = __shfl_sync(0xffffffffu, i2, leader);
+    w0 = __shfl_sync(0xffffffffu, w0, leader);
+    w1 = __shfl_sync(0xffffffffu, w1, leader);
+    w2 = __shfl_sync(0xffffffffu, w2, leader);
+    if (!live) return;
     const size_t fb = (size_t)b * s * cvec;
     if (VEC == 4) {
         const float4 *f4 = reinterpret_cast<const float4 *>(feat);
@@ -106,12 +128,16 @@ KDPC_API int kdpc_interp3(int b, int n, int s, int c, const float *q_xyz, const 
     KDPC_CHECK_ARGS(q_xyz && c_xyz && idx && feat && out && b > 0 && n > 0 && s > 0 && c > 0);
     cudaStream_t st = to_stream(stream);
     const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
-    if (vec) {
-        const long long total = (long long)b * n * (c / 4);
-        interp3_kernel<4><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, s, c / 4, q_xyz, c_xyz, idx, feat, out, w_out);
+    const int cvec = vec ? c / 4 : c;
+    const long long total = (long long)b * n * cvec;
+    const unsigned grid = (unsigned)div_up_ll(total, 256);
+    if (total < (1ll << 31)) {                               // 32-bit index arithmetic (every shape of the model)
+        if (vec) interp3_kernel<4, unsigned><<<grid, 256, 0, st>>>((unsigned)total, n, s, cvec, q_xyz, c_xyz, idx, feat, out, w_out);
+        else interp3_kernel<1, unsigned><<<grid, 256, 0, st>>>((unsigned)total, n, s, cvec, q_xyz, c_xyz, idx, feat, out, w_out);
     } else {
-        const long long total = (long long)b * n * c;
-        interp3_kernel<1><<<(unsigned)div_up_ll(total, 256), 256, 0, st>>>(total, n, s, c, q_xyz, c_xyz, idx, feat, out, w_out);
+        if (div_up_ll(total, 256) >= (1ll << 31)) return KDPC_EUNSUPPORTED;
+        if (vec) interp3_kernel<4, long long><<<grid, 256, 0, st>>>(total, n, s, cvec, q_xyz, c_xyz, idx, feat, out, w_out);
+        else interp3_kernel<1, long long><<<grid, 256, 0, st>>>(total, n, s, cvec, q_xyz, c_xyz, idx, feat, out, w_out);
     }
     KDPC_RETURN_LAST();
 }
